@@ -1,0 +1,428 @@
+"""numpy front-end for the CPU oracle (oracle/mnr_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (minarrow_b200/) never does.
+
+Function names and argument order follow the reference's leaf API
+(src/kernels/arithmetic/dispatch.rs:74-79,147-152,221-226; src/kernels/bitmask/dispatch.rs:96-295):
+slices in, `(data, mask_bytes | None)` out, `KernelError` for the reference's `Err(KernelError::..)`
+and for its panics (dense integer division by zero).
+A bitmask is `(bytes: np.ndarray[uint8], len_bits: int)`, Arrow layout (LSB first, 1 = valid).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmnr_oracle.so")
+
+ADD, SUB, MUL, DIV, REM, POW, FLOORDIV = range(7)
+OPS = {"add": ADD, "subtract": SUB, "multiply": MUL, "divide": DIV, "remainder": REM, "power": POW,
+       "floordiv": FLOORDIV}
+AND, OR, XOR = range(3)
+
+
+class KernelError(Exception):
+    def __init__(self, kind: str, msg: str = ""):
+        super().__init__(f"{kind}: {msg}")
+        self.kind = kind
+
+
+class Bits(NamedTuple):
+    """Arrow validity / boolean bitmask: ceil(len/8) bytes, LSB first, slack bits zero."""
+    bits: np.ndarray
+    len: int
+
+    def to_bools(self) -> np.ndarray:
+        return np.unpackbits(self.bits, bitorder="little")[: self.len].astype(bool)
+
+    @staticmethod
+    def from_bools(b) -> "Bits":
+        b = np.asarray(b, dtype=bool)
+        return Bits(np.packbits(b, bitorder="little"), int(b.size))
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "mnr_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_bits_count_ones.restype = C.c_uint64
+        _lib.orc_bits_null_count.restype = C.c_uint64
+        _lib.orc_popcount_mask.restype = C.c_uint64
+        _lib.orc_simd_sum_i64.restype = C.c_int64
+        _lib.orc_hotloop_sum_i64.restype = C.c_int64
+        _lib.orc_rayon_simd_sum_i64.restype = C.c_int64
+        _lib.orc_simd_sum_f64.restype = C.c_double
+        _lib.orc_hotloop_sum_f64.restype = C.c_double
+        _lib.orc_rayon_simd_sum_f64.restype = C.c_double
+    return _lib
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _sz(n) -> C.c_size_t:
+    return C.c_size_t(int(n))
+
+
+_NAMES = {np.dtype(np.int8): "i8", np.dtype(np.uint8): "u8", np.dtype(np.int16): "i16",
+          np.dtype(np.uint16): "u16", np.dtype(np.int32): "i32", np.dtype(np.uint32): "u32",
+          np.dtype(np.int64): "i64", np.dtype(np.uint64): "u64", np.dtype(np.float32): "f32",
+          np.dtype(np.float64): "f64"}
+
+
+def _mask_bytes(mask, n: int) -> Optional[np.ndarray]:
+    if mask is None:
+        return None
+    bits = mask.bits if isinstance(mask, Bits) else np.asarray(mask, dtype=np.uint8)
+    need = (n + 7) // 8
+    if bits.size < need:
+        raise KernelError("InvalidArguments", f"mask has {bits.size} bytes, need {need}")
+    return np.ascontiguousarray(bits)
+
+
+def _check(rc: int):
+    if rc == -2:
+        raise KernelError("LengthMismatch", "apply numeric: length mismatch")
+    if rc == -10:
+        raise KernelError("DivideByZero", "dense integer kernel: division by zero (reference panics)")
+    if rc != 0:
+        raise KernelError("Unknown", str(rc))
+
+
+def apply_int(lhs, rhs, op: int, mask=None):
+    """apply_int_{i32,u32,i64,u64,...} — src/kernels/arithmetic/dispatch.rs:65-133."""
+    lhs = np.ascontiguousarray(lhs)
+    rhs = np.ascontiguousarray(rhs, dtype=lhs.dtype)
+    name = _NAMES[lhs.dtype]
+    n = lhs.size
+    m = _mask_bytes(mask, n)
+    out = np.empty(n, dtype=lhs.dtype)
+    om = np.zeros((n + 7) // 8, dtype=np.uint8) if m is not None else None
+    rc = getattr(lib(), f"orc_apply_int_{name}")(_p(lhs), _sz(n), _p(rhs), _sz(rhs.size), C.c_int(op),
+                                                  _p(m), _p(out), _p(om))
+    _check(rc)
+    return out, (Bits(om, n) if om is not None else None)
+
+
+def apply_float(lhs, rhs, op: int, mask=None):
+    """apply_float_{f32,f64} — src/kernels/arithmetic/dispatch.rs:138-206."""
+    lhs = np.ascontiguousarray(lhs)
+    rhs = np.ascontiguousarray(rhs, dtype=lhs.dtype)
+    name = _NAMES[lhs.dtype]
+    n = lhs.size
+    m = _mask_bytes(mask, n)
+    out = np.empty(n, dtype=lhs.dtype)
+    om = np.zeros((n + 7) // 8, dtype=np.uint8) if m is not None else None
+    rc = getattr(lib(), f"orc_apply_float_{name}")(_p(lhs), _sz(n), _p(rhs), _sz(rhs.size), C.c_int(op),
+                                                    _p(m), _p(out), _p(om))
+    _check(rc)
+    return out, (Bits(om, n) if om is not None else None)
+
+
+def apply(lhs, rhs, op: int, mask=None):
+    lhs = np.asarray(lhs)
+    return apply_float(lhs, rhs, op, mask) if lhs.dtype.kind == "f" else apply_int(lhs, rhs, op, mask)
+
+
+def apply_fma(lhs, rhs, acc, mask=None, fused: bool = True):
+    """apply_fma_{f32,f64} — src/kernels/arithmetic/dispatch.rs:211-290."""
+    lhs = np.ascontiguousarray(lhs)
+    rhs = np.ascontiguousarray(rhs, dtype=lhs.dtype)
+    acc = np.ascontiguousarray(acc, dtype=lhs.dtype)
+    name = _NAMES[lhs.dtype]
+    n = lhs.size
+    m = _mask_bytes(mask, n)
+    out = np.empty(n, dtype=lhs.dtype)
+    om = np.zeros((n + 7) // 8, dtype=np.uint8) if m is not None else None
+    rc = getattr(lib(), f"orc_apply_fma_{name}")(_p(lhs), _sz(n), _p(rhs), _sz(rhs.size), _p(acc),
+                                                  _sz(acc.size), _p(m), C.c_int(int(fused)), _p(out), _p(om))
+    _check(rc)
+    return out, (Bits(om, n) if om is not None else None)
+
+
+# ---- scalar broadcast / promotion (routing layer) ---------------------------------------------
+
+def broadcast_length_1(value, length: int, dtype) -> np.ndarray:
+    """broadcast_length_1_array — src/kernels/routing/broadcast.rs:25-47 (materialises `len` copies)."""
+    return np.full(length, value, dtype=dtype)
+
+
+def resolve_binary_arithmetic(op: int, lhs, rhs, null_mask=None):
+    """resolve_binary_arithmetic — src/kernels/routing/arithmetic.rs:214-406.
+
+    Length-1 broadcast (routing/broadcast.rs:87-112), same-dtype dispatch, and the two mixed pairs
+    (i32,f64)->f64 and (i32,f32)->f32 via `as` casts (:244-269,342-373).  The optional mask is the one
+    pre-merged mask of the leaf API, indexed from bit 0."""
+    lhs = np.asarray(lhs)
+    rhs = np.asarray(rhs)
+    if lhs.size != rhs.size:
+        if lhs.size == 1:
+            lhs = broadcast_length_1(lhs.reshape(-1)[0], rhs.size, lhs.dtype)
+        elif rhs.size == 1:
+            rhs = broadcast_length_1(rhs.reshape(-1)[0], lhs.size, rhs.dtype)
+        else:
+            raise KernelError("LengthMismatch", f"cannot broadcast arrays of length {lhs.size} and {rhs.size}")
+    lt, rt = lhs.dtype, rhs.dtype
+    if lt == rt and lt in (np.int32, np.int64, np.uint32, np.uint64, np.float32, np.float64):
+        return apply(lhs, rhs, op, null_mask)
+    pair = {lt, rt}
+    if pair == {np.dtype(np.int32), np.dtype(np.float64)}:
+        return apply_float(lhs.astype(np.float64), rhs.astype(np.float64), op, null_mask)
+    if pair == {np.dtype(np.int32), np.dtype(np.float32)}:
+        return apply_float(lhs.astype(np.float32), rhs.astype(np.float32), op, null_mask)
+    raise KernelError("UnsupportedType", "Unsupported array type combination for arithmetic operations")
+
+
+# ---- bitmask kernels ----------------------------------------------------------------------------
+
+def _win(m):
+    """BitmaskVT = (&Bitmask, offset, len) — src/aliases.rs."""
+    mask, off, ln = m
+    return np.ascontiguousarray(mask.bits), int(mask.len), int(off), int(ln)
+
+
+def new_set_all(length: int, value: bool) -> Bits:
+    out = np.zeros((length + 7) // 8, dtype=np.uint8)
+    lib().orc_bits_new_set_all(_p(out), _sz(length), C.c_int(int(value)))
+    return Bits(out, length)
+
+
+def bitmask_binop(lhs, rhs, op: int) -> Bits:
+    """bitmask_binop — src/kernels/bitmask/dispatch.rs:47-56 -> simd.rs:95-139."""
+    lb, _, lo, ln = _win(lhs)
+    rb, _, ro, _ = _win(rhs)
+    out = np.zeros((ln + 7) // 8, dtype=np.uint8)
+    lib().orc_bitmask_binop(_p(lb), _sz(lo), _p(rb), _sz(ro), _sz(ln), C.c_int(op), _p(out))
+    return Bits(out, ln)
+
+
+def and_masks(lhs, rhs) -> Bits:
+    return bitmask_binop(lhs, rhs, AND)
+
+
+def or_masks(lhs, rhs) -> Bits:
+    return bitmask_binop(lhs, rhs, OR)
+
+
+def xor_masks(lhs, rhs) -> Bits:
+    return bitmask_binop(lhs, rhs, XOR)
+
+
+def not_mask(src) -> Bits:
+    """not_mask — bitmask/dispatch.rs:135-144 -> simd.rs:169-203."""
+    b, _, off, ln = _win(src)
+    out = np.zeros((ln + 7) // 8, dtype=np.uint8)
+    lib().orc_bitmask_not(_p(b), _sz(off), _sz(ln), _p(out))
+    return Bits(out, ln)
+
+
+def popcount_mask(m) -> int:
+    """popcount_mask — bitmask/dispatch.rs:258-267 -> simd.rs:596-645."""
+    b, mlen, off, ln = _win(m)
+    return int(lib().orc_popcount_mask(_p(b), _sz(mlen), _sz(off), _sz(ln)))
+
+
+def count_ones(mask: Bits) -> int:
+    """Bitmask::count_ones — src/structs/bitmask.rs:393-406."""
+    return int(lib().orc_bits_count_ones(_p(np.ascontiguousarray(mask.bits)), _sz(mask.len)))
+
+
+def null_count(mask: Bits) -> int:
+    return mask.len - count_ones(mask)
+
+
+def all_true_mask(mask: Bits) -> bool:
+    return bool(lib().orc_all_true_mask(_p(np.ascontiguousarray(mask.bits)), _sz(mask.len)))
+
+
+def all_false_mask(mask: Bits) -> bool:
+    return bool(lib().orc_all_false_mask(_p(np.ascontiguousarray(mask.bits)), _sz(mask.len)))
+
+
+def _two(a, b):
+    ab, al, ao, ln = _win(a)
+    bb, bl, bo, _ = _win(b)
+    return ab, al, ao, bb, bl, bo, ln
+
+
+def eq_mask(a, b) -> Bits:
+    ab, al, ao, bb, bl, bo, ln = _two(a, b)
+    out = np.zeros((ln + 7) // 8, dtype=np.uint8)
+    if lib().orc_eq_mask(_p(ab), _sz(al), _sz(ao), _p(bb), _sz(bl), _sz(bo), _sz(ln), _p(out)):
+        raise KernelError("Panic", "eq_bits_mask: offsets must be 64-bit aligned")
+    return Bits(out, ln)
+
+
+def ne_mask(a, b) -> Bits:
+    ab, al, ao, bb, bl, bo, ln = _two(a, b)
+    out = np.zeros((ln + 7) // 8, dtype=np.uint8)
+    if lib().orc_ne_mask(_p(ab), _sz(al), _sz(ao), _p(bb), _sz(bl), _sz(bo), _sz(ln), _p(out)):
+        raise KernelError("Panic", "eq_bits_mask: offsets must be 64-bit aligned")
+    return Bits(out, ln)
+
+
+def all_eq(a, b) -> bool:
+    ab, al, ao, bb, bl, bo, ln = _two(a, b)
+    return bool(lib().orc_all_eq_mask(_p(ab), _sz(al), _sz(ao), _p(bb), _sz(bl), _sz(bo), _sz(ln)))
+
+
+def all_ne(a, b) -> bool:
+    ab, al, ao, bb, bl, bo, ln = _two(a, b)
+    return bool(lib().orc_all_ne_mask(_p(ab), _sz(al), _sz(ao), _p(bb), _sz(bl), _sz(bo), _sz(ln)))
+
+
+def in_mask(lhs, rhs) -> Bits:
+    lb, _, lo, ln = _win(lhs)
+    rb, rl, ro, _ = _win(rhs)
+    out = np.zeros((ln + 7) // 8, dtype=np.uint8)
+    lib().orc_in_mask(_p(lb), _sz(lo), _p(rb), _sz(rl), _sz(ro), _sz(ln), _p(out))
+    return Bits(out, ln)
+
+
+def not_in_mask(lhs, rhs) -> Bits:
+    lb, _, lo, ln = _win(lhs)
+    rb, rl, ro, _ = _win(rhs)
+    out = np.zeros((ln + 7) // 8, dtype=np.uint8)
+    lib().orc_not_in_mask(_p(lb), _sz(lo), _p(rb), _sz(rl), _sz(ro), _sz(ln), _p(out))
+    return Bits(out, ln)
+
+
+def merge_bitmasks_to_new(lhs: Optional[Bits], rhs: Optional[Bits], length: int) -> Optional[Bits]:
+    """merge_bitmasks_to_new (per-row AND) — src/kernels/bitmask/mod.rs:171-197."""
+    if lhs is None and rhs is None:
+        return None
+    out = np.zeros((length + 7) // 8, dtype=np.uint8)
+    lib().orc_merge_bitmasks_to_new(_p(None if lhs is None else np.ascontiguousarray(lhs.bits)),
+                                    _p(None if rhs is None else np.ascontiguousarray(rhs.bits)),
+                                    _sz(length), _p(out))
+    return Bits(out, length)
+
+
+def union(a: Bits, b: Bits) -> Bits:
+    """Bitmask::union (bitwise OR) — src/structs/bitmask.rs:661-669."""
+    assert a.len == b.len, "Bitmask::union length mismatch"
+    out = np.zeros((a.len + 7) // 8, dtype=np.uint8)
+    lib().orc_bits_union(_p(np.ascontiguousarray(a.bits)), _p(np.ascontiguousarray(b.bits)), _sz(a.len), _p(out))
+    return Bits(out, a.len)
+
+
+def intersect(a: Bits, b: Bits) -> Bits:
+    assert a.len == b.len
+    out = np.zeros((a.len + 7) // 8, dtype=np.uint8)
+    lib().orc_bits_intersect(_p(np.ascontiguousarray(a.bits)), _p(np.ascontiguousarray(b.bits)), _sz(a.len), _p(out))
+    return Bits(out, a.len)
+
+
+def invert(a: Bits) -> Bits:
+    out = np.zeros((a.len + 7) // 8, dtype=np.uint8)
+    lib().orc_bits_invert(_p(np.ascontiguousarray(a.bits)), _sz(a.len), _p(out))
+    return Bits(out, a.len)
+
+
+def union_opt(a: Optional[Bits], b: Optional[Bits]) -> Optional[Bits]:
+    """Bitmask::union_opt — src/structs/bitmask.rs:651-657."""
+    if a is None and b is None:
+        return None
+    if a is None:
+        return b
+    if b is None:
+        return a
+    return union(a, b)
+
+
+# ---- sums (bench-defined) and null-aware aggregates -----------------------------------------------
+
+def simd_sum_i64(data, lanes: int = 4) -> int:
+    d = np.ascontiguousarray(data, dtype=np.int64)
+    return int(lib().orc_simd_sum_i64(_p(d), _sz(d.size), C.c_int(lanes)))
+
+
+def simd_sum_f64(data, lanes: int = 4) -> float:
+    d = np.ascontiguousarray(data, dtype=np.float64)
+    return float(lib().orc_simd_sum_f64(_p(d), _sz(d.size), C.c_int(lanes)))
+
+
+def hotloop_sum_i64(data, lanes: int = 4) -> int:
+    d = np.ascontiguousarray(data, dtype=np.int64)
+    return int(lib().orc_hotloop_sum_i64(_p(d), _sz(d.size), C.c_int(lanes)))
+
+
+def hotloop_sum_f64(data, lanes: int = 4) -> float:
+    d = np.ascontiguousarray(data, dtype=np.float64)
+    return float(lib().orc_hotloop_sum_f64(_p(d), _sz(d.size), C.c_int(lanes)))
+
+
+def rayon_simd_sum_i64(data, lanes: int = 4, threads: int = 1) -> int:
+    d = np.ascontiguousarray(data, dtype=np.int64)
+    return int(lib().orc_rayon_simd_sum_i64(_p(d), _sz(d.size), C.c_int(lanes), C.c_int(threads)))
+
+
+def rayon_simd_sum_f64(data, lanes: int = 4, threads: int = 1) -> float:
+    d = np.ascontiguousarray(data, dtype=np.float64)
+    partials = np.zeros((d.size + (1 << 20) - 1) >> 20, dtype=np.float64)
+    return float(lib().orc_rayon_simd_sum_f64(_p(d), _sz(d.size), C.c_int(lanes), C.c_int(threads), _p(partials)))
+
+
+class _AggI(C.Structure):
+    _fields_ = [("sum", C.c_int64), ("min", C.c_int64), ("max", C.c_int64), ("count", C.c_uint64)]
+
+
+class _AggU(C.Structure):
+    _fields_ = [("sum", C.c_uint64), ("min", C.c_uint64), ("max", C.c_uint64), ("count", C.c_uint64)]
+
+
+class _AggF(C.Structure):
+    _fields_ = [("sum", C.c_double), ("min", C.c_double), ("max", C.c_double), ("count", C.c_uint64)]
+
+
+def stats(data, validity: Optional[Bits] = None) -> dict:
+    """Null-aware {sum, min, max, count, mean}; definition in DESIGN.md (reference-unpinned)."""
+    d = np.ascontiguousarray(data)
+    name = _NAMES[d.dtype]
+    agg = {"i": _AggI, "u": _AggU, "f": _AggF}[d.dtype.kind]()
+    v = None if validity is None else _mask_bytes(validity, d.size)
+    getattr(lib(), f"orc_stats_{name}")(_p(d), _sz(d.size), _p(v), C.byref(agg))
+    cnt = int(agg.count)
+    out = {"sum": agg.sum, "min": agg.min, "max": agg.max, "count": cnt}
+    out["mean"] = (float(agg.sum) / cnt) if cnt else float("nan")
+    return out
+
+
+def par_masked_sum_i64(data, validity: Optional[Bits], threads: int = 1):
+    d = np.ascontiguousarray(data, dtype=np.int64)
+    v = None if validity is None else _mask_bytes(validity, d.size)
+    s, c = C.c_int64(0), C.c_uint64(0)
+    lib().orc_par_masked_sum_i64(_p(d), _sz(d.size), _p(v), C.c_int(threads), C.byref(s), C.byref(c))
+    return int(s.value), int(c.value)
+
+
+def par_apply_float_f64(lhs, rhs, op: int, mask: Optional[Bits], threads: int, out=None, out_mask=None):
+    lhs = np.ascontiguousarray(lhs, dtype=np.float64)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    n = lhs.size
+    m = None if mask is None else _mask_bytes(mask, n)
+    out = np.empty(n, dtype=np.float64) if out is None else out
+    om = (np.zeros((n + 7) // 8, dtype=np.uint8) if out_mask is None else out_mask) if m is not None else None
+    lib().orc_par_apply_float_f64(_p(lhs), _p(rhs), _sz(n), C.c_int(op), _p(m), C.c_int(threads), _p(out), _p(om))
+    return out, (Bits(om, n) if om is not None else None)
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())

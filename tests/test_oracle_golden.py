@@ -1,0 +1,245 @@
+"""Pins the CPU oracle against the reference's own known-answer tests (transcribed, file:line in each
+case) and against independent second opinions (numpy, pyarrow.compute, math.fsum)."""
+import math
+
+import numpy as np
+import pytest
+
+import kat_runner
+from backends import OracleBackend
+from oracle import oracle as orc
+
+CASES = kat_runner.load_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[kat_runner.case_id(c) for c in CASES])
+def test_reference_kat(case):
+    assert kat_runner.run_case(case, OracleBackend()) in ("ok", "skipped")
+
+
+def test_every_kind_is_exercised():
+    kinds = {c["kind"] for c in CASES}
+    assert {"apply_int", "apply_float", "apply_fma", "merge_and", "bits_binop", "bits_not", "bits_popcount",
+            "route", "super_route", "sum_arange"} <= kinds
+
+
+# ---- independent cross-checks --------------------------------------------------------------------------
+
+INT_DTYPES = [np.int32, np.uint32, np.int64, np.uint64]
+
+
+def _rand_int(rng, dt, n, small=False):
+    info = np.iinfo(dt)
+    if small:
+        return rng.integers(max(info.min, -50), min(info.max, 50), n, dtype=dt, endpoint=True)
+    a = rng.integers(info.min, info.max, n, dtype=dt, endpoint=True)
+    # sprinkle edge values
+    edges = np.array([info.min, info.max, 0, 1, info.max - 1] + ([-1] if info.min < 0 else []), dtype=dt)
+    idx = rng.integers(0, n, 64)
+    a[idx] = edges[rng.integers(0, len(edges), 64)]
+    return a
+
+
+@pytest.mark.parametrize("dt", INT_DTYPES)
+def test_int_wrapping_ops_match_numpy(dt):
+    rng = np.random.default_rng(1)
+    a, b = _rand_int(rng, dt, 5000), _rand_int(rng, dt, 5000)
+    with np.errstate(over="ignore"):
+        for op, f in ((orc.ADD, np.add), (orc.SUB, np.subtract), (orc.MUL, np.multiply)):
+            got, m = orc.apply_int(a, b, op)
+            assert m is None and np.array_equal(got, f(a, b))
+
+
+@pytest.mark.parametrize("dt", INT_DTYPES)
+def test_int_div_rem_floordiv_semantics(dt):
+    rng = np.random.default_rng(2)
+    n = 4000
+    a, b = _rand_int(rng, dt, n), _rand_int(rng, dt, n, small=True)
+    mask = rng.random(n) < 0.9
+    bits = orc.Bits.from_bools(mask)
+    A, B = a.astype(object), b.astype(object)
+    info = np.iinfo(dt)
+
+    def wrap(v):
+        v &= (1 << info.bits) - 1
+        return v - (1 << info.bits) if (info.min < 0 and v >= (1 << (info.bits - 1))) else v
+
+    def trunc_div(x, y):
+        q = abs(x) // abs(y)
+        return q if (x < 0) == (y < 0) else -q
+
+    for op in (orc.DIV, orc.REM, orc.FLOORDIV):
+        got, m = orc.apply_int(a, b, op, bits)
+        valid = m.to_bools()
+        for i in range(n):
+            if not mask[i] or B[i] == 0:
+                assert got[i] == 0 and not valid[i]
+                continue
+            q = trunc_div(A[i], B[i])
+            r = A[i] - q * B[i]
+            exp = {orc.DIV: q, orc.REM: r, orc.FLOORDIV: A[i] // B[i]}[op]
+            assert int(got[i]) == wrap(exp) and valid[i], (op, A[i], B[i], got[i], exp)
+
+
+def test_int_min_over_minus_one_wraps():
+    # ASSUMPTION documented in DESIGN.md (core::simd guard): MIN / -1 = MIN, MIN % -1 = 0.
+    for dt in (np.int32, np.int64):
+        mn = np.iinfo(dt).min
+        a, b = np.array([mn], dtype=dt), np.array([-1], dtype=dt)
+        assert orc.apply_int(a, b, orc.DIV)[0][0] == mn
+        assert orc.apply_int(a, b, orc.REM)[0][0] == 0
+        assert orc.apply_int(a, b, orc.FLOORDIV)[0][0] == mn
+
+
+@pytest.mark.parametrize("dt", INT_DTYPES)
+def test_int_power_is_wrapping_repeated_multiply(dt):
+    rng = np.random.default_rng(3)
+    a = _rand_int(rng, dt, 300)
+    e = rng.integers(0, 70, 300).astype(dt)
+    got, _ = orc.apply_int(a, e, orc.POW)
+    bits = np.iinfo(dt).bits
+    for x, k, g in zip(a.astype(object), e.astype(object), got.astype(object)):
+        assert (g - pow(x, k)) % (1 << bits) == 0
+    if np.iinfo(dt).min < 0:  # negative exponent -> to_u32() is None -> 0 -> 1   (std.rs:67)
+        got, _ = orc.apply_int(np.array([7, -3], dtype=dt), np.array([-1, -5], dtype=dt), orc.POW)
+        assert list(got) == [1, 1]
+    if bits == 64:  # exponent above u32::MAX -> 0 -> 1
+        got, _ = orc.apply_int(np.array([7], dtype=dt), np.array([1 << 33], dtype=dt), orc.POW)
+        assert list(got) == [1]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_float_ops_match_numpy_ieee(dt):
+    rng = np.random.default_rng(4)
+    n = 20000
+    a, b = rng.standard_normal(n).astype(dt), rng.standard_normal(n).astype(dt)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, np.finfo(dt).tiny / 4, np.finfo(dt).max], dtype=dt)
+    a[rng.integers(0, n, 200)] = special[rng.integers(0, len(special), 200)]
+    b[rng.integers(0, n, 200)] = special[rng.integers(0, len(special), 200)]
+    with np.errstate(all="ignore"):
+        for op, f in ((orc.ADD, np.add), (orc.SUB, np.subtract), (orc.MUL, np.multiply), (orc.DIV, np.divide),
+                      (orc.REM, np.fmod)):
+            got, _ = orc.apply_float(a, b, op)
+            exp = f(a, b)
+            assert np.array_equal(got.view(np.uint32 if dt == np.float32 else np.uint64)[~np.isnan(exp)],
+                                  exp.view(np.uint32 if dt == np.float32 else np.uint64)[~np.isnan(exp)]), op
+            assert np.array_equal(np.isnan(got), np.isnan(exp))
+        got, _ = orc.apply_float(a, b, orc.FLOORDIV)
+        exp = np.floor(a / b)
+        assert np.array_equal(got[~np.isnan(exp)], exp[~np.isnan(exp)])
+
+
+def test_float_masked_zeroes_nulls_and_keeps_nan_valid():
+    a = np.array([1.0, np.nan, 3.0, 4.0, 5.0])
+    b = np.array([0.0, 1.0, 1.0, 0.0, 2.0])
+    m = orc.Bits.from_bools([True, True, False, True, True])
+    got, om = orc.apply_float(a, b, orc.DIV, m)
+    assert np.isinf(got[0]) and np.isnan(got[1]) and got[2] == 0.0 and not np.signbit(got[2])
+    assert list(om.to_bools()) == [True, True, False, True, True]
+
+
+def test_fma_is_single_rounding():
+    a, b, c = np.array([1.0 + 2.0 ** -30]), np.array([1.0 - 2.0 ** -30]), np.array([-1.0])
+    fused, _ = orc.apply_fma(a, b, c)
+    unfused, _ = orc.apply_fma(a, b, c, fused=False)
+    assert fused[0] == -(2.0 ** -60) and unfused[0] == 0.0
+
+
+def test_bitmask_ops_match_numpy_on_odd_lengths():
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 8, 9, 63, 64, 65, 127, 128, 129, 1000, 4099):
+        a, b = rng.random(n) < 0.5, rng.random(n) < 0.5
+        A, B = orc.Bits.from_bools(a), orc.Bits.from_bools(b)
+        for f, g in ((orc.and_masks, np.logical_and), (orc.or_masks, np.logical_or), (orc.xor_masks, np.logical_xor)):
+            out = f((A, 0, n), (B, 0, n))
+            assert np.array_equal(out.to_bools(), g(a, b))
+            assert out.bits.size == (n + 7) // 8
+            if n % 8:
+                assert out.bits[-1] >> (n % 8) == 0  # trailing bits cleared
+        nt = orc.not_mask((A, 0, n))
+        assert np.array_equal(nt.to_bools(), ~a) and (n % 8 == 0 or nt.bits[-1] >> (n % 8) == 0)
+        assert orc.popcount_mask((A, 0, n)) == int(a.sum()) == orc.count_ones(A)
+        assert orc.null_count(A) == n - int(a.sum())
+        assert np.array_equal(orc.merge_bitmasks_to_new(A, B, n).to_bools(), a & b)
+        assert np.array_equal(orc.merge_bitmasks_to_new(A, None, n).to_bools(), a)
+        assert orc.merge_bitmasks_to_new(None, None, n) is None
+        assert np.array_equal(orc.union(A, B).to_bools(), a | b)
+
+
+def test_bitmask_window_offsets_floor_to_bytes_like_reference():
+    # bitmask_window_bytes (bitmask/mod.rs:124-128): offset/8 floors sub-byte offsets.
+    rng = np.random.default_rng(6)
+    a, b = rng.random(256) < 0.5, rng.random(256) < 0.5
+    A, B = orc.Bits.from_bools(a), orc.Bits.from_bools(b)
+    out = orc.and_masks((A, 64, 100), (B, 128, 100))
+    assert np.array_equal(out.to_bools(), a[64:164] & b[128:228])
+    out = orc.and_masks((A, 67, 40), (B, 3, 40))  # floored to bits 64 and 0
+    assert np.array_equal(out.to_bools(), a[64:104] & b[0:40])
+    assert orc.popcount_mask((A, 64, 100)) == int(a[64:164].sum())
+
+
+def test_sum_orders_agree_and_match_exact():
+    rng = np.random.default_rng(7)
+    d = rng.integers(-2 ** 63, 2 ** 63 - 1, 3_000_001, dtype=np.int64)
+    exact = int(d.astype(object).sum())
+    exp = (exact + 2 ** 63) % 2 ** 64 - 2 ** 63
+    assert orc.simd_sum_i64(d) == orc.hotloop_sum_i64(d) == orc.rayon_simd_sum_i64(d, threads=4) == exp
+    f = rng.standard_normal(3_000_001)
+    ref = math.fsum(f)
+    scale = math.fsum(np.abs(f))
+    for got in (orc.simd_sum_f64(f), orc.hotloop_sum_f64(f), orc.rayon_simd_sum_f64(f, threads=4)):
+        assert abs(got - ref) <= 1e-12 * scale
+
+
+def test_null_aware_stats_match_pyarrow():
+    pa = pytest.importorskip("pyarrow")
+    pc = pytest.importorskip("pyarrow.compute")
+    rng = np.random.default_rng(8)
+    n = 100_003
+    valid = rng.random(n) < 0.9
+    V = orc.Bits.from_bools(valid)
+    for dt in (np.int32, np.int64, np.uint32, np.uint64, np.float32, np.float64):
+        if np.dtype(dt).kind == "f":
+            d = rng.standard_normal(n).astype(dt)
+            d[rng.integers(0, n, 50)] = np.nan
+            d[rng.integers(0, n, 50)] = -0.0
+        else:
+            d = rng.integers(0 if np.dtype(dt).kind == "u" else -10 ** 6, 10 ** 6, n).astype(dt)
+        arr = pa.array(d, mask=~valid)
+        st = orc.stats(d, V)
+        assert st["count"] == pc.count(arr).as_py() == int(valid.sum())
+        mm = pc.min_max(arr).as_py()
+        if np.dtype(dt).kind == "f":
+            nn = pa.array(d, mask=~valid | np.isnan(d))
+            mm = pc.min_max(nn).as_py()
+            assert st["min"] == mm["min"] and st["max"] == mm["max"]
+            assert math.isnan(pc.sum(arr).as_py()) and math.isnan(st["sum"])
+            clean = np.where(np.isnan(d), 0, d)
+            st2 = orc.stats(clean, V)
+            ref = math.fsum(clean[valid].astype(np.float64))
+            assert abs(st2["sum"] - ref) <= 1e-12 * math.fsum(np.abs(clean[valid].astype(np.float64)))
+        else:
+            assert st["min"] == mm["min"] and st["max"] == mm["max"]
+            assert st["sum"] == pc.sum(arr).as_py()
+            assert math.isclose(st["mean"], pc.mean(arr).as_py(), rel_tol=1e-12)
+    # all-null and empty
+    st = orc.stats(np.arange(10, dtype=np.int64), orc.Bits.from_bools(np.zeros(10, bool)))
+    assert st["count"] == 0 and math.isnan(st["mean"])
+    assert orc.stats(np.array([], dtype=np.float64))["count"] == 0
+    # i64 sum wraps like pyarrow / Rust wrapping_add
+    big = np.array([2 ** 63 - 1, 1], dtype=np.int64)
+    assert orc.stats(big)["sum"] == -2 ** 63
+    s, c = orc.par_masked_sum_i64(big, None, threads=2)
+    assert (s, c) == (-2 ** 63, 2)
+
+
+def test_par_masked_sum_matches_stats():
+    rng = np.random.default_rng(9)
+    n = (1 << 21) + 12345
+    d = rng.integers(-2 ** 63, 2 ** 63 - 1, n, dtype=np.int64)
+    valid = rng.random(n) < 0.9
+    V = orc.Bits.from_bools(valid)
+    st = orc.stats(d, V)
+    assert orc.par_masked_sum_i64(d, V, threads=4) == (st["sum"], st["count"])
+    with np.errstate(over="ignore"):
+        assert st["sum"] == int(np.where(valid, d, 0).sum(dtype=np.int64))
