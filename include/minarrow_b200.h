@@ -1,0 +1,263 @@
+/*
+ * minarrow_b200.h — C ABI of the B200-native drop-in for Minarrow's columnar compute hot path.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to pbower/minarrow
+ * v0.10.1).  The seam in the reference is the set of free functions in
+ * src/kernels/arithmetic/dispatch.rs and src/kernels/bitmask/dispatch.rs, called from the router
+ * src/kernels/routing/arithmetic.rs:278-339 and directly by users; INTEGRATION.md shows the Rust
+ * `extern "C"` block + build.rs lines a maintainer adds to bind them.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only; no CUDA or torch types.  A CUDA stream crosses as `void*`.
+ *  - Return 0 on success, a negative mnr_status otherwise; mnr_last_error() gives the message
+ *    (thread-local, like ArrowArrayStream::get_last_error, src/ffi/arrow_c_ffi.rs:160-168).
+ *    Codes -1..-10 are the KernelError variants in declaration order (src/enums/error.rs:157-187).
+ *  - Layout is Arrow's, byte for byte: values = contiguous T[len]; validity /
+ *    boolean data = ceil(len/8) bytes, bit i = byte i>>3 bit i&7 (LSB first), 1 = valid, bits >= len
+ *    zero (Bitmask::mask_trailing_bits, src/structs/bitmask.rs:83-90).
+ *  - Inputs are borrowed and never written; outputs are fresh and owned by the caller
+ *    (dispatch.rs:88-97).  An output validity mask exists iff an input mask was passed
+ *    (dispatch.rs:90-104).
+ *  - A context owns one CUDA stream.  Device-resident calls are asynchronous on that stream unless
+ *    stated; anything returning a host scalar synchronises.  One context per host thread at a time.
+ *  - There is no CPU fallback: without a usable sm_100 device every call fails with MNR_ERR_NO_DEVICE.
+ */
+#ifndef MINARROW_B200_H
+#define MINARROW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNR_ABI_VERSION 1
+
+typedef struct mnr_ctx mnr_ctx;   /* device + stream + scratch                                          */
+typedef struct mnr_buf mnr_buf;   /* device-resident values buffer: the Vec64<T>/Buffer<T> analogue      */
+typedef struct mnr_bits mnr_bits; /* device-resident bit-packed mask: the Bitmask analogue               */
+
+/* Element types of IntegerArray<T> / FloatArray<T> (src/structs/variants/{integer,float}.rs);
+ * 8/16-bit integers are the reference's `extended_numeric_types` feature (dispatch.rs:380-387). */
+typedef enum {
+    MNR_I32 = 0, MNR_U32 = 1, MNR_I64 = 2, MNR_U64 = 3, MNR_F32 = 4, MNR_F64 = 5,
+    MNR_I8 = 6, MNR_U8 = 7, MNR_I16 = 8, MNR_U16 = 9
+} mnr_dtype;
+
+/* ArithmeticOperator, declaration order (src/enums/operators.rs:19-48). */
+typedef enum {
+    MNR_ADD = 0, MNR_SUB = 1, MNR_MUL = 2, MNR_DIV = 3, MNR_REM = 4, MNR_POW = 5, MNR_FLOORDIV = 6
+} mnr_op;
+
+/* LogicalOperator (src/enums/operators.rs:88-104). */
+typedef enum { MNR_AND = 0, MNR_OR = 1, MNR_XOR = 2 } mnr_logical_op;
+
+/* How two input validity masks combine when both are given to a fused element-wise call.
+ * AND = merge_bitmasks_to_new / Bitmask::intersect (src/kernels/bitmask/mod.rs:171-197; used by
+ *       impl_apply_datetime!, dispatch.rs:321-322) — valid iff both valid.
+ * OR  = Bitmask::union as used by route_super_array_broadcast
+ *       (src/kernels/broadcast/super_array.rs:214-229; src/structs/bitmask.rs:661-669).
+ * With one mask only, that mask is used as is in either mode (super_array.rs:218-220). */
+typedef enum { MNR_MASK_AND = 0, MNR_MASK_OR = 1 } mnr_mask_mode;
+
+typedef enum {
+    MNR_OK = 0,
+    MNR_ERR_TYPE_MISMATCH = -1,
+    MNR_ERR_LENGTH_MISMATCH = -2,     /* confirm_equal_len, src/utils.rs:163-171                         */
+    MNR_ERR_BROADCASTING = -3,
+    MNR_ERR_OPERATOR_MISMATCH = -4,
+    MNR_ERR_UNSUPPORTED_TYPE = -5,    /* routing/arithmetic.rs:403                                       */
+    MNR_ERR_COLUMN_NOT_FOUND = -6,
+    MNR_ERR_INVALID_ARGUMENTS = -7,
+    MNR_ERR_PLAN = -8,
+    MNR_ERR_OUT_OF_BOUNDS = -9,
+    MNR_ERR_DIVIDE_BY_ZERO = -10,     /* the dense integer kernels' panic, std.rs:54-55,61-62,69-70      */
+    MNR_ERR_CUDA = -100,
+    MNR_ERR_NO_DEVICE = -101,
+    MNR_ERR_OUT_OF_MEMORY = -102
+} mnr_status;
+
+/* 8-byte scalar whose active member follows the column dtype's accumulator type:
+ * I8..I64 -> i64, U8..U64 -> u64, F32/F64 -> f64. */
+typedef union { int64_t i64; uint64_t u64; double f64; } mnr_scalar64;
+
+/* Null-aware aggregate of one column (32 bytes; also the per-GPU partial that is all-reduced). */
+typedef struct {
+    mnr_scalar64 sum;   /* wrapping two's complement for integers; f64 for floats                        */
+    mnr_scalar64 min;   /* identity when nothing qualifies: INT_MAX-of-type / UINT_MAX-of-type / NaN     */
+    mnr_scalar64 max;   /* identity: INT_MIN-of-type / 0 / NaN                                           */
+    uint64_t count;     /* number of valid rows (popcount of validity, or len)                           */
+} mnr_agg;
+
+/* ---- library / context ----------------------------------------------------------------------------- */
+int mnr_abi_version(void);
+const char* mnr_last_error(void);
+int mnr_device_count(void);
+int mnr_ctx_create(int device, mnr_ctx** out);
+/* Borrow the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); `cuda_stream` = cudaStream_t. */
+int mnr_ctx_create_on_stream(int device, void* cuda_stream, mnr_ctx** out);
+void mnr_ctx_destroy(mnr_ctx* ctx);
+int mnr_ctx_synchronize(mnr_ctx* ctx);
+int mnr_ctx_device(const mnr_ctx* ctx);
+void* mnr_ctx_stream(const mnr_ctx* ctx);
+/* Number of kernels of this library launched through `ctx` so far. */
+uint64_t mnr_ctx_launch_count(const mnr_ctx* ctx);
+/* Kernel variant knobs for tuning sweeps ("reduce_unroll", "reduce_blocks_per_sm", "ew_unroll", ...).
+ * Unknown keys return MNR_ERR_INVALID_ARGUMENTS.  Results never depend on these for integer work;
+ * float sums change order with the reduce knobs (documented in DESIGN.md). */
+int mnr_ctx_set_option(mnr_ctx* ctx, const char* key, int64_t value);
+
+/* ---- device-resident buffers: Vec64<T> / Buffer<T> (src/structs/buffer.rs:126-139) -------------------- */
+int mnr_buf_alloc(mnr_ctx* ctx, mnr_dtype dtype, size_t len, mnr_buf** out);
+/* Arrow-layout-preserving upload of `len` elements (Array::data_ptr_and_byte_len, src/enums/array.rs:2563). */
+int mnr_buf_upload(mnr_ctx* ctx, mnr_dtype dtype, const void* host, size_t len, mnr_buf** out);
+/* Non-owning view of caller-owned device memory. */
+int mnr_buf_wrap(mnr_ctx* ctx, mnr_dtype dtype, void* device_ptr, size_t len, mnr_buf** out);
+/* ArrayV window `(array, offset, len)` (src/structs/views/array_view.rs:79-94): non-owning, parent must outlive it. */
+int mnr_buf_slice(const mnr_buf* parent, size_t offset, size_t len, mnr_buf** out);
+int mnr_buf_download(mnr_ctx* ctx, const mnr_buf* buf, void* host);   /* synchronises */
+size_t mnr_buf_len(const mnr_buf* buf);
+int mnr_buf_dtype(const mnr_buf* buf);
+void* mnr_buf_device_ptr(const mnr_buf* buf);
+void mnr_buf_free(mnr_buf* buf);
+
+/* ---- device-resident bitmasks: Bitmask (src/structs/bitmask.rs:66-71) --------------------------------- */
+int mnr_bits_alloc(mnr_ctx* ctx, size_t len_bits, mnr_bits** out);
+/* Bitmask::new_set_all (bitmask.rs:94-105). */
+int mnr_bits_new_set_all(mnr_ctx* ctx, size_t len_bits, int value, mnr_bits** out);
+/* Upload ceil(len_bits/8) bytes (Array::null_mask_ptr_and_byte_len, src/enums/array.rs:2672); slack bits are cleared. */
+int mnr_bits_upload(mnr_ctx* ctx, const uint8_t* host_bytes, size_t len_bits, mnr_bits** out);
+int mnr_bits_wrap(mnr_ctx* ctx, void* device_ptr, size_t len_bits, mnr_bits** out);
+int mnr_bits_download(mnr_ctx* ctx, const mnr_bits* bits, uint8_t* host_bytes);   /* synchronises */
+size_t mnr_bits_len(const mnr_bits* bits);
+void* mnr_bits_device_ptr(const mnr_bits* bits);
+void mnr_bits_free(mnr_bits* bits);
+
+/* ---- element-wise arithmetic, device-resident ----------------------------------------------------------
+ * apply_int_{i32,u32,i64,u64,..} / apply_float_{f32,f64} (src/kernels/arithmetic/dispatch.rs:65-206,376-402)
+ * with the caller-side mask merge fused in.  One HBM pass: out[i] = valid ? lhs[i] op rhs[i] : 0.
+ *  - no mask: dense kernel, *out_mask = NULL; integer Div/Rem/FloorDiv with a zero divisor returns
+ *    MNR_ERR_DIVIDE_BY_ZERO (the reference panics; output contents unspecified) — this one case synchronises.
+ *  - mask(s): invalid row => value 0 + validity 0; integer Div/Rem/FloorDiv by zero => value 0 + validity 0
+ *    (std.rs:96-136, simd.rs:268-328); float results keep the input validity (NaN/Inf stay valid).
+ *  - integers wrap; MIN / -1 = MIN, MIN % -1 = 0 (assumption A.2); floats are IEEE with no FMA
+ *    contraction; Power = exp(b * ln a) (tolerance parity only).
+ * `mode` matters only when both masks are given.  lhs/rhs must share dtype and length. */
+int mnr_ew_binary(mnr_ctx* ctx, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lhs_mask,
+                  const mnr_bits* rhs_mask, mnr_mask_mode mode, mnr_buf** out, mnr_bits** out_mask);
+/* Same, into caller-provided outputs (out_mask required iff a mask is given). */
+int mnr_ew_binary_into(mnr_ctx* ctx, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lhs_mask,
+                       const mnr_bits* rhs_mask, mnr_mask_mode mode, mnr_buf* out, mnr_bits* out_mask);
+/* Scalar broadcast without materialising the length-1 operand (replaces broadcast_length_1_array +
+ * the binary kernel, src/kernels/routing/broadcast.rs:25-112).  `scalar` points at one host element of the
+ * array's dtype; scalar_is_lhs selects `scalar op arr[i]` vs `arr[i] op scalar` (operand order is
+ * significant: src/kernels/broadcast/scalar.rs:1332-1350). */
+int mnr_ew_scalar(mnr_ctx* ctx, mnr_op op, const mnr_buf* arr, const void* scalar, int scalar_is_lhs,
+                  const mnr_bits* mask, mnr_buf** out, mnr_bits** out_mask);
+int mnr_ew_scalar_into(mnr_ctx* ctx, mnr_op op, const mnr_buf* arr, const void* scalar, int scalar_is_lhs,
+                       const mnr_bits* mask, mnr_buf* out, mnr_bits* out_mask);
+/* apply_fma_{f32,f64} (dispatch.rs:211-290,404-418): out = fma(a, b, c), single rounding. */
+int mnr_ew_fma(mnr_ctx* ctx, const mnr_buf* a, const mnr_buf* b, const mnr_buf* c, const mnr_bits* mask,
+               mnr_buf** out, mnr_bits** out_mask);
+int mnr_ew_fma_into(mnr_ctx* ctx, const mnr_buf* a, const mnr_buf* b, const mnr_buf* c, const mnr_bits* mask,
+                    mnr_buf* out, mnr_bits* out_mask);
+/* Mixed-type promotion of the router (routing/arithmetic.rs:244-269,342-373): an I32 operand against an
+ * F64 / F32 operand is cast on load (`as f64` / `as f32`) inside the same pass; output has the float dtype. */
+int mnr_ew_binary_promote(mnr_ctx* ctx, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lhs_mask,
+                          const mnr_bits* rhs_mask, mnr_mask_mode mode, mnr_buf** out, mnr_bits** out_mask);
+
+/* ---- bitmask kernels, device-resident (src/kernels/bitmask/dispatch.rs) ---------------------------------
+ * Windows are BitmaskVT = (&Bitmask, offset, len).  Like the reference (bitmask_window_bytes,
+ * src/kernels/bitmask/mod.rs:124-128) binop/not start at BYTE offset/8: sub-byte offsets are floored. */
+/* and_masks / or_masks / xor_masks (dispatch.rs:96-131) -> bitmask_binop_simd (simd.rs:95-139). */
+int mnr_bits_binop(mnr_ctx* ctx, mnr_logical_op op, const mnr_bits* lhs, size_t lhs_offset, const mnr_bits* rhs,
+                   size_t rhs_offset, size_t len, mnr_bits** out);
+int mnr_bits_binop_into(mnr_ctx* ctx, mnr_logical_op op, const mnr_bits* lhs, size_t lhs_offset,
+                        const mnr_bits* rhs, size_t rhs_offset, size_t len, mnr_bits* out);
+/* not_mask (dispatch.rs:135-144) -> bitmask_unop_simd (simd.rs:169-203); BooleanArray `!` (boolean.rs:853-866). */
+int mnr_bits_not(mnr_ctx* ctx, const mnr_bits* src, size_t offset, size_t len, mnr_bits** out);
+int mnr_bits_not_into(mnr_ctx* ctx, const mnr_bits* src, size_t offset, size_t len, mnr_bits* out);
+/* popcount_mask (dispatch.rs:258-267 -> simd.rs:596-645): set bits of words [offset/64 ..) over `len` bits.
+ * Bitmask::count_ones / null_count (bitmask.rs:393-417): offset 0, len = mask len; null_count = len - ones.
+ * Synchronises. */
+int mnr_bits_popcount(mnr_ctx* ctx, const mnr_bits* mask, size_t offset, size_t len, uint64_t* ones);
+/* all_true_mask / all_false_mask (dispatch.rs:273-295). Synchronise. */
+int mnr_bits_all_true(mnr_ctx* ctx, const mnr_bits* mask, int* out);
+int mnr_bits_all_false(mnr_ctx* ctx, const mnr_bits* mask, int* out);
+/* Validity merge as a stand-alone mask (normally fused into mnr_ew_*): AND = merge_bitmasks_to_new
+ * (bitmask/mod.rs:171-197), OR = Bitmask::union_opt (bitmask.rs:651-669).  Either side may be NULL
+ * ("no nulls"); both NULL => *out = NULL. */
+int mnr_bits_merge(mnr_ctx* ctx, const mnr_bits* lhs, const mnr_bits* rhs, size_t len, mnr_mask_mode mode,
+                   mnr_bits** out);
+/* eq_mask / ne_mask (dispatch.rs:178-200 -> simd.rs:402-472): offsets must be multiples of 64
+ * (the reference panics otherwise => MNR_ERR_INVALID_ARGUMENTS). */
+int mnr_bits_eq(mnr_ctx* ctx, const mnr_bits* a, size_t a_offset, const mnr_bits* b, size_t b_offset, size_t len,
+                int negate, mnr_bits** out);
+/* all_eq / all_ne (dispatch.rs:204-226 -> simd.rs:490-581); all_ne is !all_eq as in the reference. Synchronise. */
+int mnr_bits_all_eq(mnr_ctx* ctx, const mnr_bits* a, size_t a_offset, const mnr_bits* b, size_t b_offset,
+                    size_t len, int* out);
+/* in_mask / not_in_mask (dispatch.rs:150-172 -> simd.rs:327-398). */
+int mnr_bits_in(mnr_ctx* ctx, const mnr_bits* lhs, size_t lhs_offset, const mnr_bits* rhs, size_t rhs_offset,
+                size_t len, int negate, mnr_bits** out);
+
+/* ---- reductions, device-resident -------------------------------------------------------------------------
+ * Sum follows the benches that define it in the reference (benches/benchmark_parallel_simd.rs:44-97,
+ * benches/hotloop_benchmark_simd.rs:56-174): integer sums wrap and are bit-exact in any order; float sums
+ * use the fixed order documented in DESIGN.md (<= 1e-12 relative to the reference order).  count / min /
+ * max / mean and null-skipping are not in the reference tree (downstream `simd-kernels` crate); their
+ * definition is DESIGN.md "A.6".  `validity` may be NULL (dense).  I32/U32 widen to 64-bit sums, F32 sums in f64. */
+int mnr_reduce_stats(mnr_ctx* ctx, const mnr_buf* buf, const mnr_bits* validity, mnr_agg* out_host);  /* syncs */
+int mnr_reduce_sum(mnr_ctx* ctx, const mnr_buf* buf, const mnr_bits* validity, mnr_scalar64* out_sum,
+                   uint64_t* out_count);                                                             /* syncs */
+/* Asynchronous forms: the 32-byte mnr_agg is written to DEVICE memory `out_device` (16-byte aligned) on the
+ * context stream — the per-GPU partial handed to the NCCL all-reduce.  with_minmax = 0 leaves min/max at
+ * their identities and runs the cheaper sum+count kernel. */
+int mnr_reduce_stats_async(mnr_ctx* ctx, const mnr_buf* buf, const mnr_bits* validity, int with_minmax,
+                           void* out_device);
+/* mean = (double)sum / (double)count on the host from a (combined) aggregate; NaN when count == 0. */
+double mnr_agg_mean(mnr_dtype dtype, const mnr_agg* agg);
+/* Combine per-chunk / per-GPU partials in index order (the documented rank-order float add). */
+int mnr_agg_combine(mnr_dtype dtype, const mnr_agg* partials, size_t n, mnr_agg* out);
+
+/* ---- host-slice drop-ins: exactly the reference leaf signatures ------------------------------------------
+ * `fn apply_int_i64(lhs:&[i64], rhs:&[i64], op, mask:Option<&Bitmask>) -> Result<IntegerArray<i64>,KernelError>`
+ * (dispatch.rs:74-79,147-152): host pointers in, host pointers out; upload, kernel and download are pipelined
+ * in chunks on the context's copy streams.  `mask` is the single pre-merged validity (NULL = None); `out_mask`
+ * (ceil(len/8) bytes) is written iff `mask` is given.  Fastest with pinned (page-locked) host memory. */
+int mnr_apply_host(mnr_ctx* ctx, mnr_dtype dtype, mnr_op op, const void* lhs, size_t lhs_len, const void* rhs,
+                   size_t rhs_len, const uint8_t* mask, void* out, uint8_t* out_mask);
+int mnr_apply_int_i32(mnr_ctx*, const int32_t* lhs, size_t lhs_len, const int32_t* rhs, size_t rhs_len, mnr_op op,
+                      const uint8_t* mask, int32_t* out, uint8_t* out_mask);
+int mnr_apply_int_u32(mnr_ctx*, const uint32_t* lhs, size_t lhs_len, const uint32_t* rhs, size_t rhs_len, mnr_op op,
+                      const uint8_t* mask, uint32_t* out, uint8_t* out_mask);
+int mnr_apply_int_i64(mnr_ctx*, const int64_t* lhs, size_t lhs_len, const int64_t* rhs, size_t rhs_len, mnr_op op,
+                      const uint8_t* mask, int64_t* out, uint8_t* out_mask);
+int mnr_apply_int_u64(mnr_ctx*, const uint64_t* lhs, size_t lhs_len, const uint64_t* rhs, size_t rhs_len, mnr_op op,
+                      const uint8_t* mask, uint64_t* out, uint8_t* out_mask);
+int mnr_apply_float_f32(mnr_ctx*, const float* lhs, size_t lhs_len, const float* rhs, size_t rhs_len, mnr_op op,
+                        const uint8_t* mask, float* out, uint8_t* out_mask);
+int mnr_apply_float_f64(mnr_ctx*, const double* lhs, size_t lhs_len, const double* rhs, size_t rhs_len, mnr_op op,
+                        const uint8_t* mask, double* out, uint8_t* out_mask);
+/* apply_fma_f32 / apply_fma_f64 (dispatch.rs:221-226). */
+int mnr_apply_fma_host(mnr_ctx* ctx, mnr_dtype dtype, const void* lhs, size_t lhs_len, const void* rhs,
+                       size_t rhs_len, const void* acc, size_t acc_len, const uint8_t* mask, void* out,
+                       uint8_t* out_mask);
+/* Null-aware aggregate of a host column (the sum the benches time, plus count/min/max): chunked upload
+ * overlapped with the reduction kernel; one 32-byte result comes back. */
+int mnr_stats_host(mnr_ctx* ctx, mnr_dtype dtype, const void* data, size_t len, const uint8_t* validity,
+                   int with_minmax, mnr_agg* out);
+/* bitmask_binop over host bytes (BitmaskVT windows, byte-floored offsets as above). */
+int mnr_bitmask_binop_host(mnr_ctx* ctx, mnr_logical_op op, const uint8_t* lhs, size_t lhs_offset,
+                           const uint8_t* rhs, size_t rhs_offset, size_t len, uint8_t* out);
+/* Page-lock / unlock a caller buffer so the drop-ins above copy at full PCIe speed. */
+int mnr_host_register(void* ptr, size_t bytes);
+int mnr_host_unregister(void* ptr);
+/* Pinned host allocation (the download side of SharedBuffer::from_owner, src/structs/shared_buffer/mod.rs:187). */
+int mnr_host_alloc(size_t bytes, void** out);
+void mnr_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINARROW_B200_H */

@@ -1,0 +1,899 @@
+// C ABI of libminarrow_b200.so (include/minarrow_b200.h): contexts, device-resident buffers / bitmasks,
+// argument validation with the reference's error behaviour, and the host-slice drop-in pipelines.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+#include "reduce_kernels.cuh"
+
+namespace mnr {
+extern int g_ew_grid_cap;
+__global__ void clear_trailing_kernel(uint8_t* bits, uint64_t len) {
+    if (len & 7) bits[(len - 1) >> 3] &= (uint8_t)((1u << (unsigned)(len & 7)) - 1u);
+}
+}  // namespace mnr
+
+using namespace mnr;
+
+// ---- errors ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char* what) {
+    const int code = (e == cudaErrorMemoryAllocation) ? MNR_ERR_OUT_OF_MEMORY
+                     : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice)
+                         ? MNR_ERR_NO_DEVICE
+                         : MNR_ERR_CUDA;
+    return fail(code, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+#define CU(x)                                            \
+    do {                                                 \
+        cudaError_t e__ = (x);                           \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #x); \
+    } while (0)
+#define REQUIRE(cond, code, ...) \
+    do {                         \
+        if (!(cond)) return fail(code, __VA_ARGS__); \
+    } while (0)
+
+static bool valid_dtype(int d) { return d >= MNR_I32 && d <= MNR_U16; }
+static bool is_float_dtype(int d) { return d == MNR_F32 || d == MNR_F64; }
+static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+static size_t mask_bytes(size_t bits) { return (bits + 7) >> 3; }
+
+extern "C" {
+
+int mnr_abi_version(void) { return MNR_ABI_VERSION; }
+const char* mnr_last_error(void) { return g_err.c_str(); }
+
+int mnr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---- context -------------------------------------------------------------------------------------------------
+static int ctx_init(int device, cudaStream_t stream, bool own, mnr_ctx** out) {
+    REQUIRE(out, MNR_ERR_INVALID_ARGUMENTS, "mnr_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MNR_ERR_NO_DEVICE, "no CUDA device (%s); minarrow_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    REQUIRE(device >= 0 && device < n, MNR_ERR_NO_DEVICE, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    REQUIRE(prop.major >= 10, MNR_ERR_NO_DEVICE,
+            "device %d is sm_%d%d; this library carries sm_100a code only (no fallback path)", device, prop.major,
+            prop.minor);
+    CU(cudaSetDevice(device));
+    mnr_ctx* c = new mnr_ctx();
+    c->device = device;
+    c->own_stream = own;
+    if (own) CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    else c->stream = stream;
+    for (int i = 0; i < 3; ++i) CU(cudaStreamCreateWithFlags(&c->slot_stream[i], cudaStreamNonBlocking));
+    const size_t pbytes = sizeof(AggRaw) * (size_t)reduce_max_grid();
+    for (int i = 0; i < 4; ++i) {
+        CU(cudaMalloc(&c->partials[i], pbytes));
+        CU(cudaMalloc(&c->ticket[i], 64));
+        CU(cudaMemset(c->ticket[i], 0, 64));
+    }
+    CU(cudaMalloc(&c->d_agg, sizeof(AggRaw)));
+    CU(cudaMalloc(&c->d_count, 64));
+    CU(cudaHostAlloc(&c->h_scratch, 256, cudaHostAllocDefault));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;   // keep freed blocks cached: fresh outputs per call without cudaMalloc cost
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c;
+    return MNR_OK;
+}
+
+int mnr_ctx_create(int device, mnr_ctx** out) { return ctx_init(device, nullptr, true, out); }
+int mnr_ctx_create_on_stream(int device, void* cuda_stream, mnr_ctx** out) {
+    return ctx_init(device, static_cast<cudaStream_t>(cuda_stream), false, out);
+}
+
+void mnr_ctx_destroy(mnr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 3; ++i) {
+        if (c->slot_stream[i]) { cudaStreamSynchronize(c->slot_stream[i]); cudaStreamDestroy(c->slot_stream[i]); }
+        for (int j = 0; j < 6; ++j) if (c->stage[i][j]) cudaFree(c->stage[i][j]);
+    }
+    for (int i = 0; i < 4; ++i) { cudaFree(c->partials[i]); cudaFree(c->ticket[i]); }
+    if (c->chunk_aggs) cudaFree(c->chunk_aggs);
+    cudaFree(c->d_agg);
+    cudaFree(c->d_count);
+    cudaFreeHost(c->h_scratch);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int mnr_ctx_synchronize(mnr_ctx* c) {
+    REQUIRE(c, MNR_ERR_INVALID_ARGUMENTS, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return MNR_OK;
+}
+int mnr_ctx_device(const mnr_ctx* c) { return c ? c->device : -1; }
+void* mnr_ctx_stream(const mnr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t mnr_ctx_launch_count(const mnr_ctx* c) { return c ? c->launches : 0; }
+
+int mnr_ctx_set_option(mnr_ctx* c, const char* key, int64_t value) {
+    REQUIRE(c && key, MNR_ERR_INVALID_ARGUMENTS, "ctx/key is NULL");
+    if (!strcmp(key, "ew_grid_cap")) { g_ew_grid_cap = (int)value; return MNR_OK; }
+    if (!strcmp(key, "host_chunk_rows")) {
+        REQUIRE(value >= 1024 && value % 1024 == 0, MNR_ERR_INVALID_ARGUMENTS, "host_chunk_rows must be a multiple of 1024");
+        c->host_chunk_rows = (size_t)value;
+        return MNR_OK;
+    }
+    return fail(MNR_ERR_INVALID_ARGUMENTS, "unknown option '%s'", key);
+}
+
+// ---- buffers ---------------------------------------------------------------------------------------------------
+static int dev_alloc(mnr_ctx* c, size_t bytes, void** p) {
+    CU(cudaSetDevice(c->device));
+    CU(cudaMallocAsync(p, pad256(bytes ? bytes : 1), c->stream));
+    return MNR_OK;
+}
+
+int mnr_buf_alloc(mnr_ctx* c, mnr_dtype dtype, size_t len, mnr_buf** out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "ctx/out is NULL");
+    REQUIRE(valid_dtype(dtype), MNR_ERR_UNSUPPORTED_TYPE, "unknown dtype %d", (int)dtype);
+    void* p = nullptr;
+    int rc = dev_alloc(c, len * dtype_size(dtype), &p);
+    if (rc) return rc;
+    *out = new mnr_buf{c, dtype, p, len, true};
+    return MNR_OK;
+}
+
+int mnr_buf_upload(mnr_ctx* c, mnr_dtype dtype, const void* host, size_t len, mnr_buf** out) {
+    REQUIRE(host || len == 0, MNR_ERR_INVALID_ARGUMENTS, "host pointer is NULL");
+    int rc = mnr_buf_alloc(c, dtype, len, out);
+    if (rc) return rc;
+    if (len) {
+        CU(cudaMemcpyAsync((*out)->ptr, host, len * dtype_size(dtype), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));   // the caller may reuse `host` on return
+    }
+    return MNR_OK;
+}
+
+int mnr_buf_wrap(mnr_ctx* c, mnr_dtype dtype, void* device_ptr, size_t len, mnr_buf** out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "ctx/out is NULL");
+    REQUIRE(valid_dtype(dtype), MNR_ERR_UNSUPPORTED_TYPE, "unknown dtype %d", (int)dtype);
+    REQUIRE(device_ptr || len == 0, MNR_ERR_INVALID_ARGUMENTS, "device pointer is NULL");
+    REQUIRE((reinterpret_cast<uintptr_t>(device_ptr) % dtype_size(dtype)) == 0, MNR_ERR_INVALID_ARGUMENTS,
+            "device pointer is not aligned to the element size");
+    *out = new mnr_buf{c, dtype, device_ptr, len, false};
+    return MNR_OK;
+}
+
+int mnr_buf_slice(const mnr_buf* parent, size_t offset, size_t len, mnr_buf** out) {
+    REQUIRE(parent && out, MNR_ERR_INVALID_ARGUMENTS, "parent/out is NULL");
+    REQUIRE(offset <= parent->len && len <= parent->len - offset, MNR_ERR_OUT_OF_BOUNDS,
+            "slice [%zu, %zu) out of bounds for length %zu", offset, offset + len, parent->len);
+    *out = new mnr_buf{parent->ctx, parent->dtype, static_cast<char*>(parent->ptr) + offset * dtype_size(parent->dtype),
+                       len, false};
+    return MNR_OK;
+}
+
+int mnr_buf_download(mnr_ctx* c, const mnr_buf* b, void* host) {
+    REQUIRE(c && b && (host || b->len == 0), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    if (b->len) CU(cudaMemcpyAsync(host, b->ptr, b->len * dtype_size(b->dtype), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MNR_OK;
+}
+size_t mnr_buf_len(const mnr_buf* b) { return b ? b->len : 0; }
+int mnr_buf_dtype(const mnr_buf* b) { return b ? (int)b->dtype : -1; }
+void* mnr_buf_device_ptr(const mnr_buf* b) { return b ? b->ptr : nullptr; }
+void mnr_buf_free(mnr_buf* b) {
+    if (!b) return;
+    if (b->owned && b->ptr) { cudaSetDevice(b->ctx->device); cudaFreeAsync(b->ptr, b->ctx->stream); }
+    delete b;
+}
+
+int mnr_bits_alloc(mnr_ctx* c, size_t len_bits, mnr_bits** out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "ctx/out is NULL");
+    void* p = nullptr;
+    int rc = dev_alloc(c, mask_bytes(len_bits), &p);
+    if (rc) return rc;
+    *out = new mnr_bits{c, static_cast<uint8_t*>(p), len_bits, true};
+    return MNR_OK;
+}
+
+int mnr_bits_new_set_all(mnr_ctx* c, size_t len_bits, int value, mnr_bits** out) {
+    int rc = mnr_bits_alloc(c, len_bits, out);
+    if (rc) return rc;
+    if (len_bits) {
+        CU(cudaMemsetAsync((*out)->ptr, value ? 0xFF : 0, mask_bytes(len_bits), c->stream));
+        if (value && (len_bits & 7)) { clear_trailing_kernel<<<1, 1, 0, c->stream>>>((*out)->ptr, len_bits); c->launches++; }
+        CU(cudaGetLastError());
+    }
+    return MNR_OK;
+}
+
+int mnr_bits_upload(mnr_ctx* c, const uint8_t* host_bytes, size_t len_bits, mnr_bits** out) {
+    REQUIRE(host_bytes || len_bits == 0, MNR_ERR_INVALID_ARGUMENTS, "host pointer is NULL");
+    int rc = mnr_bits_alloc(c, len_bits, out);
+    if (rc) return rc;
+    if (len_bits) {
+        CU(cudaMemcpyAsync((*out)->ptr, host_bytes, mask_bytes(len_bits), cudaMemcpyHostToDevice, c->stream));
+        if (len_bits & 7) { clear_trailing_kernel<<<1, 1, 0, c->stream>>>((*out)->ptr, len_bits); c->launches++; }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return MNR_OK;
+}
+
+int mnr_bits_wrap(mnr_ctx* c, void* device_ptr, size_t len_bits, mnr_bits** out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "ctx/out is NULL");
+    REQUIRE(device_ptr || len_bits == 0, MNR_ERR_INVALID_ARGUMENTS, "device pointer is NULL");
+    *out = new mnr_bits{c, static_cast<uint8_t*>(device_ptr), len_bits, false};
+    return MNR_OK;
+}
+
+int mnr_bits_download(mnr_ctx* c, const mnr_bits* b, uint8_t* host_bytes) {
+    REQUIRE(c && b && (host_bytes || b->len == 0), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    if (b->len) CU(cudaMemcpyAsync(host_bytes, b->ptr, mask_bytes(b->len), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MNR_OK;
+}
+size_t mnr_bits_len(const mnr_bits* b) { return b ? b->len : 0; }
+void* mnr_bits_device_ptr(const mnr_bits* b) { return b ? b->ptr : nullptr; }
+void mnr_bits_free(mnr_bits* b) {
+    if (!b) return;
+    if (b->owned && b->ptr) { cudaSetDevice(b->ctx->device); cudaFreeAsync(b->ptr, b->ctx->stream); }
+    delete b;
+}
+
+// ---- element-wise ------------------------------------------------------------------------------------------------
+static uint64_t scalar_to_bits(mnr_dtype dt, const void* scalar) {
+    uint64_t b = 0;
+    memcpy(&b, scalar, dtype_size(dt));
+    return b;
+}
+
+// Launch + (dense integer Div/Rem/FloorDiv only) the reference's divide-by-zero panic as an error code.
+static int run_ew(mnr_ctx* c, EwArgs& a, cudaStream_t s, bool promote, mnr_dtype lt, mnr_dtype rt) {
+    if (a.n == 0) return MNR_OK;
+    const bool dense_int_div = !a.lmask && !a.rmask && !is_float_dtype(a.dtype) &&
+                               (a.op == MNR_DIV || a.op == MNR_REM || a.op == MNR_FLOORDIV);
+    a.div0_flag = c->ticket[0] + 8;
+    if (dense_int_div) CU(cudaMemsetAsync(a.div0_flag, 0, 4, s));
+    CU(promote ? launch_ew_promote(a, lt, rt, s) : launch_ew_binary(a, s));
+    c->launches++;
+    if (dense_int_div) {
+        unsigned int* h = static_cast<unsigned int*>(c->h_scratch);
+        CU(cudaMemcpyAsync(h, a.div0_flag, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (*h) return fail(MNR_ERR_DIVIDE_BY_ZERO, "%s by zero in dense integer kernel (the reference panics here)",
+                            a.op == MNR_DIV ? "Division" : a.op == MNR_REM ? "Remainder" : "Floor division");
+    }
+    return MNR_OK;
+}
+
+static int check_masks(const mnr_bits* lm, const mnr_bits* rm, size_t n) {
+    REQUIRE(!lm || lm->len >= n, MNR_ERR_INVALID_ARGUMENTS, "lhs mask has %zu bits, need %zu", lm->len, n);
+    REQUIRE(!rm || rm->len >= n, MNR_ERR_INVALID_ARGUMENTS, "rhs mask has %zu bits, need %zu", rm->len, n);
+    return MNR_OK;
+}
+
+int mnr_ew_binary_into(mnr_ctx* c, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lm,
+                       const mnr_bits* rm, mnr_mask_mode mode, mnr_buf* out, mnr_bits* out_mask) {
+    REQUIRE(c && lhs && rhs && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(op >= MNR_ADD && op <= MNR_FLOORDIV, MNR_ERR_OPERATOR_MISMATCH, "unknown operator %d", (int)op);
+    REQUIRE(lhs->len == rhs->len, MNR_ERR_LENGTH_MISMATCH, "apply numeric: length mismatch (lhs: %zu, rhs: %zu)",
+            lhs->len, rhs->len);
+    REQUIRE(lhs->dtype == rhs->dtype, MNR_ERR_UNSUPPORTED_TYPE,
+            "Unsupported array type combination for arithmetic operations (dtypes %d, %d)", (int)lhs->dtype,
+            (int)rhs->dtype);
+    REQUIRE(out->dtype == lhs->dtype && out->len == lhs->len, MNR_ERR_INVALID_ARGUMENTS, "output buffer shape/dtype mismatch");
+    const bool masked = lm || rm;
+    REQUIRE(!masked || (out_mask && out_mask->len == lhs->len), MNR_ERR_INVALID_ARGUMENTS,
+            "masked call needs an output mask of %zu bits", lhs->len);
+    int rc = check_masks(lm, rm, lhs->len);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    EwArgs a{};
+    a.dtype = lhs->dtype; a.op = op; a.lhs = lhs->ptr; a.rhs = rhs->ptr;
+    a.lmask = lm ? lm->ptr : nullptr; a.rmask = rm ? rm->ptr : nullptr; a.mask_or = mode == MNR_MASK_OR;
+    a.out = out->ptr; a.out_mask = masked ? out_mask->ptr : nullptr; a.n = lhs->len;
+    return run_ew(c, a, c->stream, false, lhs->dtype, rhs->dtype);
+}
+
+static int alloc_outputs(mnr_ctx* c, mnr_dtype dt, size_t n, bool masked, mnr_buf** out, mnr_bits** out_mask) {
+    REQUIRE(out && out_mask, MNR_ERR_INVALID_ARGUMENTS, "out/out_mask is NULL");
+    *out = nullptr; *out_mask = nullptr;
+    int rc = mnr_buf_alloc(c, dt, n, out);
+    if (rc) return rc;
+    if (masked) {
+        rc = mnr_bits_alloc(c, n, out_mask);
+        if (rc) { mnr_buf_free(*out); *out = nullptr; return rc; }
+    }
+    return MNR_OK;
+}
+static int drop_outputs(int rc, mnr_buf** out, mnr_bits** out_mask) {
+    if (rc) { mnr_buf_free(*out); mnr_bits_free(*out_mask); *out = nullptr; *out_mask = nullptr; }
+    return rc;
+}
+
+int mnr_ew_binary(mnr_ctx* c, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lm, const mnr_bits* rm,
+                  mnr_mask_mode mode, mnr_buf** out, mnr_bits** out_mask) {
+    REQUIRE(c && lhs && rhs, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(lhs->len == rhs->len, MNR_ERR_LENGTH_MISMATCH, "apply numeric: length mismatch (lhs: %zu, rhs: %zu)",
+            lhs->len, rhs->len);
+    int rc = alloc_outputs(c, lhs->dtype, lhs->len, lm || rm, out, out_mask);
+    if (rc) return rc;
+    return drop_outputs(mnr_ew_binary_into(c, op, lhs, rhs, lm, rm, mode, *out, *out_mask), out, out_mask);
+}
+
+int mnr_ew_scalar_into(mnr_ctx* c, mnr_op op, const mnr_buf* arr, const void* scalar, int scalar_is_lhs,
+                       const mnr_bits* mask, mnr_buf* out, mnr_bits* out_mask) {
+    REQUIRE(c && arr && scalar && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(op >= MNR_ADD && op <= MNR_FLOORDIV, MNR_ERR_OPERATOR_MISMATCH, "unknown operator %d", (int)op);
+    REQUIRE(out->dtype == arr->dtype && out->len == arr->len, MNR_ERR_INVALID_ARGUMENTS, "output buffer shape/dtype mismatch");
+    REQUIRE(!mask || (out_mask && out_mask->len == arr->len), MNR_ERR_INVALID_ARGUMENTS,
+            "masked call needs an output mask of %zu bits", arr->len);
+    int rc = check_masks(mask, nullptr, arr->len);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    EwArgs a{};
+    a.dtype = arr->dtype; a.op = op;
+    a.lhs = scalar_is_lhs ? nullptr : arr->ptr;
+    a.rhs = scalar_is_lhs ? arr->ptr : nullptr;
+    a.scalar_bits = scalar_to_bits(arr->dtype, scalar);
+    a.lmask = mask ? mask->ptr : nullptr; a.rmask = nullptr; a.mask_or = 0;
+    a.out = out->ptr; a.out_mask = mask ? out_mask->ptr : nullptr; a.n = arr->len;
+    return run_ew(c, a, c->stream, false, arr->dtype, arr->dtype);
+}
+
+int mnr_ew_scalar(mnr_ctx* c, mnr_op op, const mnr_buf* arr, const void* scalar, int scalar_is_lhs, const mnr_bits* mask,
+                  mnr_buf** out, mnr_bits** out_mask) {
+    REQUIRE(c && arr, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    int rc = alloc_outputs(c, arr->dtype, arr->len, mask != nullptr, out, out_mask);
+    if (rc) return rc;
+    return drop_outputs(mnr_ew_scalar_into(c, op, arr, scalar, scalar_is_lhs, mask, *out, *out_mask), out, out_mask);
+}
+
+int mnr_ew_fma_into(mnr_ctx* c, const mnr_buf* a, const mnr_buf* b, const mnr_buf* acc, const mnr_bits* mask, mnr_buf* out,
+                    mnr_bits* out_mask) {
+    REQUIRE(c && a && b && acc && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(a->len == b->len, MNR_ERR_LENGTH_MISMATCH, "apply numeric: length mismatch (lhs: %zu, rhs: %zu)", a->len, b->len);
+    REQUIRE(a->len == acc->len, MNR_ERR_LENGTH_MISMATCH, "acc length mismatch (lhs: %zu, rhs: %zu)", a->len, acc->len);
+    REQUIRE(is_float_dtype(a->dtype) && b->dtype == a->dtype && acc->dtype == a->dtype, MNR_ERR_UNSUPPORTED_TYPE,
+            "fma needs three F32 or three F64 operands");
+    REQUIRE(out->dtype == a->dtype && out->len == a->len, MNR_ERR_INVALID_ARGUMENTS, "output buffer shape/dtype mismatch");
+    REQUIRE(!mask || (out_mask && out_mask->len == a->len), MNR_ERR_INVALID_ARGUMENTS,
+            "masked call needs an output mask of %zu bits", a->len);
+    int rc = check_masks(mask, nullptr, a->len);
+    if (rc) return rc;
+    if (a->len == 0) return MNR_OK;
+    CU(cudaSetDevice(c->device));
+    CU(launch_ew_fma(a->dtype, a->ptr, b->ptr, acc->ptr, mask ? mask->ptr : nullptr, out->ptr,
+                     mask ? out_mask->ptr : nullptr, a->len, c->stream));
+    c->launches++;
+    return MNR_OK;
+}
+
+int mnr_ew_fma(mnr_ctx* c, const mnr_buf* a, const mnr_buf* b, const mnr_buf* acc, const mnr_bits* mask, mnr_buf** out,
+               mnr_bits** out_mask) {
+    REQUIRE(c && a && b && acc, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(a->len == b->len, MNR_ERR_LENGTH_MISMATCH, "apply numeric: length mismatch (lhs: %zu, rhs: %zu)", a->len, b->len);
+    REQUIRE(a->len == acc->len, MNR_ERR_LENGTH_MISMATCH, "acc length mismatch (lhs: %zu, rhs: %zu)", a->len, acc->len);
+    int rc = alloc_outputs(c, a->dtype, a->len, mask != nullptr, out, out_mask);
+    if (rc) return rc;
+    return drop_outputs(mnr_ew_fma_into(c, a, b, acc, mask, *out, *out_mask), out, out_mask);
+}
+
+int mnr_ew_binary_promote(mnr_ctx* c, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lm,
+                          const mnr_bits* rm, mnr_mask_mode mode, mnr_buf** out, mnr_bits** out_mask) {
+    REQUIRE(c && lhs && rhs, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(op >= MNR_ADD && op <= MNR_FLOORDIV, MNR_ERR_OPERATOR_MISMATCH, "unknown operator %d", (int)op);
+    REQUIRE(lhs->len == rhs->len, MNR_ERR_LENGTH_MISMATCH, "arithmetic_dispatch => Length mismatch: LHS %zu RHS %zu",
+            lhs->len, rhs->len);
+    if (lhs->dtype == rhs->dtype) return mnr_ew_binary(c, op, lhs, rhs, lm, rm, mode, out, out_mask);
+    mnr_dtype ot;
+    const mnr_dtype l = lhs->dtype, r = rhs->dtype;
+    if ((l == MNR_I32 && r == MNR_F64) || (l == MNR_F64 && r == MNR_I32)) ot = MNR_F64;
+    else if ((l == MNR_I32 && r == MNR_F32) || (l == MNR_F32 && r == MNR_I32)) ot = MNR_F32;
+    else return fail(MNR_ERR_UNSUPPORTED_TYPE, "Unsupported array type combination for arithmetic operations (dtypes %d, %d)",
+                     (int)l, (int)r);
+    int rc = check_masks(lm, rm, lhs->len);
+    if (rc) return rc;
+    rc = alloc_outputs(c, ot, lhs->len, lm || rm, out, out_mask);
+    if (rc) return rc;
+    EwArgs a{};
+    a.dtype = ot; a.op = op; a.lhs = lhs->ptr; a.rhs = rhs->ptr;
+    a.lmask = lm ? lm->ptr : nullptr; a.rmask = rm ? rm->ptr : nullptr; a.mask_or = mode == MNR_MASK_OR;
+    a.out = (*out)->ptr; a.out_mask = (lm || rm) ? (*out_mask)->ptr : nullptr; a.n = lhs->len;
+    return drop_outputs(run_ew(c, a, c->stream, true, l, r), out, out_mask);
+}
+
+// ---- bitmask kernels ------------------------------------------------------------------------------------------------
+static int check_window(const mnr_bits* m, uint64_t pos, size_t len, const char* what) {
+    REQUIRE((pos >> 3) + mask_bytes(len) <= mask_bytes(m->len) || len == 0, MNR_ERR_OUT_OF_BOUNDS,
+            "%s: window [%llu, +%zu) leaves the %zu-bit mask", what, (unsigned long long)pos, len, m->len);
+    return MNR_OK;
+}
+
+int mnr_bits_binop_into(mnr_ctx* c, mnr_logical_op op, const mnr_bits* lhs, size_t lo, const mnr_bits* rhs, size_t ro,
+                        size_t len, mnr_bits* out) {
+    REQUIRE(c && lhs && rhs && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(op >= MNR_AND && op <= MNR_XOR, MNR_ERR_OPERATOR_MISMATCH, "unknown logical operator %d", (int)op);
+    REQUIRE(out->len == len, MNR_ERR_INVALID_ARGUMENTS, "output mask has %zu bits, need %zu", out->len, len);
+    const uint64_t lp = (uint64_t)(lo / 8) * 8, rp = (uint64_t)(ro / 8) * 8;   // bitmask_window_bytes floors to bytes
+    int rc = check_window(lhs, lp, len, "bitmask_binop lhs");
+    if (rc) return rc;
+    rc = check_window(rhs, rp, len, "bitmask_binop rhs");
+    if (rc) return rc;
+    if (len == 0) return MNR_OK;
+    CU(cudaSetDevice(c->device));
+    CU(launch_bits_op((int)op, lhs->ptr, lp, lhs->len, rhs->ptr, rp, rhs->len, len, out->ptr, c->stream));
+    c->launches++;
+    return MNR_OK;
+}
+
+int mnr_bits_binop(mnr_ctx* c, mnr_logical_op op, const mnr_bits* lhs, size_t lo, const mnr_bits* rhs, size_t ro,
+                   size_t len, mnr_bits** out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    *out = nullptr;
+    int rc = mnr_bits_alloc(c, len, out);
+    if (rc) return rc;
+    rc = mnr_bits_binop_into(c, op, lhs, lo, rhs, ro, len, *out);
+    if (rc) { mnr_bits_free(*out); *out = nullptr; }
+    return rc;
+}
+
+int mnr_bits_not_into(mnr_ctx* c, const mnr_bits* src, size_t off, size_t len, mnr_bits* out) {
+    REQUIRE(c && src && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(out->len == len, MNR_ERR_INVALID_ARGUMENTS, "output mask has %zu bits, need %zu", out->len, len);
+    const uint64_t sp = (uint64_t)(off / 8) * 8;
+    int rc = check_window(src, sp, len, "bitmask_unop");
+    if (rc) return rc;
+    if (len == 0) return MNR_OK;
+    CU(cudaSetDevice(c->device));
+    CU(launch_bits_op(4, src->ptr, sp, src->len, nullptr, 0, 0, len, out->ptr, c->stream));
+    c->launches++;
+    return MNR_OK;
+}
+
+int mnr_bits_not(mnr_ctx* c, const mnr_bits* src, size_t off, size_t len, mnr_bits** out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    *out = nullptr;
+    int rc = mnr_bits_alloc(c, len, out);
+    if (rc) return rc;
+    rc = mnr_bits_not_into(c, src, off, len, *out);
+    if (rc) { mnr_bits_free(*out); *out = nullptr; }
+    return rc;
+}
+
+static int popcount_sync(mnr_ctx* c, const mnr_bits* a, uint64_t ap, const mnr_bits* b, uint64_t bp, size_t len,
+                         uint64_t* ones) {
+    CU(cudaSetDevice(c->device));
+    if (len == 0) { *ones = 0; return MNR_OK; }
+    CU(cudaMemsetAsync(c->d_count, 0, 8, c->stream));
+    CU(launch_bits_popcount(a->ptr, ap, a->len, b ? b->ptr : nullptr, bp, b ? b->len : 0, len, c->d_count, c->stream));
+    c->launches++;
+    unsigned long long* h = static_cast<unsigned long long*>(c->h_scratch);
+    CU(cudaMemcpyAsync(h, c->d_count, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *ones = *h;
+    return MNR_OK;
+}
+
+int mnr_bits_popcount(mnr_ctx* c, const mnr_bits* m, size_t off, size_t len, uint64_t* ones) {
+    REQUIRE(c && m && ones, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    const uint64_t p = (uint64_t)(off / 64) * 64;   // popcount_mask_simd: word_start = offset / 64
+    int rc = check_window(m, p, len, "popcount_mask");
+    if (rc) return rc;
+    return popcount_sync(c, m, p, nullptr, 0, len, ones);
+}
+
+int mnr_bits_all_true(mnr_ctx* c, const mnr_bits* m, int* out) {
+    REQUIRE(c && m && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    uint64_t ones = 0;
+    int rc = popcount_sync(c, m, 0, nullptr, 0, m->len, &ones);
+    if (rc) return rc;
+    *out = ones == m->len;
+    return MNR_OK;
+}
+int mnr_bits_all_false(mnr_ctx* c, const mnr_bits* m, int* out) {
+    REQUIRE(c && m && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    uint64_t ones = 0;
+    int rc = popcount_sync(c, m, 0, nullptr, 0, m->len, &ones);
+    if (rc) return rc;
+    *out = ones == 0;
+    return MNR_OK;
+}
+
+int mnr_bits_merge(mnr_ctx* c, const mnr_bits* lhs, const mnr_bits* rhs, size_t len, mnr_mask_mode mode, mnr_bits** out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    *out = nullptr;
+    if (!lhs && !rhs) return MNR_OK;
+    int rc = check_masks(lhs, rhs, len);
+    if (rc) return rc;
+    rc = mnr_bits_alloc(c, len, out);
+    if (rc) return rc;
+    if (len == 0) return MNR_OK;
+    CU(cudaSetDevice(c->device));
+    if (lhs && rhs)
+        CU(launch_bits_op(mode == MNR_MASK_OR ? 1 : 0, lhs->ptr, 0, lhs->len, rhs->ptr, 0, rhs->len, len, (*out)->ptr, c->stream));
+    else {
+        const mnr_bits* m = lhs ? lhs : rhs;
+        CU(launch_bits_op(5, m->ptr, 0, m->len, nullptr, 0, 0, len, (*out)->ptr, c->stream));
+    }
+    c->launches++;
+    return MNR_OK;
+}
+
+int mnr_bits_eq(mnr_ctx* c, const mnr_bits* a, size_t ao, const mnr_bits* b, size_t bo, size_t len, int negate,
+                mnr_bits** out) {
+    REQUIRE(c && a && b && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    *out = nullptr;
+    if (len == 0) return mnr_bits_alloc(c, 0, out);
+    REQUIRE(ao % 64 == 0 && bo % 64 == 0, MNR_ERR_INVALID_ARGUMENTS,
+            "eq_bits_mask: offsets must be 64-bit aligned (got a: %zu, b: %zu)", ao, bo);
+    int rc = check_window(a, ao, len, "eq_mask a");
+    if (rc) return rc;
+    rc = check_window(b, bo, len, "eq_mask b");
+    if (rc) return rc;
+    rc = mnr_bits_alloc(c, len, out);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    CU(launch_bits_op(negate ? 2 : 3, a->ptr, ao, a->len, b->ptr, bo, b->len, len, (*out)->ptr, c->stream));
+    c->launches++;
+    return MNR_OK;
+}
+
+int mnr_bits_all_eq(mnr_ctx* c, const mnr_bits* a, size_t ao, const mnr_bits* b, size_t bo, size_t len, int* out) {
+    REQUIRE(c && a && b && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    if (len == 0) { *out = 1; return MNR_OK; }
+    REQUIRE(len < 64 || (ao % 64 == 0 && bo % 64 == 0), MNR_ERR_INVALID_ARGUMENTS,
+            "all_eq_mask_simd: offsets must be 64-bit aligned (got a: %zu, b: %zu)", ao, bo);
+    const uint64_t ap = (uint64_t)(ao / 64) * 64, bp = (uint64_t)(bo / 64) * 64;
+    int rc = check_window(a, ap, len, "all_eq a");
+    if (rc) return rc;
+    rc = check_window(b, bp, len, "all_eq b");
+    if (rc) return rc;
+    uint64_t diff = 0;
+    rc = popcount_sync(c, a, ap, b, bp, len, &diff);
+    if (rc) return rc;
+    *out = diff == 0;
+    return MNR_OK;
+}
+
+int mnr_bits_in(mnr_ctx* c, const mnr_bits* lhs, size_t lo, const mnr_bits* rhs, size_t ro, size_t len, int negate,
+                mnr_bits** out) {
+    REQUIRE(c && lhs && rhs && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    *out = nullptr;
+    if (len == 0) return mnr_bits_alloc(c, 0, out);
+    const uint64_t rp = (uint64_t)(ro / 64) * 64;
+    int rc = check_window(rhs, rp, len, "in_mask rhs");
+    if (rc) return rc;
+    uint64_t ones = 0;
+    rc = popcount_sync(c, rhs, rp, nullptr, 0, len, &ones);
+    if (rc) return rc;
+    const bool has_true = ones != 0, has_false = ones != len;
+    mnr_bits* r = nullptr;
+    if (has_true && has_false) rc = mnr_bits_new_set_all(c, len, 1, &r);
+    else if (has_true) {   // lhs.slice_clone(lhs_off, len): exact bit offset (bitmask.rs:604-626)
+        rc = check_window(lhs, lo, len, "in_mask lhs");
+        if (!rc) rc = mnr_bits_alloc(c, len, &r);
+        if (!rc) {
+            CU(launch_bits_op(5, lhs->ptr, lo, lhs->len, nullptr, 0, 0, len, r->ptr, c->stream));
+            c->launches++;
+        }
+    } else rc = mnr_bits_not(c, lhs, lo, len, &r);
+    if (rc) { mnr_bits_free(r); return rc; }
+    if (negate) {   // not_in_mask = not_mask(in_mask)
+        mnr_bits* nr = nullptr;
+        rc = mnr_bits_not(c, r, 0, len, &nr);
+        mnr_bits_free(r);
+        if (rc) return rc;
+        r = nr;
+    }
+    *out = r;
+    return MNR_OK;
+}
+
+// ---- reductions ------------------------------------------------------------------------------------------------------
+static int check_reduce(const mnr_ctx* c, const mnr_buf* b, const mnr_bits* v) {
+    REQUIRE(c && b, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(!v || v->len >= b->len, MNR_ERR_INVALID_ARGUMENTS, "validity has %zu bits, need %zu", v->len, b->len);
+    return MNR_OK;
+}
+
+int mnr_reduce_stats_async(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, int with_minmax, void* out_device) {
+    int rc = check_reduce(c, b, v);
+    if (rc) return rc;
+    REQUIRE(out_device && (reinterpret_cast<uintptr_t>(out_device) & 15u) == 0, MNR_ERR_INVALID_ARGUMENTS,
+            "out_device must be a 16-byte aligned device pointer");
+    CU(cudaSetDevice(c->device));
+    CU(launch_reduce_stats(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, with_minmax != 0, c->partials[3], c->ticket[3],
+                           static_cast<AggRaw*>(out_device), c->stream));
+    c->launches++;
+    return MNR_OK;
+}
+
+static int reduce_sync(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, bool minmax, mnr_agg* out) {
+    int rc = mnr_reduce_stats_async(c, b, v, minmax, c->d_agg);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_scratch, c->d_agg, sizeof(AggRaw), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_scratch, sizeof(mnr_agg));
+    return MNR_OK;
+}
+
+int mnr_reduce_stats(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, mnr_agg* out_host) {
+    REQUIRE(out_host, MNR_ERR_INVALID_ARGUMENTS, "out is NULL");
+    return reduce_sync(c, b, v, true, out_host);
+}
+
+int mnr_reduce_sum(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, mnr_scalar64* out_sum, uint64_t* out_count) {
+    REQUIRE(out_sum, MNR_ERR_INVALID_ARGUMENTS, "out_sum is NULL");
+    mnr_agg a;
+    int rc = reduce_sync(c, b, v, false, &a);
+    if (rc) return rc;
+    *out_sum = a.sum;
+    if (out_count) *out_count = a.count;
+    return MNR_OK;
+}
+
+static int dtype_kind(mnr_dtype dt) {   // 0 signed, 1 unsigned, 2 float
+    switch (dt) {
+        case MNR_F32: case MNR_F64: return 2;
+        case MNR_U8: case MNR_U16: case MNR_U32: case MNR_U64: return 1;
+        default: return 0;
+    }
+}
+
+double mnr_agg_mean(mnr_dtype dtype, const mnr_agg* a) {
+    if (!a || a->count == 0) return std::numeric_limits<double>::quiet_NaN();
+    const int k = dtype_kind(dtype);
+    const double s = k == 2 ? a->sum.f64 : k == 1 ? (double)a->sum.u64 : (double)a->sum.i64;
+    return s / (double)a->count;
+}
+
+static double fmin_skip(double a, double b) {
+    if (b != b) return a;
+    if (a != a) return b;
+    if (b < a) return b;
+    if (b == a && std::signbit(b)) return b;
+    return a;
+}
+static double fmax_skip(double a, double b) {
+    if (b != b) return a;
+    if (a != a) return b;
+    if (b > a) return b;
+    if (b == a && !std::signbit(b)) return b;
+    return a;
+}
+
+int mnr_agg_combine(mnr_dtype dtype, const mnr_agg* p, size_t n, mnr_agg* out) {
+    REQUIRE(out && (p || n == 0), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(n >= 1, MNR_ERR_INVALID_ARGUMENTS, "need at least one partial (identities are dtype-specific)");
+    const int k = dtype_kind(dtype);
+    mnr_agg r = p[0];
+    for (size_t i = 1; i < n; ++i) {
+        r.count += p[i].count;
+        if (k == 2) {
+            r.sum.f64 = r.sum.f64 + p[i].sum.f64;   // index order: the documented rank-order add
+            r.min.f64 = fmin_skip(r.min.f64, p[i].min.f64);
+            r.max.f64 = fmax_skip(r.max.f64, p[i].max.f64);
+        } else if (k == 1) {
+            r.sum.u64 += p[i].sum.u64;
+            if (p[i].min.u64 < r.min.u64) r.min.u64 = p[i].min.u64;
+            if (p[i].max.u64 > r.max.u64) r.max.u64 = p[i].max.u64;
+        } else {
+            r.sum.u64 += p[i].sum.u64;   // wrapping
+            if (p[i].min.i64 < r.min.i64) r.min.i64 = p[i].min.i64;
+            if (p[i].max.i64 > r.max.i64) r.max.i64 = p[i].max.i64;
+        }
+    }
+    *out = r;
+    return MNR_OK;
+}
+
+// ---- host-slice drop-ins ---------------------------------------------------------------------------------------------
+// Chunks of `host_chunk_rows` rows cycle through 3 device staging slots, each with its own stream:
+// H2D(inputs) -> kernel -> D2H(outputs) are ordered inside a slot and overlap across slots, so the PCIe link
+// is busy in both directions while the kernels run.
+static int ensure_stage(mnr_ctx* c, size_t bytes_per_array) {
+    if (c->stage_bytes >= bytes_per_array) return MNR_OK;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 6; ++j) {
+            if (c->stage[i][j]) { CU(cudaFree(c->stage[i][j])); c->stage[i][j] = nullptr; }
+            // 0 lhs, 1 rhs, 2 acc, 3 out: full width; 4 mask, 5 out_mask: 1 bit per row (<= bytes/8 for 8-bit types)
+            CU(cudaMalloc(&c->stage[i][j], pad256(j < 4 ? bytes_per_array : bytes_per_array / 8 + 16)));
+        }
+    c->stage_bytes = bytes_per_array;
+    return MNR_OK;
+}
+
+static int sync_slots(mnr_ctx* c) {
+    for (int i = 0; i < 3; ++i) CU(cudaStreamSynchronize(c->slot_stream[i]));
+    return MNR_OK;
+}
+
+static int apply_host_impl(mnr_ctx* c, mnr_dtype dtype, int op, bool is_fma, const void* lhs, size_t lhs_len,
+                           const void* rhs, size_t rhs_len, const void* acc, size_t acc_len, const uint8_t* mask,
+                           void* out, uint8_t* out_mask) {
+    REQUIRE(c, MNR_ERR_INVALID_ARGUMENTS, "ctx is NULL");
+    REQUIRE(valid_dtype(dtype), MNR_ERR_UNSUPPORTED_TYPE, "unknown dtype %d", (int)dtype);
+    REQUIRE(lhs_len == rhs_len, MNR_ERR_LENGTH_MISMATCH, "apply numeric: length mismatch (lhs: %zu, rhs: %zu)", lhs_len, rhs_len);
+    if (is_fma) {
+        REQUIRE(lhs_len == acc_len, MNR_ERR_LENGTH_MISMATCH, "acc length mismatch (lhs: %zu, rhs: %zu)", lhs_len, acc_len);
+        REQUIRE(is_float_dtype(dtype), MNR_ERR_UNSUPPORTED_TYPE, "fma needs F32 or F64");
+    } else {
+        REQUIRE(op >= MNR_ADD && op <= MNR_FLOORDIV, MNR_ERR_OPERATOR_MISMATCH, "unknown operator %d", op);
+    }
+    const size_t n = lhs_len;
+    if (n == 0) return MNR_OK;
+    REQUIRE(lhs && rhs && out && (!is_fma || acc) && (!mask || out_mask), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const size_t es = dtype_size(dtype), chunk = c->host_chunk_rows;
+    int rc = ensure_stage(c, chunk * 8);
+    if (rc) return rc;
+    const bool dense_int_div = !mask && !is_fma && !is_float_dtype(dtype) && (op == MNR_DIV || op == MNR_REM || op == MNR_FLOORDIV);
+    unsigned int* flag = c->ticket[0] + 8;
+    if (dense_int_div) { CU(cudaMemsetAsync(flag, 0, 4, c->slot_stream[0])); CU(cudaStreamSynchronize(c->slot_stream[0])); }
+    size_t k = 0;
+    for (size_t r0 = 0; r0 < n; r0 += chunk, ++k) {
+        const int sl = (int)(k % 3);
+        cudaStream_t s = c->slot_stream[sl];
+        const size_t rows = n - r0 < chunk ? n - r0 : chunk;
+        void** st = c->stage[sl];
+        CU(cudaMemcpyAsync(st[0], static_cast<const char*>(lhs) + r0 * es, rows * es, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(st[1], static_cast<const char*>(rhs) + r0 * es, rows * es, cudaMemcpyHostToDevice, s));
+        if (is_fma) CU(cudaMemcpyAsync(st[2], static_cast<const char*>(acc) + r0 * es, rows * es, cudaMemcpyHostToDevice, s));
+        if (mask) CU(cudaMemcpyAsync(st[4], mask + r0 / 8, mask_bytes(rows), cudaMemcpyHostToDevice, s));
+        if (is_fma) {
+            CU(launch_ew_fma(dtype, st[0], st[1], st[2], mask ? static_cast<uint8_t*>(st[4]) : nullptr, st[3],
+                             mask ? static_cast<uint8_t*>(st[5]) : nullptr, rows, s));
+        } else {
+            EwArgs a{};
+            a.dtype = dtype; a.op = op; a.lhs = st[0]; a.rhs = st[1];
+            a.lmask = mask ? static_cast<uint8_t*>(st[4]) : nullptr;
+            a.out = st[3]; a.out_mask = mask ? static_cast<uint8_t*>(st[5]) : nullptr; a.n = rows; a.div0_flag = flag;
+            CU(launch_ew_binary(a, s));
+        }
+        c->launches++;
+        CU(cudaMemcpyAsync(static_cast<char*>(out) + r0 * es, st[3], rows * es, cudaMemcpyDeviceToHost, s));
+        if (mask) CU(cudaMemcpyAsync(out_mask + r0 / 8, st[5], mask_bytes(rows), cudaMemcpyDeviceToHost, s));
+    }
+    rc = sync_slots(c);
+    if (rc) return rc;
+    if (dense_int_div) {
+        unsigned int* h = static_cast<unsigned int*>(c->h_scratch);
+        CU(cudaMemcpy(h, flag, 4, cudaMemcpyDeviceToHost));
+        if (*h) return fail(MNR_ERR_DIVIDE_BY_ZERO, "%s by zero in dense integer kernel (the reference panics here)",
+                            op == MNR_DIV ? "Division" : op == MNR_REM ? "Remainder" : "Floor division");
+    }
+    return MNR_OK;
+}
+
+int mnr_apply_host(mnr_ctx* c, mnr_dtype dtype, mnr_op op, const void* lhs, size_t lhs_len, const void* rhs, size_t rhs_len,
+                   const uint8_t* mask, void* out, uint8_t* out_mask) {
+    return apply_host_impl(c, dtype, (int)op, false, lhs, lhs_len, rhs, rhs_len, nullptr, 0, mask, out, out_mask);
+}
+int mnr_apply_fma_host(mnr_ctx* c, mnr_dtype dtype, const void* lhs, size_t lhs_len, const void* rhs, size_t rhs_len,
+                       const void* acc, size_t acc_len, const uint8_t* mask, void* out, uint8_t* out_mask) {
+    return apply_host_impl(c, dtype, 0, true, lhs, lhs_len, rhs, rhs_len, acc, acc_len, mask, out, out_mask);
+}
+
+#define MNR_TYPED_APPLY(NAME, CT, DT)                                                                                  \
+    int NAME(mnr_ctx* c, const CT* lhs, size_t lhs_len, const CT* rhs, size_t rhs_len, mnr_op op, const uint8_t* mask, \
+             CT* out, uint8_t* out_mask) {                                                                             \
+        return mnr_apply_host(c, DT, op, lhs, lhs_len, rhs, rhs_len, mask, out, out_mask);                             \
+    }
+MNR_TYPED_APPLY(mnr_apply_int_i32, int32_t, MNR_I32)
+MNR_TYPED_APPLY(mnr_apply_int_u32, uint32_t, MNR_U32)
+MNR_TYPED_APPLY(mnr_apply_int_i64, int64_t, MNR_I64)
+MNR_TYPED_APPLY(mnr_apply_int_u64, uint64_t, MNR_U64)
+MNR_TYPED_APPLY(mnr_apply_float_f32, float, MNR_F32)
+MNR_TYPED_APPLY(mnr_apply_float_f64, double, MNR_F64)
+#undef MNR_TYPED_APPLY
+
+int mnr_stats_host(mnr_ctx* c, mnr_dtype dtype, const void* data, size_t len, const uint8_t* validity, int with_minmax,
+                   mnr_agg* out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(valid_dtype(dtype), MNR_ERR_UNSUPPORTED_TYPE, "unknown dtype %d", (int)dtype);
+    REQUIRE(data || len == 0, MNR_ERR_INVALID_ARGUMENTS, "data is NULL");
+    CU(cudaSetDevice(c->device));
+    const size_t es = dtype_size(dtype), chunk = c->host_chunk_rows;
+    const size_t nchunks = len ? (len + chunk - 1) / chunk : 1;
+    int rc = ensure_stage(c, chunk * 8);
+    if (rc) return rc;
+    if (c->chunk_aggs_cap < nchunks) {
+        if (c->chunk_aggs) CU(cudaFree(c->chunk_aggs));
+        CU(cudaMalloc(&c->chunk_aggs, sizeof(AggRaw) * nchunks));
+        c->chunk_aggs_cap = nchunks;
+    }
+    for (size_t k = 0; k < nchunks; ++k) {
+        const int sl = (int)(k % 3);
+        cudaStream_t s = c->slot_stream[sl];
+        const size_t r0 = k * chunk;
+        const size_t rows = len - r0 < chunk ? len - r0 : chunk;
+        void** st = c->stage[sl];
+        if (rows) {
+            CU(cudaMemcpyAsync(st[0], static_cast<const char*>(data) + r0 * es, rows * es, cudaMemcpyHostToDevice, s));
+            if (validity) CU(cudaMemcpyAsync(st[4], validity + r0 / 8, mask_bytes(rows), cudaMemcpyHostToDevice, s));
+        }
+        CU(launch_reduce_stats(dtype, st[0], validity ? static_cast<uint8_t*>(st[4]) : nullptr, rows, with_minmax != 0,
+                               c->partials[sl], c->ticket[sl], c->chunk_aggs + k, s));
+        c->launches++;
+    }
+    rc = sync_slots(c);
+    if (rc) return rc;
+    std::vector<mnr_agg> parts(nchunks);
+    CU(cudaMemcpy(parts.data(), c->chunk_aggs, sizeof(mnr_agg) * nchunks, cudaMemcpyDeviceToHost));
+    return mnr_agg_combine(dtype, parts.data(), nchunks, out);
+}
+
+int mnr_bitmask_binop_host(mnr_ctx* c, mnr_logical_op op, const uint8_t* lhs, size_t lo, const uint8_t* rhs, size_t ro,
+                           size_t len, uint8_t* out) {
+    REQUIRE(c, MNR_ERR_INVALID_ARGUMENTS, "ctx is NULL");
+    REQUIRE(op >= MNR_AND && op <= MNR_XOR, MNR_ERR_OPERATOR_MISMATCH, "unknown logical operator %d", (int)op);
+    if (len == 0) return MNR_OK;
+    REQUIRE(lhs && rhs && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const uint8_t *lp = lhs + lo / 8, *rp = rhs + ro / 8;   // byte-floored window starts
+    const size_t chunk_bits = c->host_chunk_rows * 8;        // multiple of 8192 bits
+    int rc = ensure_stage(c, c->host_chunk_rows * 8);
+    if (rc) return rc;
+    size_t k = 0;
+    for (size_t b0 = 0; b0 < len; b0 += chunk_bits, ++k) {
+        const int sl = (int)(k % 3);
+        cudaStream_t s = c->slot_stream[sl];
+        const size_t bits = len - b0 < chunk_bits ? len - b0 : chunk_bits;
+        void** st = c->stage[sl];
+        CU(cudaMemcpyAsync(st[0], lp + b0 / 8, mask_bytes(bits), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(st[1], rp + b0 / 8, mask_bytes(bits), cudaMemcpyHostToDevice, s));
+        CU(launch_bits_op((int)op, static_cast<uint8_t*>(st[0]), 0, bits, static_cast<uint8_t*>(st[1]), 0, bits, bits,
+                          static_cast<uint8_t*>(st[3]), s));
+        c->launches++;
+        CU(cudaMemcpyAsync(out + b0 / 8, st[3], mask_bytes(bits), cudaMemcpyDeviceToHost, s));
+    }
+    return sync_slots(c);
+}
+
+int mnr_host_register(void* ptr, size_t bytes) {
+    REQUIRE(ptr && bytes, MNR_ERR_INVALID_ARGUMENTS, "NULL/empty range");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return MNR_OK;
+}
+int mnr_host_unregister(void* ptr) {
+    REQUIRE(ptr, MNR_ERR_INVALID_ARGUMENTS, "NULL pointer");
+    CU(cudaHostUnregister(ptr));
+    return MNR_OK;
+}
+int mnr_host_alloc(size_t bytes, void** out) {
+    REQUIRE(out, MNR_ERR_INVALID_ARGUMENTS, "out is NULL");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return MNR_OK;
+}
+void mnr_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+// Null-aware element-wise arithmetic in one HBM pass.
+//
+// Replaces int_dense_body / int_masked_body / float_dense_body / float_masked_body / fma bodies
+// (src/kernels/arithmetic/simd.rs:52-751, std.rs:41-230) and, fused in, the caller-side validity merge
+// (merge_bitmasks_to_new, src/kernels/bitmask/mod.rs:171-197; Bitmask::union, src/structs/bitmask.rs:661-669)
+// and the scalar broadcast that the reference materialises (routing/broadcast.rs:25-47).
+//
+// Mapping: a lane owns one 16-byte vector (2 x 64-bit or 4 x 32-bit rows); a warp owns 32*U consecutive
+// vectors, so each load/store instruction of a warp covers 512 contiguous bytes and the U output validity
+// bytes-groups of a warp are contiguous.  Validity is read as the byte holding the lane's rows and written
+// by one lane per byte after a shuffle gather — never a read-modify-write as in write_simd_mask_bits
+// (src/utils.rs:255-283), never more than ceil(len/8) bytes.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace mnr {
+
+enum { CLS_CHEAP = 0, CLS_DIV = 1, CLS_POW = 2, CLS_REM = 3 };
+
+__host__ __device__ constexpr int op_class(bool is_float, int op) {
+    return (op == MNR_ADD || op == MNR_SUB || op == MNR_MUL) ? CLS_CHEAP
+           : (op == MNR_POW)                                  ? CLS_POW
+           : (is_float && op == MNR_REM)                      ? CLS_REM
+                                                              : CLS_DIV;
+}
+
+// ---- one element ---------------------------------------------------------------------------------------
+// Integers: Add/Sub/Mul wrap; Div/Rem truncate, FloorDiv per std.rs:68-77; MIN / -1 = MIN and
+// MIN % -1 = 0 (core::simd's guard; DESIGN.md assumption); zero divisor => ok = false, value 0.
+// Power: exponent = rhs.to_u32().unwrap_or(0) (std.rs:67), wrapping repeated multiply (simd.rs:94-100)
+// evaluated by squaring — same residue mod 2^bits.
+template <typename T, int CLS>
+__device__ __forceinline__ T int_elem(int op, T l, T r, bool& ok) {
+    using UT = typename std::make_unsigned<T>::type;
+    ok = true;
+    if constexpr (CLS == CLS_CHEAP) {
+        const UT a = (UT)l, b = (UT)r;
+        return (T)(UT)(op == MNR_ADD ? a + b : op == MNR_SUB ? a - b : a * b);
+    } else if constexpr (CLS == CLS_DIV) {
+        if (r == 0) { ok = false; return 0; }
+        if constexpr (std::is_signed<T>::value) {
+            if (l == (T)((UT)1 << (sizeof(T) * 8 - 1)) && r == (T)-1) return op == MNR_REM ? (T)0 : l;
+        }
+        const T q = (T)(l / r);
+        const T m = (T)(l - (T)((UT)q * (UT)r));
+        if (op == MNR_DIV) return q;
+        if (op == MNR_REM) return m;
+        if constexpr (std::is_signed<T>::value) {
+            if (m != 0 && ((l ^ r) < 0)) return (T)((UT)q - 1);
+        }
+        return q;
+    } else {
+        uint32_t e;
+        if constexpr (std::is_signed<T>::value) e = (r < 0 || (uint64_t)r > 0xFFFFFFFFull) ? 0u : (uint32_t)r;
+        else e = ((uint64_t)r > 0xFFFFFFFFull) ? 0u : (uint32_t)r;
+        UT base = (UT)l, acc = 1;
+        while (e) {
+            if (e & 1u) acc = (UT)(acc * base);
+            base = (UT)(base * base);
+            e >>= 1;
+        }
+        return (T)acc;
+    }
+}
+
+// Floats: single IEEE operations, no contraction (the TU is built with -fmad=false), `%` = fmod,
+// Power = exp(b * ln a), FloorDiv = floor(a / b)  (std.rs:144-157).
+template <typename T, int CLS>
+__device__ __forceinline__ T float_elem(int op, T a, T b) {
+    if constexpr (CLS == CLS_CHEAP) {
+        return op == MNR_ADD ? a + b : op == MNR_SUB ? a - b : a * b;
+    } else if constexpr (CLS == CLS_DIV) {
+        const T q = a / b;
+        return op == MNR_DIV ? q : floor(q);
+    } else if constexpr (CLS == CLS_REM) {
+        return fmod(a, b);
+    } else {
+        return exp(b * log(a));
+    }
+}
+
+template <typename T, int CLS>
+__device__ __forceinline__ T elem(int op, T l, T r, bool& ok) {
+    if constexpr (Traits<T>::is_float) { ok = true; return float_elem<T, CLS>(op, l, r); }
+    else return int_elem<T, CLS>(op, l, r, ok);
+}
+
+// ---- validity helpers ------------------------------------------------------------------------------------
+// Guarded variant of load_valid_bits: only bytes that hold rows < n are touched.
+template <int NBITS>
+__device__ __forceinline__ uint32_t load_valid_bits_guard(const uint8_t* __restrict__ mask, uint64_t row0, uint64_t n) {
+    if (row0 >= n) return 0;
+    uint32_t bits;
+    if constexpr (NBITS <= 8) {
+        bits = (ldg_u8(mask + (row0 >> 3)) >> (uint32_t)(row0 & 7)) & ((1u << NBITS) - 1u);
+    } else {
+        bits = 0;
+        const uint8_t* p = mask + (row0 >> 3);
+#pragma unroll
+        for (int j = 0; j < NBITS / 8; ++j)
+            if (row0 + 8ull * j < n) bits |= ldg_u8(p + j) << (8 * j);
+    }
+    const uint64_t left = n - row0;
+    if (left < NBITS) bits &= (1u << (uint32_t)left) - 1u;
+    return bits;
+}
+
+// Gather the per-lane validity bits of a warp into bytes and store them.  VEC rows per lane; lanes hold
+// consecutive row groups starting at a multiple of 32*VEC rows.  `row0` is the lane's first row; lanes whose
+// rows are all >= n pass bits = 0 and store nothing.
+template <int VEC>
+__device__ __forceinline__ void store_valid_bits(uint8_t* __restrict__ out_mask, uint64_t row0, uint64_t n, uint32_t bits) {
+    if constexpr (VEC < 8) {
+        constexpr int LPB = 8 / VEC;   // lanes per output byte
+        uint32_t x = bits;
+#pragma unroll
+        for (int s = 1; s < LPB; s <<= 1) x |= __shfl_down_sync(0xffffffffu, x, s) << (VEC * s);
+        if (((threadIdx.x & 31) % LPB) == 0 && row0 < n) out_mask[row0 >> 3] = (uint8_t)x;
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC / 8; ++j)
+            if (row0 + 8ull * j < n) out_mask[(row0 >> 3) + j] = (uint8_t)(bits >> (8 * j));
+    }
+}
+
+template <typename T, typename VecT> struct VecU {
+    static constexpr int VEC = sizeof(VecT) / sizeof(T);
+    union { VecT v; T e[VEC]; };
+};
+
+struct EwDev {
+    const void* lhs;
+    const void* rhs;
+    uint64_t scalar_bits;
+    const uint8_t* lmask;
+    const uint8_t* rmask;
+    int mask_or;
+    void* out;
+    uint8_t* out_mask;
+    uint64_t n;
+    unsigned int* div0_flag;
+    int op;
+};
+
+template <typename T> __device__ __forceinline__ T scalar_from_bits(uint64_t b) {
+    T v;
+    memcpy(&v, &b, sizeof(T));   // little-endian: the low bytes hold the element
+    return v;
+}
+
+template <int VEC, bool GUARD>
+__device__ __forceinline__ uint32_t merged_bits(const EwDev& a, uint64_t row0) {
+    uint32_t m;
+    if (a.lmask && a.rmask) {
+        const uint32_t x = GUARD ? load_valid_bits_guard<VEC>(a.lmask, row0, a.n) : load_valid_bits<VEC>(a.lmask, row0);
+        const uint32_t y = GUARD ? load_valid_bits_guard<VEC>(a.rmask, row0, a.n) : load_valid_bits<VEC>(a.rmask, row0);
+        m = a.mask_or ? (x | y) : (x & y);
+    } else {
+        const uint8_t* p = a.lmask ? a.lmask : a.rmask;
+        m = GUARD ? load_valid_bits_guard<VEC>(p, row0, a.n) : load_valid_bits<VEC>(p, row0);
+    }
+    return m;
+}
+
+// Element-wise binary kernel.  TL/TR: stored operand types (== T except for the cast-on-load promotion).
+template <typename T, typename TL, typename TR, typename VecT, int CLS, bool MASKED, int BLOCK, int U>
+__global__ void __launch_bounds__(BLOCK) ew_binary_kernel(const EwDev a) {
+    constexpr int VEC = sizeof(VecT) / sizeof(T);
+    // Operand vectors carry VEC elements of their own (possibly narrower) type.
+    struct alignas(sizeof(TL) * VEC) LV { TL e[VEC]; };
+    struct alignas(sizeof(TR) * VEC) RV { TR e[VEC]; };
+    using LVec = typename std::conditional<std::is_same<TL, T>::value, VecT, LV>::type;
+    using RVec = typename std::conditional<std::is_same<TR, T>::value, VecT, RV>::type;
+
+    const LVec* __restrict__ lp = static_cast<const LVec*>(a.lhs);
+    const RVec* __restrict__ rp = static_cast<const RVec*>(a.rhs);
+    VecT* __restrict__ op_ = static_cast<VecT*>(a.out);
+    const int op = a.op;
+    const uint64_t n = a.n;
+    const uint64_t nvec_full = n / VEC;
+    constexpr uint64_t WTILE = 32ull * U;
+    const uint64_t ntiles = nvec_full / WTILE;
+    const uint64_t warps = (uint64_t)gridDim.x * (BLOCK / 32);
+    const uint64_t gwarp = (uint64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const T sval = scalar_from_bits<T>(a.scalar_bits);
+    bool div0 = false;
+
+    for (uint64_t t = gwarp; t < ntiles; t += warps) {
+        const uint64_t v0 = t * WTILE + lane;
+        union LU { LVec v; TL e[VEC]; } L[U];
+        union RU { RVec v; TR e[VEC]; } R[U];
+        uint32_t mb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (lp) L[u].v = ldg_stream(lp + v0 + 32ull * u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (rp) R[u].v = ldg_stream(rp + v0 + 32ull * u);
+        if constexpr (MASKED) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) mb[u] = merged_bits<VEC, false>(a, (v0 + 32ull * u) * VEC);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            VecU<T, VecT> O;
+            uint32_t ob = 0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const T l = lp ? (T)L[u].e[k] : sval;
+                const T r = rp ? (T)R[u].e[k] : sval;
+                bool ok;
+                const T val = elem<T, CLS>(op, l, r, ok);
+                if constexpr (MASKED) {
+                    const bool valid = ((mb[u] >> k) & 1u) && ok;
+                    O.e[k] = valid ? val : (T)0;
+                    ob |= (uint32_t)valid << k;
+                } else {
+                    O.e[k] = val;
+                    div0 |= !ok;
+                }
+            }
+            stg_stream(op_ + v0 + 32ull * u, O.v);
+            if constexpr (MASKED) store_valid_bits<VEC>(a.out_mask, (v0 + 32ull * u) * VEC, n, ob);
+        }
+    }
+
+    // Guarded remainder: vectors past the last full warp tile, including a final partial vector.
+    const uint64_t nvec_ceil = (n + VEC - 1) / VEC;
+    for (uint64_t vb = ntiles * WTILE + gwarp * 32ull; vb < nvec_ceil; vb += warps * 32ull) {
+        const uint64_t v = vb + lane;
+        const uint64_t row0 = v * VEC;
+        const int nrows = row0 >= n ? 0 : (n - row0 >= (uint64_t)VEC ? VEC : (int)(n - row0));
+        VecU<T, VecT> O;
+        uint32_t ob = 0;
+        if (nrows > 0) {
+            union LU { LVec v; TL e[VEC]; } L;
+            union RU { RVec v; TR e[VEC]; } R;
+            if (nrows == VEC) {
+                if (lp) L.v = ldg_stream(lp + v);
+                if (rp) R.v = ldg_stream(rp + v);
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    if (k < nrows) {
+                        if (lp) L.e[k] = static_cast<const TL*>(a.lhs)[row0 + k];
+                        if (rp) R.e[k] = static_cast<const TR*>(a.rhs)[row0 + k];
+                    } else {
+                        if (lp) L.e[k] = (TL)1;
+                        if (rp) R.e[k] = (TR)1;
+                    }
+                }
+            }
+            uint32_t m = 0;
+            if constexpr (MASKED) m = merged_bits<VEC, true>(a, row0);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const T l = lp ? (T)L.e[k] : sval;
+                const T r = rp ? (T)R.e[k] : sval;
+                bool ok;
+                const T val = elem<T, CLS>(op, l, r, ok);
+                if constexpr (MASKED) {
+                    const bool valid = ((m >> k) & 1u) && ok && k < nrows;
+                    O.e[k] = valid ? val : (T)0;
+                    ob |= (uint32_t)valid << k;
+                } else {
+                    O.e[k] = val;
+                    if (k < nrows) div0 |= !ok;
+                }
+            }
+            if (nrows == VEC) stg_stream(op_ + v, O.v);
+            else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) if (k < nrows) static_cast<T*>(a.out)[row0 + k] = O.e[k];
+            }
+        }
+        if constexpr (MASKED) store_valid_bits<VEC>(a.out_mask, row0, n, ob);
+    }
+    if constexpr (!MASKED && !Traits<T>::is_float && CLS == CLS_DIV) {
+        if (div0) *a.div0_flag = 1u;
+    }
+}
+
+// FMA: out = fma(a, b, c) with one rounding (apply_fma_*, dispatch.rs:211-290; simd.rs:620,714).
+template <typename T, typename VecT, bool MASKED, int BLOCK, int U>
+__global__ void __launch_bounds__(BLOCK)
+ew_fma_kernel(const T* __restrict__ pa, const T* __restrict__ pb, const T* __restrict__ pc,
+              const uint8_t* __restrict__ mask, T* __restrict__ out, uint8_t* __restrict__ out_mask, uint64_t n) {
+    constexpr int VEC = sizeof(VecT) / sizeof(T);
+    const VecT* __restrict__ va = reinterpret_cast<const VecT*>(pa);
+    const VecT* __restrict__ vb_ = reinterpret_cast<const VecT*>(pb);
+    const VecT* __restrict__ vc = reinterpret_cast<const VecT*>(pc);
+    VecT* __restrict__ vo = reinterpret_cast<VecT*>(out);
+    const uint64_t nvec_ceil = (n + VEC - 1) / VEC;
+    const uint64_t warps = (uint64_t)gridDim.x * (BLOCK / 32);
+    const uint64_t gwarp = (uint64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    constexpr uint64_t WTILE = 32ull * U;
+    const uint64_t ntiles = (n / VEC) / WTILE;
+    for (uint64_t t = gwarp; t < ntiles; t += warps) {
+        const uint64_t v0 = t * WTILE + lane;
+        VecU<T, VecT> A[U], B[U], C[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            A[u].v = ldg_stream(va + v0 + 32ull * u);
+            B[u].v = ldg_stream(vb_ + v0 + 32ull * u);
+            C[u].v = ldg_stream(vc + v0 + 32ull * u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t row0 = (v0 + 32ull * u) * VEC;
+            uint32_t m = 0;
+            if constexpr (MASKED) m = load_valid_bits<VEC>(mask, row0);
+            VecU<T, VecT> O;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const T val = fma(A[u].e[k], B[u].e[k], C[u].e[k]);
+                O.e[k] = (!MASKED || ((m >> k) & 1u)) ? val : (T)0;
+            }
+            stg_stream(vo + v0 + 32ull * u, O.v);
+            if constexpr (MASKED) store_valid_bits<VEC>(out_mask, row0, n, m);
+        }
+    }
+    for (uint64_t vb0 = ntiles * WTILE + gwarp * 32ull; vb0 < nvec_ceil; vb0 += warps * 32ull) {
+        const uint64_t v = vb0 + lane, row0 = v * VEC;
+        uint32_t m = 0;
+        if constexpr (MASKED) m = load_valid_bits_guard<VEC>(mask, row0, n);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            if (row0 + k < n) {
+                const T val = fma(pa[row0 + k], pb[row0 + k], pc[row0 + k]);
+                out[row0 + k] = (!MASKED || ((m >> k) & 1u)) ? val : (T)0;
+            }
+        }
+        if constexpr (MASKED) store_valid_bits<VEC>(out_mask, row0, n, m);
+    }
+}
+
+}  // namespace mnr

@@ -1,0 +1,86 @@
+// Internal declarations shared by the translation units of libminarrow_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/minarrow_b200.h"
+
+namespace mnr {
+
+struct AggRaw;
+
+// ---- kernel launchers (one per .cu) --------------------------------------------------------------------
+int reduce_max_grid();
+cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
+                                AggRaw* partials, unsigned int* ticket, AggRaw* out, cudaStream_t s);
+
+// Element-wise binary op.  lhs/rhs: device pointers, or NULL for the side held in `scalar_bits`
+// (at most one).  lmask/rmask: NULL or validity bytes indexed from bit 0.  out_mask: required iff a mask is
+// given.  div0_flag: device word set to 1 when a dense integer Div/Rem/FloorDiv meets a zero divisor.
+struct EwArgs {
+    mnr_dtype dtype;
+    int op;
+    const void* lhs;
+    const void* rhs;
+    uint64_t scalar_bits;
+    const uint8_t* lmask;
+    const uint8_t* rmask;
+    int mask_or;            // 0 = AND, 1 = OR (only when both masks are present)
+    void* out;
+    uint8_t* out_mask;
+    uint64_t n;
+    unsigned int* div0_flag;
+};
+cudaError_t launch_ew_binary(const EwArgs& a, cudaStream_t s);
+// I32 operand promoted on load against an F32/F64 operand (routing/arithmetic.rs:244-269).
+cudaError_t launch_ew_promote(const EwArgs& a, mnr_dtype lhs_dtype, mnr_dtype rhs_dtype, cudaStream_t s);
+cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void* c, const uint8_t* mask, void* out,
+                          uint8_t* out_mask, uint64_t n, cudaStream_t s);
+
+// Bitmask logic over windows.  op: 0 AND, 1 OR, 2 XOR, 3 XNOR, 4 NOT(a), 5 COPY(a).  Bit positions are the
+// exact window starts (the API layer floors them where the reference does).  Writes ceil(len/8) bytes,
+// slack bits of the last byte zero; reads stay inside [0, ceil(x_bits_total/8)).
+cudaError_t launch_bits_op(int op, const uint8_t* a, uint64_t a_bitpos, uint64_t a_total_bits, const uint8_t* b,
+                           uint64_t b_bitpos, uint64_t b_total_bits, uint64_t len, uint8_t* out, cudaStream_t s);
+// Popcount of (a [xor b]) over len bits from the given bit positions; accumulates into *result (pre-zeroed).
+cudaError_t launch_bits_popcount(const uint8_t* a, uint64_t a_bitpos, uint64_t a_total_bits, const uint8_t* b,
+                                 uint64_t b_bitpos, uint64_t b_total_bits, uint64_t len,
+                                 unsigned long long* result, cudaStream_t s);
+
+}  // namespace mnr
+
+// ---- handle types ----------------------------------------------------------------------------------------
+struct mnr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    // scratch (device).  Index 0..2: the host-pipeline slots, 3: the context stream.
+    mnr::AggRaw* partials[4] = {};
+    unsigned int* ticket[4] = {};          // [i][0] reduction ticket; ticket[0][8] dense-int divide-by-zero flag
+    mnr::AggRaw* d_agg = nullptr;          // result slot for synchronous reductions
+    unsigned long long* d_count = nullptr; // popcount result
+    void* h_scratch = nullptr;             // 256 bytes, pinned
+    // host drop-in pipeline: 3 staging slots, one stream each
+    cudaStream_t slot_stream[3] = {};
+    void* stage[3][6] = {};                // lhs, rhs, acc, out, mask, out_mask
+    size_t stage_bytes = 0;
+    size_t host_chunk_rows = (size_t)1 << 22;
+    mnr::AggRaw* chunk_aggs = nullptr;     // one aggregate per chunk of mnr_stats_host
+    size_t chunk_aggs_cap = 0;
+};
+
+struct mnr_buf {
+    mnr_ctx* ctx;
+    mnr_dtype dtype;
+    void* ptr;
+    size_t len;
+    bool owned;
+};
+
+struct mnr_bits {
+    mnr_ctx* ctx;
+    uint8_t* ptr;
+    size_t len;     // bits
+    bool owned;
+};

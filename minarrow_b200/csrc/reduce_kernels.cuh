@@ -1,0 +1,265 @@
+// Null-aware column aggregates (sum / min / max / count) in one HBM pass.
+//
+// Replaces the sums the reference defines in its benches (benches/benchmark_parallel_simd.rs:44-97,
+// benches/hotloop_benchmark_simd.rs:56-174) and adds the null-skipping + count/min/max the north-star asks
+// for (definition: DESIGN.md "A.6"; the reference keeps those kernels in the downstream simd-kernels crate).
+//
+// Shape of the computation (this is also the documented float summation order):
+//   * the column is cut into 16-byte (or 32-byte) vectors; warp w of the grid owns "warp tiles" of
+//     32*U consecutive vectors, tiles w, w+W, w+2W, ... (W = warps in the grid);
+//   * a lane adds the vectors it loads in index order into VEC per-slot accumulators (slot k = element k
+//     of the vector — the analogue of the reference's SIMD lanes), then adds the slots in slot order;
+//   * lanes combine by xor-butterfly (offsets 16,8,4,2,1), warps combine in warp order inside the block,
+//     every block stores one partial, and the last block to finish (atomic ticket) folds the partials:
+//     thread t adds partials t, t+BLOCK, ... in index order, then the same block reduction.
+//   Grid and block sizes are compile-time constants or functions of len only, so a float sum is
+//   bit-reproducible run to run and device to device.
+// Validity costs 1 bit per row: each lane reads the byte that holds its vector's bits (no alignment or
+// padding requirement on the mask), zeroes invalid rows with a select — never a multiply, stored values
+// at null slots may be NaN/Inf — and popcounts its bits for `count`.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace mnr {
+
+struct alignas(16) AggRaw {   // device image of mnr_agg
+    uint64_t sum, mn, mx, count;
+};
+
+template <typename T> struct MinMax {
+    // Identity of min / max when nothing qualifies (DESIGN.md "A.6").
+    __device__ static T min_identity();
+    __device__ static T max_identity();
+};
+#define MNR_MM_INT(T, MX, MN)                                        \
+    template <> struct MinMax<T> {                                   \
+        __device__ static T min_identity() { return MX; }            \
+        __device__ static T max_identity() { return MN; }            \
+    };
+MNR_MM_INT(int8_t, INT8_MAX, INT8_MIN) MNR_MM_INT(uint8_t, UINT8_MAX, 0)
+MNR_MM_INT(int16_t, INT16_MAX, INT16_MIN) MNR_MM_INT(uint16_t, UINT16_MAX, 0)
+MNR_MM_INT(int32_t, INT32_MAX, INT32_MIN) MNR_MM_INT(uint32_t, UINT32_MAX, 0)
+MNR_MM_INT(int64_t, INT64_MAX, INT64_MIN) MNR_MM_INT(uint64_t, UINT64_MAX, 0)
+#undef MNR_MM_INT
+template <> struct MinMax<float> {
+    __device__ static float min_identity() { return __int_as_float(0x7fc00000); }
+    __device__ static float max_identity() { return __int_as_float(0x7fc00000); }
+};
+template <> struct MinMax<double> {
+    __device__ static double min_identity() { return __longlong_as_double(0x7ff8000000000000ll); }
+    __device__ static double max_identity() { return __longlong_as_double(0x7ff8000000000000ll); }
+};
+
+// min/max combine.  Integers: plain.  Floats: NaN never wins (NaN doubles as "empty"), -0.0 < +0.0 so
+// the result does not depend on the order in which equal zeros are met.
+template <typename T> __device__ __forceinline__ T comb_min(T a, T b) {
+    if constexpr (Traits<T>::is_float) {
+        if (b != b) return a;
+        if (a != a) return b;
+        if (b < a) return b;
+        if (b == a && signbit(b)) return b;
+        return a;
+    } else {
+        return b < a ? b : a;
+    }
+}
+template <typename T> __device__ __forceinline__ T comb_max(T a, T b) {
+    if constexpr (Traits<T>::is_float) {
+        if (b != b) return a;
+        if (a != a) return b;
+        if (b > a) return b;
+        if (b == a && !signbit(b)) return b;
+        return a;
+    } else {
+        return b > a ? b : a;
+    }
+}
+
+template <typename A> __device__ __forceinline__ uint64_t acc_bits(A v) {
+    if constexpr (sizeof(A) == 8 && !std::is_floating_point<A>::value) return (uint64_t)v;
+    else return (uint64_t)__double_as_longlong((double)v);
+}
+template <typename A> __device__ __forceinline__ A acc_from_bits(uint64_t b) {
+    if constexpr (std::is_floating_point<A>::value) return (A)__longlong_as_double((long long)b);
+    else return (A)b;
+}
+// min/max travel widened to the accumulator type (i64 / u64 / f64), as mnr_agg stores them.
+template <typename T> __device__ __forceinline__ uint64_t mm_bits(T v) {
+    using A = typename Traits<T>::Acc;
+    return acc_bits<A>((A)v);
+}
+template <typename T> __device__ __forceinline__ T mm_from_bits(uint64_t b) {
+    using A = typename Traits<T>::Acc;
+    return (T)acc_from_bits<A>(b);
+}
+
+template <typename T, bool MINMAX> struct Partial {
+    using A = typename Traits<T>::Acc;
+    A sum;
+    T mn, mx;
+    uint64_t cnt;
+    __device__ __forceinline__ void init() {
+        sum = (A)0; cnt = 0;
+        mn = MinMax<T>::min_identity(); mx = MinMax<T>::max_identity();
+    }
+    __device__ __forceinline__ void merge(const Partial& o) {
+        if constexpr (Traits<T>::is_float) sum = sum + o.sum;
+        else sum = (A)((uint64_t)sum + (uint64_t)o.sum);
+        cnt += o.cnt;
+        if constexpr (MINMAX) { mn = comb_min(mn, o.mn); mx = comb_max(mx, o.mx); }
+    }
+    __device__ __forceinline__ Partial shfl_xor(int off) const {
+        Partial r;
+        r.sum = acc_from_bits<A>(__shfl_xor_sync(0xffffffffu, (unsigned long long)acc_bits<A>(sum), off));
+        r.cnt = __shfl_xor_sync(0xffffffffu, (unsigned long long)cnt, off);
+        if constexpr (MINMAX) {
+            r.mn = mm_from_bits<T>(__shfl_xor_sync(0xffffffffu, (unsigned long long)mm_bits<T>(mn), off));
+            r.mx = mm_from_bits<T>(__shfl_xor_sync(0xffffffffu, (unsigned long long)mm_bits<T>(mx), off));
+        } else { r.mn = mn; r.mx = mx; }
+        return r;
+    }
+    __device__ __forceinline__ AggRaw raw() const { return AggRaw{acc_bits<A>(sum), mm_bits<T>(mn), mm_bits<T>(mx), cnt}; }
+    __device__ __forceinline__ void from_raw(const AggRaw& r) {
+        sum = acc_from_bits<A>(r.sum); cnt = r.count; mn = mm_from_bits<T>(r.mn); mx = mm_from_bits<T>(r.mx);
+    }
+};
+
+// Block-wide combine; result valid in thread 0.  Deterministic: butterfly in lanes, warp order in smem.
+template <typename P, int BLOCK> __device__ __forceinline__ P block_combine(P p, AggRaw* smem) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) p.merge(p.shfl_xor(off));
+    constexpr int NW = BLOCK / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = p.raw();
+    __syncthreads();
+    if (warp == 0) {
+        P q; q.init();
+        if (lane == 0) {
+#pragma unroll 1
+            for (int w = 0; w < NW; ++w) { P t; t.from_raw(smem[w]); if (w == 0) q = t; else q.merge(t); }
+        }
+        p = q;
+    }
+    __syncthreads();
+    return p;
+}
+
+template <typename T, typename VecT, bool MASKED, bool MINMAX>
+__device__ __forceinline__ void accum_vec(const VecT& v, uint32_t bits, typename Traits<T>::Acc* slot,
+                                          Partial<T, MINMAX>& p) {
+    constexpr int VEC = sizeof(VecT) / sizeof(T);
+    using A = typename Traits<T>::Acc;
+    union { VecT v; T e[VEC]; } u;
+    u.v = v;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        const bool ok = !MASKED || ((bits >> k) & 1u);
+        const T x = u.e[k];
+        if constexpr (Traits<T>::is_float) slot[k] = slot[k] + (ok ? (A)x : (A)0);
+        else slot[k] = (A)((uint64_t)slot[k] + (ok ? (uint64_t)(A)x : 0ull));
+        if constexpr (MINMAX) {
+            if (ok) { p.mn = comb_min(p.mn, x); p.mx = comb_max(p.mx, x); }
+        }
+    }
+    if constexpr (MASKED) p.cnt += (uint64_t)__popc(bits);
+}
+
+// One launch = whole column -> one mnr_agg (two-level finish inside the launch via an atomic ticket).
+__device__ __forceinline__ AggRaw load_partial(const AggRaw* p) {   // L2-coherent read of another block's partial
+    AggRaw r;
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(r.sum), "=l"(r.mn) : "l"(p));
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(r.mx), "=l"(r.count) : "l"(&p->mx));
+    return r;
+}
+
+template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MINB, int U>
+__global__ void __launch_bounds__(BLOCK, MINB)
+reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
+                    AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket, AggRaw* __restrict__ out) {
+    constexpr int VEC = sizeof(VecT) / sizeof(T);
+    using A = typename Traits<T>::Acc;
+    using P = Partial<T, MINMAX>;
+    __shared__ AggRaw smem[BLOCK / 32];
+    __shared__ bool is_last;
+
+    P p; p.init();
+    A slot[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) slot[k] = (A)0;
+
+    const VecT* __restrict__ vp = reinterpret_cast<const VecT*>(data);
+    const uint64_t nvec = n / VEC;
+    constexpr uint64_t WTILE = 32ull * U;                       // vectors per warp tile
+    const uint64_t ntiles = nvec / WTILE;
+    const uint64_t warps = (uint64_t)gridDim.x * (BLOCK / 32);
+    const uint64_t gwarp = (uint64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+
+    for (uint64_t t = gwarp; t < ntiles; t += warps) {
+        const uint64_t v0 = t * WTILE + lane;
+        VecT v[U];
+        uint32_t bits[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ldg_stream(vp + v0 + 32ull * u);
+        if constexpr (MASKED) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) bits[u] = load_valid_bits<VEC>(mask, (v0 + 32ull * u) * VEC);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) accum_vec<T, VecT, MASKED, MINMAX>(v[u], MASKED ? bits[u] : 0u, slot, p);
+    }
+    // Vectors past the last full warp tile (< 32*U of them), spread over the grid's first threads.
+    {
+        const uint64_t gtid = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+        for (uint64_t v = ntiles * WTILE + gtid; v < nvec; v += (uint64_t)gridDim.x * BLOCK) {
+            uint32_t b = 0;
+            if constexpr (MASKED) b = load_valid_bits<VEC>(mask, v * VEC);
+            accum_vec<T, VecT, MASKED, MINMAX>(ldg_stream(vp + v), b, slot, p);
+        }
+        // Rows past the last full vector (< VEC of them): one thread, row by row.
+        if (gtid == 0) {
+            for (uint64_t r = nvec * VEC; r < n; ++r) {
+                const bool ok = !MASKED || row_valid(mask, r);
+                if (ok) {
+                    const T x = data[r];
+                    if constexpr (Traits<T>::is_float) slot[0] = slot[0] + (A)x;
+                    else slot[0] = (A)((uint64_t)slot[0] + (uint64_t)(A)x);
+                    if constexpr (MINMAX) { p.mn = comb_min(p.mn, x); p.mx = comb_max(p.mx, x); }
+                    if constexpr (MASKED) p.cnt += 1;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        if constexpr (Traits<T>::is_float) p.sum = p.sum + slot[k];
+        else p.sum = (A)((uint64_t)p.sum + (uint64_t)slot[k]);
+    }
+
+    p = block_combine<P, BLOCK>(p, smem);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = p.raw();
+        __threadfence();
+        const unsigned int done = atomicAdd(ticket, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    P q; q.init();
+    bool first = true;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += BLOCK) {
+        P t; t.from_raw(load_partial(partials + i));
+        if (first) { q = t; first = false; } else q.merge(t);
+    }
+    q = block_combine<P, BLOCK>(q, smem);
+    if (threadIdx.x == 0) {
+        if constexpr (!MASKED) q.cnt = n;
+        *out = q.raw();
+        *ticket = 0;   // re-arm for the next launch on this stream
+    }
+}
+
+}  // namespace mnr

@@ -1,0 +1,167 @@
+"""Device-resident operations over `DeviceBuffer` / `DeviceBitmask` (thin, typed wrappers of the C ABI).
+
+These are the calls a GPU-resident pipeline chains without leaving HBM; the host-slice drop-ins in
+`minarrow_b200.kernels.*` are built from the same kernels plus upload/download.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .core import (ArithmeticOperator, Context, DeviceBitmask, DeviceBuffer, LogicalOperator, MaskMode, check,
+                   dtype_code)
+
+
+def _h(x):
+    return None if x is None else x.h
+
+
+def _outs(ctx: Context, ob, om) -> Tuple[DeviceBuffer, Optional[DeviceBitmask]]:
+    return DeviceBuffer(ctx, ob), (DeviceBitmask(ctx, om) if om.value else None)
+
+
+def ew_binary(ctx: Context, op: int, lhs: DeviceBuffer, rhs: DeviceBuffer, lhs_mask: Optional[DeviceBitmask] = None,
+              rhs_mask: Optional[DeviceBitmask] = None, mode: int = MaskMode.And):
+    """Fused null-aware `lhs op rhs` (apply_int_* / apply_float_*, dispatch.rs:65-206 + mask merge)."""
+    ob, om = C.c_void_p(), C.c_void_p()
+    check(ctx.lib.mnr_ew_binary(ctx.h, int(op), lhs.h, rhs.h, _h(lhs_mask), _h(rhs_mask), int(mode), C.byref(ob),
+                                C.byref(om)))
+    return _outs(ctx, ob, om)
+
+
+def ew_binary_into(ctx: Context, op: int, lhs, rhs, lhs_mask, rhs_mask, mode, out: DeviceBuffer,
+                   out_mask: Optional[DeviceBitmask]) -> None:
+    check(ctx.lib.mnr_ew_binary_into(ctx.h, int(op), lhs.h, rhs.h, _h(lhs_mask), _h(rhs_mask), int(mode), out.h,
+                                     _h(out_mask)))
+
+
+def ew_binary_promote(ctx: Context, op: int, lhs, rhs, lhs_mask=None, rhs_mask=None, mode: int = MaskMode.And):
+    """Mixed (i32, f64)/(i32, f32) operands, cast on load (routing/arithmetic.rs:244-269,342-373)."""
+    ob, om = C.c_void_p(), C.c_void_p()
+    check(ctx.lib.mnr_ew_binary_promote(ctx.h, int(op), lhs.h, rhs.h, _h(lhs_mask), _h(rhs_mask), int(mode),
+                                        C.byref(ob), C.byref(om)))
+    return _outs(ctx, ob, om)
+
+
+def _scalar_arg(arr: DeviceBuffer, scalar):
+    s = np.array([scalar], dtype=arr.dtype)
+    return s, s.ctypes.data_as(C.c_void_p)
+
+
+def ew_scalar(ctx: Context, op: int, arr: DeviceBuffer, scalar, scalar_is_lhs: bool,
+              mask: Optional[DeviceBitmask] = None):
+    """`arr op scalar` / `scalar op arr` with the scalar in a register (no broadcast_length_1_array)."""
+    keep, sp = _scalar_arg(arr, scalar)
+    ob, om = C.c_void_p(), C.c_void_p()
+    check(ctx.lib.mnr_ew_scalar(ctx.h, int(op), arr.h, sp, int(scalar_is_lhs), _h(mask), C.byref(ob), C.byref(om)))
+    return _outs(ctx, ob, om)
+
+
+def ew_scalar_into(ctx: Context, op: int, arr, scalar, scalar_is_lhs: bool, mask, out, out_mask) -> None:
+    keep, sp = _scalar_arg(arr, scalar)
+    check(ctx.lib.mnr_ew_scalar_into(ctx.h, int(op), arr.h, sp, int(scalar_is_lhs), _h(mask), out.h, _h(out_mask)))
+
+
+def ew_fma(ctx: Context, a, b, acc, mask: Optional[DeviceBitmask] = None):
+    ob, om = C.c_void_p(), C.c_void_p()
+    check(ctx.lib.mnr_ew_fma(ctx.h, a.h, b.h, acc.h, _h(mask), C.byref(ob), C.byref(om)))
+    return _outs(ctx, ob, om)
+
+
+def ew_fma_into(ctx: Context, a, b, acc, mask, out, out_mask) -> None:
+    check(ctx.lib.mnr_ew_fma_into(ctx.h, a.h, b.h, acc.h, _h(mask), out.h, _h(out_mask)))
+
+
+def bits_binop(ctx: Context, op: int, lhs: DeviceBitmask, lhs_off: int, rhs: DeviceBitmask, rhs_off: int,
+               length: int) -> DeviceBitmask:
+    o = C.c_void_p()
+    check(ctx.lib.mnr_bits_binop(ctx.h, int(op), lhs.h, lhs_off, rhs.h, rhs_off, length, C.byref(o)))
+    return DeviceBitmask(ctx, o)
+
+
+def bits_binop_into(ctx: Context, op: int, lhs, lhs_off, rhs, rhs_off, length, out: DeviceBitmask) -> None:
+    check(ctx.lib.mnr_bits_binop_into(ctx.h, int(op), lhs.h, lhs_off, rhs.h, rhs_off, length, out.h))
+
+
+def bits_not(ctx: Context, src: DeviceBitmask, off: int, length: int) -> DeviceBitmask:
+    o = C.c_void_p()
+    check(ctx.lib.mnr_bits_not(ctx.h, src.h, off, length, C.byref(o)))
+    return DeviceBitmask(ctx, o)
+
+
+def bits_not_into(ctx: Context, src, off, length, out: DeviceBitmask) -> None:
+    check(ctx.lib.mnr_bits_not_into(ctx.h, src.h, off, length, out.h))
+
+
+def bits_popcount(ctx: Context, m: DeviceBitmask, off: int, length: int) -> int:
+    ones = C.c_uint64()
+    check(ctx.lib.mnr_bits_popcount(ctx.h, m.h, off, length, C.byref(ones)))
+    return int(ones.value)
+
+
+def bits_all_true(ctx: Context, m: DeviceBitmask) -> bool:
+    r = C.c_int()
+    check(ctx.lib.mnr_bits_all_true(ctx.h, m.h, C.byref(r)))
+    return bool(r.value)
+
+
+def bits_all_false(ctx: Context, m: DeviceBitmask) -> bool:
+    r = C.c_int()
+    check(ctx.lib.mnr_bits_all_false(ctx.h, m.h, C.byref(r)))
+    return bool(r.value)
+
+
+def bits_merge(ctx: Context, lhs: Optional[DeviceBitmask], rhs: Optional[DeviceBitmask], length: int,
+               mode: int = MaskMode.And) -> Optional[DeviceBitmask]:
+    o = C.c_void_p()
+    check(ctx.lib.mnr_bits_merge(ctx.h, _h(lhs), _h(rhs), length, int(mode), C.byref(o)))
+    return DeviceBitmask(ctx, o) if o.value else None
+
+
+def bits_eq(ctx: Context, a, a_off, b, b_off, length, negate: bool = False) -> DeviceBitmask:
+    o = C.c_void_p()
+    check(ctx.lib.mnr_bits_eq(ctx.h, a.h, a_off, b.h, b_off, length, int(negate), C.byref(o)))
+    return DeviceBitmask(ctx, o)
+
+
+def bits_all_eq(ctx: Context, a, a_off, b, b_off, length) -> bool:
+    r = C.c_int()
+    check(ctx.lib.mnr_bits_all_eq(ctx.h, a.h, a_off, b.h, b_off, length, C.byref(r)))
+    return bool(r.value)
+
+
+def bits_in(ctx: Context, lhs, lhs_off, rhs, rhs_off, length, negate: bool = False) -> DeviceBitmask:
+    o = C.c_void_p()
+    check(ctx.lib.mnr_bits_in(ctx.h, lhs.h, lhs_off, rhs.h, rhs_off, length, int(negate), C.byref(o)))
+    return DeviceBitmask(ctx, o)
+
+
+def _agg_dict(dtype, agg: _lib.Agg, lib) -> dict:
+    kind = np.dtype(dtype).kind
+    f = {"i": "i64", "u": "u64", "f": "f64"}[kind]
+    return {"sum": getattr(agg.sum, f), "min": getattr(agg.min, f), "max": getattr(agg.max, f),
+            "count": int(agg.count), "mean": float(lib.mnr_agg_mean(dtype_code(dtype), C.byref(agg)))}
+
+
+def reduce_stats(ctx: Context, buf: DeviceBuffer, validity: Optional[DeviceBitmask] = None) -> dict:
+    """{sum, min, max, count, mean} of a device column in one pass (synchronises)."""
+    agg = _lib.Agg()
+    check(ctx.lib.mnr_reduce_stats(ctx.h, buf.h, _h(validity), C.byref(agg)))
+    return _agg_dict(buf.dtype, agg, ctx.lib)
+
+
+def reduce_sum(ctx: Context, buf: DeviceBuffer, validity: Optional[DeviceBitmask] = None):
+    """(sum, valid_count): the sum the reference's benches time (benchmark_parallel_simd.rs:81-97), null-aware."""
+    s, c = _lib.Scalar64(), C.c_uint64()
+    check(ctx.lib.mnr_reduce_sum(ctx.h, buf.h, _h(validity), C.byref(s), C.byref(c)))
+    f = {"i": "i64", "u": "u64", "f": "f64"}[buf.dtype.kind]
+    return getattr(s, f), int(c.value)
+
+
+def reduce_stats_async(ctx: Context, buf: DeviceBuffer, validity: Optional[DeviceBitmask], with_minmax: bool,
+                       out_device_ptr: int) -> None:
+    """Writes the 32-byte `mnr_agg` partial to device memory on the context stream (no sync)."""
+    check(ctx.lib.mnr_reduce_stats_async(ctx.h, buf.h, _h(validity), int(with_minmax), C.c_void_p(out_device_ptr)))

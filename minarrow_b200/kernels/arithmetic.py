@@ -1,0 +1,111 @@
+"""Leaf arithmetic kernels with the reference's names and signatures
+(src/kernels/arithmetic/dispatch.rs:74-79,147-152,221-226):
+
+    apply_int_i64(lhs: &[i64], rhs: &[i64], op, mask: Option<&Bitmask>) -> Result<IntegerArray<i64>, KernelError>
+
+Host slices in, a fresh `IntegerArray`/`FloatArray` out; the work happens on the GPU through
+`mnr_apply_host` (chunked upload -> fused kernel -> download).  Errors follow the reference:
+LengthMismatch, and DivideByZero where the reference's dense integer kernels panic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from ..core import (ArithmeticOperator, Bitmask, Context, FloatArray, IntegerArray, KernelError, _vp, check,
+                    default_context, dtype_code)
+
+
+def _mask_arg(mask: Optional[Bitmask], n: int):
+    if mask is None:
+        return None
+    need = (n + 7) // 8
+    bits = np.ascontiguousarray(mask.bits, dtype=np.uint8)
+    if bits.size < need:
+        raise KernelError("InvalidArguments", f"mask has {bits.size} bytes, need {need}")
+    return bits
+
+
+def _apply(dtype, lhs, rhs, op, mask: Optional[Bitmask], ctx: Optional[Context]):
+    ctx = ctx or default_context()
+    lhs = np.ascontiguousarray(lhs, dtype=dtype)
+    rhs = np.ascontiguousarray(rhs, dtype=dtype)
+    n = lhs.size
+    m = _mask_arg(mask, n)
+    out = np.empty(n, dtype=dtype)
+    om = np.zeros((n + 7) // 8, dtype=np.uint8) if m is not None else None
+    check(ctx.lib.mnr_apply_host(ctx.h, dtype_code(dtype), int(op), _vp(lhs), lhs.size, _vp(rhs), rhs.size, _vp(m),
+                                 _vp(out), _vp(om)))
+    null_mask = Bitmask(om, n) if om is not None else None   # Some(mask) iff a mask was passed (dispatch.rs:90-104)
+    return (FloatArray if np.dtype(dtype).kind == "f" else IntegerArray)(out, null_mask)
+
+
+def apply_int_i32(lhs, rhs, op: ArithmeticOperator, mask: Optional[Bitmask] = None, ctx=None) -> IntegerArray:
+    return _apply(np.int32, lhs, rhs, op, mask, ctx)
+
+
+def apply_int_u32(lhs, rhs, op: ArithmeticOperator, mask: Optional[Bitmask] = None, ctx=None) -> IntegerArray:
+    return _apply(np.uint32, lhs, rhs, op, mask, ctx)
+
+
+def apply_int_i64(lhs, rhs, op: ArithmeticOperator, mask: Optional[Bitmask] = None, ctx=None) -> IntegerArray:
+    return _apply(np.int64, lhs, rhs, op, mask, ctx)
+
+
+def apply_int_u64(lhs, rhs, op: ArithmeticOperator, mask: Optional[Bitmask] = None, ctx=None) -> IntegerArray:
+    return _apply(np.uint64, lhs, rhs, op, mask, ctx)
+
+
+# `extended_numeric_types` (dispatch.rs:380-387)
+def apply_int_i16(lhs, rhs, op, mask=None, ctx=None) -> IntegerArray:
+    return _apply(np.int16, lhs, rhs, op, mask, ctx)
+
+
+def apply_int_u16(lhs, rhs, op, mask=None, ctx=None) -> IntegerArray:
+    return _apply(np.uint16, lhs, rhs, op, mask, ctx)
+
+
+def apply_int_i8(lhs, rhs, op, mask=None, ctx=None) -> IntegerArray:
+    return _apply(np.int8, lhs, rhs, op, mask, ctx)
+
+
+def apply_int_u8(lhs, rhs, op, mask=None, ctx=None) -> IntegerArray:
+    return _apply(np.uint8, lhs, rhs, op, mask, ctx)
+
+
+def apply_float_f32(lhs, rhs, op: ArithmeticOperator, mask: Optional[Bitmask] = None, ctx=None) -> FloatArray:
+    return _apply(np.float32, lhs, rhs, op, mask, ctx)
+
+
+def apply_float_f64(lhs, rhs, op: ArithmeticOperator, mask: Optional[Bitmask] = None, ctx=None) -> FloatArray:
+    return _apply(np.float64, lhs, rhs, op, mask, ctx)
+
+
+APPLY = {np.dtype(np.int32): apply_int_i32, np.dtype(np.uint32): apply_int_u32, np.dtype(np.int64): apply_int_i64,
+         np.dtype(np.uint64): apply_int_u64, np.dtype(np.int16): apply_int_i16, np.dtype(np.uint16): apply_int_u16,
+         np.dtype(np.int8): apply_int_i8, np.dtype(np.uint8): apply_int_u8, np.dtype(np.float32): apply_float_f32,
+         np.dtype(np.float64): apply_float_f64}
+
+
+def _fma(dtype, lhs, rhs, acc, mask, ctx) -> FloatArray:
+    ctx = ctx or default_context()
+    lhs, rhs, acc = (np.ascontiguousarray(x, dtype=dtype) for x in (lhs, rhs, acc))
+    n = lhs.size
+    m = _mask_arg(mask, n)
+    out = np.empty(n, dtype=dtype)
+    om = np.zeros((n + 7) // 8, dtype=np.uint8) if m is not None else None
+    check(ctx.lib.mnr_apply_fma_host(ctx.h, dtype_code(dtype), _vp(lhs), lhs.size, _vp(rhs), rhs.size, _vp(acc),
+                                     acc.size, _vp(m), _vp(out), _vp(om)))
+    return FloatArray(out, Bitmask(om, n) if om is not None else None)
+
+
+def apply_fma_f32(lhs, rhs, acc, mask: Optional[Bitmask] = None, ctx=None) -> FloatArray:
+    """apply_fma_f32 (dispatch.rs:404-410)."""
+    return _fma(np.float32, lhs, rhs, acc, mask, ctx)
+
+
+def apply_fma_f64(lhs, rhs, acc, mask: Optional[Bitmask] = None, ctx=None) -> FloatArray:
+    """apply_fma_f64 (dispatch.rs:412-418)."""
+    return _fma(np.float64, lhs, rhs, acc, mask, ctx)
