@@ -1,0 +1,24 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, smoke, bench (both arms), ncu launch list + full capture of the top kernels.
+# Usage (from the repo root on the GPU box):  bash tools/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+{ nvidia-smi; nproc; lscpu | head -20; free -g; } > $OUT/box.txt 2>&1
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 2>&1 | tail -25 | tee $OUT/pytest_gpu.txt
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke.txt
+echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | tail -3 | tee $OUT/bench_reference.json
+echo "== bench"; timeout 900 python bench.py 2>&1 | tail -5 | tee $OUT/bench.json
+echo "== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"reduce_stats|ew_binary|ew_fma|bits_|clear_trailing" -c 400 \
+    --csv --log-file $OUT/launches.csv python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_launches.log 2>&1
+tail -2 $OUT/ncu_launches.log
+echo "== ncu full: reduce"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:reduce_stats -s 3 -c 2 -f -o $OUT/prof_reduce \
+    python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-secondary > $OUT/ncu_reduce.log 2>&1
+tail -2 $OUT/ncu_reduce.log
+echo "== ncu full: ew f64 masked add"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ew_binary -s 3 -c 2 -f -o $OUT/prof_ew \
+    python bench.py --steps 3 --warmup 3 --rows 67108864 --no-e2e --no-cpu > $OUT/ncu_ew.log 2>&1
+tail -2 $OUT/ncu_ew.log
+ls -la $OUT
