@@ -1,0 +1,152 @@
+"""SuperArray / SuperTable chunks as shards over the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference's chunked containers are already independent equal-dtype units that its own route walks chunk by chunk
+(`SuperArray {chunks: Vec<Array>}`, src/structs/chunked/super_array.rs:96-103; per-chunk loop and length check,
+src/kernels/broadcast/super_array.rs:180-249).  Here chunk `i` of `n` lives on rank `floor(i * G / n)` (contiguous
+blocks, so global row order is preserved), element-wise and bitmask work runs shard-local with no communication, and a
+reduction leaves one 32-byte `mnr_agg` partial per rank that is exchanged with ONE collective — an all-gather of 32 bytes
+per rank — and folded in rank order on every rank (`mnr_agg_combine`: integer sums wrap and are order-free, float sums
+use the documented rank-order add, min/max use the NaN-skipping combine).  The backend is whatever the process group was
+created with: NCCL over NVLink on the B200 box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .core import KernelError, check, dtype_code
+
+
+def chunk_owner(i: int, n_chunks: int, world: int) -> int:
+    """Rank that owns chunk `i`: contiguous block assignment, floor(i * G / n)."""
+    if not 0 <= i < n_chunks:
+        raise KernelError("OutOfBounds", f"chunk {i} of {n_chunks}")
+    return (i * world) // n_chunks
+
+
+def shard_chunks(n_chunks: int, world: int) -> List[range]:
+    """Chunk index range of every rank (may be empty when n_chunks < world)."""
+    owners = [chunk_owner(i, n_chunks, world) for i in range(n_chunks)]
+    out = []
+    for r in range(world):
+        mine = [i for i, o in enumerate(owners) if o == r]
+        out.append(range(mine[0], mine[-1] + 1) if mine else range(0, 0))
+    return out
+
+
+def shard_rows(n_rows: int, world: int, align: int = 64) -> List[Tuple[int, int]]:
+    """Split one big Array into `world` contiguous (offset, len) windows cut on `align`-row boundaries
+    (64 rows = one validity word, so every shard's bitmask starts on a word boundary)."""
+    if world < 1 or align < 1:
+        raise KernelError("InvalidArguments", "world and align must be >= 1")
+    units = (n_rows + align - 1) // align
+    out, start = [], 0
+    for r in range(world):
+        u = units // world + (1 if r < units % world else 0)
+        length = min(u * align, n_rows - start)
+        out.append((start, max(length, 0)))
+        start += max(length, 0)
+    return out
+
+
+def agg_to_words(agg: "_lib.Agg") -> np.ndarray:
+    """The 32-byte `mnr_agg` as 4 x int64 (the wire format of the exchange)."""
+    return np.frombuffer(bytes(agg), dtype=np.int64).copy()
+
+
+def words_to_agg(words) -> "_lib.Agg":
+    w = np.ascontiguousarray(words, dtype=np.int64)
+    return _lib.Agg.from_buffer_copy(w.tobytes())
+
+
+def combine_partials(dtype, partials: Sequence) -> dict:
+    """Fold `mnr_agg` partials (4 x int64 rows) in index order through the C ABI (`mnr_agg_combine`)."""
+    lib = _lib.load()
+    p = np.ascontiguousarray(np.asarray(partials, dtype=np.int64).reshape(-1, 4))
+    if p.shape[0] == 0:
+        raise KernelError("InvalidArguments", "need at least one partial")
+    arr = (_lib.Agg * p.shape[0]).from_buffer_copy(p.tobytes())
+    out = _lib.Agg()
+    code = dtype_code(dtype)
+    check(lib.mnr_agg_combine(code, arr, p.shape[0], C.byref(out)))
+    f = {"i": "i64", "u": "u64", "f": "f64"}[np.dtype(dtype).kind]
+    return {"sum": getattr(out.sum, f), "min": getattr(out.min, f), "max": getattr(out.max, f),
+            "count": int(out.count), "mean": float(lib.mnr_agg_mean(code, C.byref(out)))}
+
+
+def exchange_partials(local, group=None):
+    """All-gather one 4 x int64 partial per rank -> tensor [world, 4] on the device of `local`.
+    `local` is a torch int64 tensor of 4 elements (on the GPU for NCCL, on the CPU for gloo)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local.view(1, 4).clone()
+    world = dist.get_world_size(group)
+    out = torch.empty(world * 4, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous().view(-1), group=group)
+    return out.view(world, 4)
+
+
+class ShardedColumn:
+    """This rank's shard of a chunked numeric column: device-resident chunks (+ optional validity) on one GPU."""
+
+    def __init__(self, ctx, dtype, chunks: Sequence, validities: Optional[Sequence] = None):
+        self.ctx, self.dtype = ctx, np.dtype(dtype)
+        self.chunks = list(chunks)                                   # DeviceBuffer per local chunk
+        self.validities = list(validities) if validities is not None else [None] * len(self.chunks)
+        if len(self.validities) != len(self.chunks):
+            raise KernelError("InvalidArguments", "one validity (or None) per chunk")
+
+    @classmethod
+    def from_host_chunks(cls, ctx, chunks: Sequence, rank: int, world: int) -> "ShardedColumn":
+        """Upload the chunks this rank owns.  `chunks` = the whole SuperArray's host chunks (IntegerArray/FloatArray)."""
+        from .core import DeviceBitmask, DeviceBuffer
+        mine = shard_chunks(len(chunks), world)[rank]
+        bufs, vals = [], []
+        dtype = np.asarray(chunks[0].data).dtype if chunks else np.dtype(np.int64)
+        for i in mine:
+            c = chunks[i]
+            bufs.append(DeviceBuffer.upload(ctx, np.ascontiguousarray(c.data)))
+            vals.append(None if c.null_mask is None else DeviceBitmask.upload(ctx, c.null_mask))
+        return cls(ctx, dtype, bufs, vals)
+
+    def local_partial(self, with_minmax: bool = True):
+        """One `mnr_agg` for this rank: per-chunk partials (one kernel launch each, asynchronous, written straight to
+        a device array) folded in chunk order.  Returns a torch int64[4] tensor on this rank's GPU."""
+        import torch
+        from . import device_ops as dev
+        n = max(1, len(self.chunks))
+        parts = torch.zeros(n, 4, dtype=torch.int64, device=torch.device("cuda", self.ctx.device))
+        for k, (b, v) in enumerate(zip(self.chunks, self.validities)):
+            dev.reduce_stats_async(self.ctx, b, v, with_minmax, parts[k].data_ptr())
+        self.ctx.synchronize()
+        if not self.chunks:
+            return None
+        host = parts.cpu().numpy()
+        out = _lib.Agg()
+        arr = (_lib.Agg * len(self.chunks)).from_buffer_copy(host.tobytes())
+        check(self.ctx.lib.mnr_agg_combine(dtype_code(self.dtype), arr, len(self.chunks), C.byref(out)))
+        return torch.from_numpy(agg_to_words(out)).to(parts.device)
+
+    def stats(self, with_minmax: bool = True, group=None) -> dict:
+        """Global {sum, min, max, count, mean} of the column: local partial -> all-gather -> rank-order combine.
+        Ranks that own no chunk contribute nothing (their slot is skipped)."""
+        import torch
+        import torch.distributed as dist
+        lp = self.local_partial(with_minmax)
+        dev_ = torch.device("cuda", self.ctx.device)
+        has = torch.tensor([0 if lp is None else 1], dtype=torch.int64, device=dev_)
+        if lp is None:
+            lp = torch.zeros(4, dtype=torch.int64, device=dev_)
+        allp = exchange_partials(lp, group).cpu().numpy()
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            flags = exchange_partials(torch.cat([has, has, has, has]), group).cpu().numpy()[:, 0]
+        else:
+            flags = np.array([int(has.item())])
+        keep = [allp[r] for r in range(allp.shape[0]) if flags[r]]
+        if not keep:
+            raise KernelError("InvalidArguments", "empty SuperArray")
+        return combine_partials(self.dtype, keep)

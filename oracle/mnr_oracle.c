@@ -534,6 +534,10 @@ typedef struct { f64 sum; f64 min; f64 max; u64 count; } orc_agg_f64;
         out->sum = sum; out->min = mn; out->max = mx; out->count = cnt;                         \
     }
 /* -fwrapv makes the signed i64 accumulate wrap like Rust's wrapping_add. */
+DEF_STATS_INT(i8, orc_agg_i64, i64, INT8_MAX, INT8_MIN)
+DEF_STATS_INT(i16, orc_agg_i64, i64, INT16_MAX, INT16_MIN)
+DEF_STATS_INT(u8, orc_agg_u64, u64, UINT8_MAX, 0)
+DEF_STATS_INT(u16, orc_agg_u64, u64, UINT16_MAX, 0)
 DEF_STATS_INT(i32, orc_agg_i64, i64, INT32_MAX, INT32_MIN)
 DEF_STATS_INT(i64, orc_agg_i64, i64, INT64_MAX, INT64_MIN)
 DEF_STATS_INT(u32, orc_agg_u64, u64, UINT32_MAX, 0)
