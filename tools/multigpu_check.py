@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Run under torchrun (one rank per GPU): a SuperArray of host chunks sharded over the ranks, reduced with
+reduce_stats_kernel per chunk + ONE NCCL all-gather of the 32-byte partials, checked against the oracle on the
+whole column; element-wise ops run shard-local and are checked per chunk.  Exit code 0 = parity on every rank."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import minarrow_b200 as mnr
+    from minarrow_b200 import sharded as sh
+    from oracle import oracle as orc
+    ctx = mnr.Context(local)
+    rng = np.random.default_rng(123)                     # every rank builds the same SuperArray, uploads only its shard
+    n_chunks, rows = 13, 250_007
+    for dt in (np.int64, np.int32, np.uint64, np.float64, np.float32):
+        chunks = []
+        for _ in range(n_chunks):
+            if np.dtype(dt).kind == "f":
+                d = (rng.standard_normal(rows) * 100).astype(dt)
+            else:
+                d = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, rows, dtype=dt, endpoint=True)
+            chunks.append(mnr.core.make_array(d, mnr.Bitmask.from_bools(rng.random(rows) < 0.9)))
+        col = sh.ShardedColumn.from_host_chunks(ctx, chunks, rank, world)
+        got = col.stats(True)
+        whole = np.concatenate([c.data for c in chunks])
+        valid = np.concatenate([c.null_mask.to_bools() for c in chunks])
+        exp = orc.stats(whole, orc.Bits.from_bools(valid))
+        assert got["count"] == exp["count"], (dt, got, exp)
+        assert got["min"] == exp["min"] and got["max"] == exp["max"], (dt, got, exp)
+        if np.dtype(dt).kind == "f":
+            assert abs(got["sum"] - exp["sum"]) <= 1e-12 * np.abs(whole[valid].astype(np.float64)).sum(), (dt, got, exp)
+        else:
+            assert got["sum"] == exp["sum"], (dt, got, exp)
+        # every rank must hold the same bits (rank-order combine)
+        bits = int(np.float64(got["sum"]).view(np.int64)) if np.dtype(dt).kind == "f" else \
+            (int(got["sum"]) + 2 ** 63) % 2 ** 64 - 2 ** 63
+        t = torch.tensor([bits], dtype=torch.int64, device="cuda")
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        assert all(int(x) == int(t) for x in g), "ranks disagree on the combined sum"
+        # shard-local element-wise op: chunk * chunk with fused validity, no communication
+        mine = sh.shard_chunks(n_chunks, world)[rank]
+        for k, i in enumerate(mine):
+            ob, om = mnr.device_ops.ew_binary(ctx, mnr.ArithmeticOperator.Multiply, col.chunks[k], col.chunks[k],
+                                              col.validities[k], col.validities[k], mnr.MaskMode.And)
+            m = orc.Bits(chunks[i].null_mask.bits, rows)
+            ed, em = orc.apply(chunks[i].data, chunks[i].data, orc.MUL, m)
+            assert ob.download().tobytes() == ed.tobytes() and np.array_equal(om.download().bits, em.bits), (dt, i)
+    dist.barrier()
+    if rank == 0:
+        print(f"multigpu_check ok: world={world}, {n_chunks} chunks x {rows} rows, 5 dtypes")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
