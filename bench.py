@@ -89,6 +89,15 @@ def host_sample(rows: int, seed: int):
     return data, bits, valid
 
 
+def host_threads() -> int:
+    """All host cores this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1,
+    and the oracle's OpenMP loops take the thread count as an explicit num_threads() argument."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_cpu(orc, data, bits, rows, threads, min_reps, max_reps, budget_s):
     """Best and mean seconds per pass of orc_par_masked_sum_i64 (par_chunks(1<<20) -> chunk sums -> combine)."""
     v = orc.Bits(bits, rows)
@@ -109,7 +118,7 @@ def run_reference(args):
     import numpy as np
     from oracle import oracle as orc
     orc.build()
-    threads = orc.max_threads()
+    threads = host_threads()
     rows = min(args.cpu_rows, args.rows)
     data, bits, valid = host_sample(rows, 1)
     exp_sum = int(data[valid].sum())
@@ -472,7 +481,7 @@ def run_b200(args):
             sd, sb = host_data[:srows].numpy(), host_bits[:srows // 8].numpy()
         else:
             sd, sb = data[:srows].cpu().numpy(), bits[:srows // 8].cpu().numpy()
-        threads = orc.max_threads()
+        threads = host_threads()
         ts, (cs, cc) = time_cpu(orc, sd, sb, srows, threads, 5, 200, 12.0)
         # the same sample through the CUDA path must agree bit for bit
         g_s, g_c = devops.reduce_sum(ctx, buf.slice(0, srows), mnr.DeviceBitmask.wrap(ctx, bits.data_ptr(), srows, bits))

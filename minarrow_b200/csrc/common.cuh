@@ -14,14 +14,38 @@ namespace mnr {
 struct alignas(16) V16 { uint64_t x, y; };                 // one 128-bit vector
 struct alignas(32) V32 { uint64_t x, y, z, w; };           // one 256-bit vector (LDG.256, sm_100+)
 
+// MNR_LD_POLICY / MNR_ST_POLICY select the cache hints (tools/sweep.cu builds one binary per combination;
+// the library default is the winner of that sweep, profiles/).
+#ifndef MNR_LD_POLICY
+#define MNR_LD_POLICY 0
+#endif
+#ifndef MNR_ST_POLICY
+#define MNR_ST_POLICY 0
+#endif
+#if MNR_LD_POLICY == 0
+#define MNR_LD "ld.global.nc.L1::no_allocate"
+#elif MNR_LD_POLICY == 1
+#define MNR_LD "ld.global.nc.L1::no_allocate.L2::256B"
+#elif MNR_LD_POLICY == 2
+#define MNR_LD "ld.global.nc"
+#else
+#define MNR_LD "ld.global.nc.L1::evict_first.L2::256B"
+#endif
+#if MNR_ST_POLICY == 0
+#define MNR_ST "st.global.cs"
+#elif MNR_ST_POLICY == 1
+#define MNR_ST "st.global"
+#else
+#define MNR_ST "st.global.L1::no_allocate"
+#endif
 __device__ __forceinline__ V16 ldg_stream(const V16* p) {
     V16 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    asm volatile(MNR_LD ".v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ V32 ldg_stream(const V32* p) {
     V32 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+    asm volatile(MNR_LD ".v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(r.x), "=l"(r.y), "=l"(r.z), "=l"(r.w) : "l"(p));
     return r;
 }
@@ -30,10 +54,10 @@ __device__ __forceinline__ V32 ldg_stream(const V32* p) {
 template <typename S> __device__ __forceinline__ S ldg_stream(const S* p) { return *p; }
 template <typename S> __device__ __forceinline__ void stg_stream(S* p, const S& v) { *p = v; }
 __device__ __forceinline__ void stg_stream(V16* p, const V16& v) {
-    asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+    asm volatile(MNR_ST ".v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
 __device__ __forceinline__ void stg_stream(V32* p, const V32& v) {
-    asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.x), "l"(v.y), "l"(v.z), "l"(v.w)
+    asm volatile(MNR_ST ".v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.x), "l"(v.y), "l"(v.z), "l"(v.w)
                  : "memory");
 }
 __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {

@@ -166,8 +166,8 @@ __device__ __forceinline__ uint32_t merged_bits(const EwDev& a, uint64_t row0) {
 }
 
 // Element-wise binary kernel.  TL/TR: stored operand types (== T except for the cast-on-load promotion).
-template <typename T, typename TL, typename TR, typename VecT, int CLS, bool MASKED, int BLOCK, int U>
-__global__ void __launch_bounds__(BLOCK) ew_binary_kernel(const EwDev a) {
+template <typename T, typename TL, typename TR, typename VecT, int CLS, bool MASKED, int BLOCK, int U, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB) ew_binary_kernel(const EwDev a) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     // Operand vectors carry VEC elements of their own (possibly narrower) type.
     struct alignas(sizeof(TL) * VEC) LV { TL e[VEC]; };
