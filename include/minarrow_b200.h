@@ -215,6 +215,15 @@ int mnr_reduce_sum(mnr_ctx* ctx, const mnr_buf* buf, const mnr_bits* validity, m
  * their identities and runs the cheaper sum+count kernel. */
 int mnr_reduce_stats_async(mnr_ctx* ctx, const mnr_buf* buf, const mnr_bits* validity, int with_minmax,
                            void* out_device);
+/* Batched fan-out: the SuperArray / Table / SuperTable routes call the leaf once per chunk and per column
+ * (src/kernels/broadcast/super_array.rs:180-249 — "TODO: Parallelise" :193 —, table.rs:31-62, super_table.rs:38-73).
+ * These take the whole list and issue ONE launch per (dtype, alignment, masked) class; aggregate i is bit-identical
+ * to mnr_reduce_stats(bufs[i], validities[i]).  `validities` may be NULL (all dense) or hold NULL entries.
+ * The async form writes n x 32 bytes to DEVICE memory `out_device` on the context stream. */
+int mnr_reduce_stats_batch(mnr_ctx* ctx, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
+                           int with_minmax, mnr_agg* out_host);                                      /* syncs */
+int mnr_reduce_stats_batch_async(mnr_ctx* ctx, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
+                                 int with_minmax, void* out_device);
 /* mean = (double)sum / (double)count on the host from a (combined) aggregate; NaN when count == 0. */
 double mnr_agg_mean(mnr_dtype dtype, const mnr_agg* agg);
 /* Combine per-chunk / per-GPU partials in index order (the documented rank-order float add). */

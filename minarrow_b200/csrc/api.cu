@@ -6,6 +6,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "internal.h"
@@ -88,7 +89,8 @@ static int ctx_init(int device, cudaStream_t stream, bool own, mnr_ctx** out) {
     if (own) CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     else c->stream = stream;
     for (int i = 0; i < 3; ++i) CU(cudaStreamCreateWithFlags(&c->slot_stream[i], cudaStreamNonBlocking));
-    const size_t pbytes = sizeof(AggRaw) * (size_t)reduce_max_grid();
+    size_t pbytes = sizeof(AggRaw) * (size_t)reduce_max_grid();
+    if (pbytes < sizeof(unsigned long long) * (size_t)popcount_max_grid()) pbytes = sizeof(unsigned long long) * (size_t)popcount_max_grid();
     for (int i = 0; i < 4; ++i) {
         CU(cudaMalloc(&c->partials[i], pbytes));
         CU(cudaMalloc(&c->ticket[i], 64));
@@ -96,7 +98,7 @@ static int ctx_init(int device, cudaStream_t stream, bool own, mnr_ctx** out) {
     }
     CU(cudaMalloc(&c->d_agg, sizeof(AggRaw)));
     CU(cudaMalloc(&c->d_count, 64));
-    CU(cudaHostAlloc(&c->h_scratch, 256, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->h_scratch, 256, cudaHostAllocMapped | cudaHostAllocPortable));   // kernels store results here directly
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;   // keep freed blocks cached: fresh outputs per call without cudaMalloc cost
@@ -120,6 +122,9 @@ void mnr_ctx_destroy(mnr_ctx* c) {
     }
     for (int i = 0; i < 4; ++i) { cudaFree(c->partials[i]); cudaFree(c->ticket[i]); }
     if (c->chunk_aggs) cudaFree(c->chunk_aggs);
+    if (c->batch_partials) cudaFree(c->batch_partials);
+    if (c->batch_segs) cudaFree(c->batch_segs);
+    if (c->batch_tickets) cudaFree(c->batch_tickets);
     cudaFree(c->d_agg);
     cudaFree(c->d_count);
     cudaFreeHost(c->h_scratch);
@@ -491,11 +496,11 @@ static int popcount_sync(mnr_ctx* c, const mnr_bits* a, uint64_t ap, const mnr_b
                          uint64_t* ones) {
     CU(cudaSetDevice(c->device));
     if (len == 0) { *ones = 0; return MNR_OK; }
-    CU(cudaMemsetAsync(c->d_count, 0, 8, c->stream));
-    CU(launch_bits_popcount(a->ptr, ap, a->len, b ? b->ptr : nullptr, bp, b ? b->len : 0, len, c->d_count, c->stream));
+    // The kernel's last block stores the count straight into mapped pinned host memory: launch + one stream sync.
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->h_scratch) + 64);
+    CU(launch_bits_popcount(a->ptr, ap, a->len, b ? b->ptr : nullptr, bp, b ? b->len : 0, len,
+                            reinterpret_cast<unsigned long long*>(c->partials[3]), c->ticket[3] + 4, c->d_count, h, c->stream));
     c->launches++;
-    unsigned long long* h = static_cast<unsigned long long*>(c->h_scratch);
-    CU(cudaMemcpyAsync(h, c->d_count, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *ones = *h;
     return MNR_OK;
@@ -630,15 +635,20 @@ int mnr_reduce_stats_async(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, int 
             "out_device must be a 16-byte aligned device pointer");
     CU(cudaSetDevice(c->device));
     CU(launch_reduce_stats(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, with_minmax != 0, c->partials[3], c->ticket[3],
-                           static_cast<AggRaw*>(out_device), c->stream));
+                           static_cast<AggRaw*>(out_device), nullptr, c->stream));
     c->launches++;
     return MNR_OK;
 }
 
+// Synchronous form: the kernel's finishing block also stores the aggregate into mapped pinned host memory, so the call
+// is one launch + one stream synchronise (no D2H memcpy).
 static int reduce_sync(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, bool minmax, mnr_agg* out) {
-    int rc = mnr_reduce_stats_async(c, b, v, minmax, c->d_agg);
+    int rc = check_reduce(c, b, v);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(c->h_scratch, c->d_agg, sizeof(AggRaw), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaSetDevice(c->device));
+    CU(launch_reduce_stats(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, minmax, c->partials[3], c->ticket[3], c->d_agg,
+                           static_cast<AggRaw*>(c->h_scratch), c->stream));
+    c->launches++;
     CU(cudaStreamSynchronize(c->stream));
     memcpy(out, c->h_scratch, sizeof(mnr_agg));
     return MNR_OK;
@@ -656,6 +666,96 @@ int mnr_reduce_sum(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, mnr_scalar64
     if (rc) return rc;
     *out_sum = a.sum;
     if (out_count) *out_count = a.count;
+    return MNR_OK;
+}
+
+
+// ---- batched reductions: one launch per (dtype, alignment tier, masked) class -----------------------------------------
+static int ensure_batch_scratch(mnr_ctx* c, size_t nseg, size_t max_blk) {
+    const size_t need_p = nseg * max_blk * sizeof(AggRaw), need_s = nseg * sizeof(ReduceSeg), need_t = nseg * sizeof(unsigned int);
+    if (c->batch_partials_bytes < need_p) {
+        if (c->batch_partials) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_partials)); c->batch_partials = nullptr; }
+        CU(cudaMalloc(&c->batch_partials, need_p));
+        c->batch_partials_bytes = need_p;
+    }
+    if (c->batch_segs_bytes < need_s) {
+        if (c->batch_segs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_segs)); c->batch_segs = nullptr; }
+        CU(cudaMalloc(&c->batch_segs, need_s * 2));
+        c->batch_segs_bytes = need_s * 2;
+    }
+    if (c->batch_tickets_bytes < need_t) {
+        if (c->batch_tickets) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_tickets)); c->batch_tickets = nullptr; }
+        CU(cudaMalloc(&c->batch_tickets, need_t * 2));
+        CU(cudaMemset(c->batch_tickets, 0, need_t * 2));   // tickets re-arm themselves after every launch
+        c->batch_tickets_bytes = need_t * 2;
+    }
+    return MNR_OK;
+}
+
+int mnr_reduce_stats_batch_async(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
+                                 int with_minmax, void* out_device) {
+    REQUIRE(c && (bufs || n == 0) && (out_device || n == 0), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE((reinterpret_cast<uintptr_t>(out_device) & 15u) == 0, MNR_ERR_INVALID_ARGUMENTS, "out_device must be 16-byte aligned");
+    if (n == 0) return MNR_OK;
+    const bool minmax = with_minmax != 0;
+    for (size_t i = 0; i < n; ++i) {
+        int rc = check_reduce(c, bufs[i], validities ? validities[i] : nullptr);
+        if (rc) return rc;
+    }
+    CU(cudaSetDevice(c->device));
+    // Group the segments by kernel instantiation; order inside a group is the caller's order.
+    struct Key { int dtype, tier, masked; };
+    std::vector<Key> keys;
+    std::vector<std::vector<ReduceSeg>> groups;
+    for (size_t i = 0; i < n; ++i) {
+        const mnr_buf* b = bufs[i];
+        const mnr_bits* v = validities ? validities[i] : nullptr;
+        const Key k{(int)b->dtype, reduce_tier(b->ptr, minmax), v ? 1 : 0};
+        size_t g = 0;
+        for (; g < keys.size(); ++g) if (keys[g].dtype == k.dtype && keys[g].tier == k.tier && keys[g].masked == k.masked) break;
+        if (g == keys.size()) { keys.push_back(k); groups.emplace_back(); }
+        ReduceSeg s;
+        s.data = b->ptr; s.mask = v ? v->ptr : nullptr; s.n = b->len;
+        s.nblk = reduce_nblk(b->dtype, b->len, k.tier, minmax); s.out_index = (uint32_t)i;
+        groups[g].push_back(s);
+    }
+    for (size_t g = 0; g < groups.size(); ++g) {
+        // gridDim.y <= 65535
+        for (size_t off = 0; off < groups[g].size(); off += 65535) {
+            const size_t cnt = std::min<size_t>(65535, groups[g].size() - off);
+            uint32_t max_blk = 1;
+            for (size_t i = 0; i < cnt; ++i) max_blk = std::max(max_blk, groups[g][off + i].nblk);
+            int rc = ensure_batch_scratch(c, cnt, max_blk);
+            if (rc) return rc;
+            // The descriptor area is double-buffered; pageable-source cudaMemcpyAsync stages the bytes before returning,
+            // so the host vector may die right after.  Stream order protects the device copy between launches.
+            char* dst = static_cast<char*>(c->batch_segs) + (c->batch_flip ? c->batch_segs_bytes / 2 : 0);
+            c->batch_flip ^= 1;
+            CU(cudaMemcpyAsync(dst, groups[g].data() + off, cnt * sizeof(ReduceSeg), cudaMemcpyHostToDevice, c->stream));
+            CU(launch_reduce_stats_batch((mnr_dtype)keys[g].dtype, keys[g].tier, keys[g].masked != 0, minmax,
+                                         reinterpret_cast<const ReduceSeg*>(dst), (uint32_t)cnt, max_blk,
+                                         static_cast<AggRaw*>(c->batch_partials), static_cast<unsigned int*>(c->batch_tickets),
+                                         static_cast<AggRaw*>(out_device), c->stream));
+            c->launches++;
+        }
+    }
+    return MNR_OK;
+}
+
+int mnr_reduce_stats_batch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
+                           int with_minmax, mnr_agg* out_host) {
+    REQUIRE(c && (out_host || n == 0), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    if (n == 0) return MNR_OK;
+    CU(cudaSetDevice(c->device));
+    if (c->chunk_aggs_cap < n) {
+        if (c->chunk_aggs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->chunk_aggs)); c->chunk_aggs = nullptr; }
+        CU(cudaMalloc(&c->chunk_aggs, sizeof(AggRaw) * n));
+        c->chunk_aggs_cap = n;
+    }
+    int rc = mnr_reduce_stats_batch_async(c, n, bufs, validities, with_minmax, c->chunk_aggs);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_host, c->chunk_aggs, sizeof(mnr_agg) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return MNR_OK;
 }
 
@@ -840,7 +940,7 @@ int mnr_stats_host(mnr_ctx* c, mnr_dtype dtype, const void* data, size_t len, co
             if (validity) CU(cudaMemcpyAsync(st[4], validity + r0 / 8, mask_bytes(rows), cudaMemcpyHostToDevice, s));
         }
         CU(launch_reduce_stats(dtype, st[0], validity ? static_cast<uint8_t*>(st[4]) : nullptr, rows, with_minmax != 0,
-                               c->partials[sl], c->ticket[sl], c->chunk_aggs + k, s));
+                               c->partials[sl], c->ticket[sl], c->chunk_aggs + k, nullptr, s));
         c->launches++;
     }
     rc = sync_slots(c);

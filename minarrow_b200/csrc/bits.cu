@@ -40,51 +40,55 @@ template <typename W> __device__ __forceinline__ W bit_op(int op, W a, W b) {
 
 constexpr int kBBlock = 256, kBU = 4;
 
+template <typename VecT>
 __global__ void __launch_bounds__(kBBlock)
 bits_op_kernel(int op, const uint8_t* __restrict__ a, uint64_t a_pos, uint64_t a_nbytes, const uint8_t* __restrict__ b,
                uint64_t b_pos, uint64_t b_nbytes, uint64_t len, uint8_t* __restrict__ out, uint64_t nvec) {
     const bool two = op <= B_XNOR;
     // ---- vector body: nvec 16-byte vectors (0 when the window is not vector-eligible) ----
     if (nvec) {
-        const V16* __restrict__ va = reinterpret_cast<const V16*>(a + (a_pos >> 3));
-        const V16* __restrict__ vb = two ? reinterpret_cast<const V16*>(b + (b_pos >> 3)) : nullptr;
-        V16* __restrict__ vo = reinterpret_cast<V16*>(out);
+        const VecT* __restrict__ va = reinterpret_cast<const VecT*>(a + (a_pos >> 3));
+        const VecT* __restrict__ vb = two ? reinterpret_cast<const VecT*>(b + (b_pos >> 3)) : nullptr;
+        VecT* __restrict__ vo = reinterpret_cast<VecT*>(out);
         const uint64_t warps = (uint64_t)gridDim.x * (kBBlock / 32);
         const uint64_t gwarp = (uint64_t)blockIdx.x * (kBBlock / 32) + (threadIdx.x >> 5);
         const int lane = threadIdx.x & 31;
         constexpr uint64_t WTILE = 32ull * kBU;
+        constexpr int NW = sizeof(VecT) / 8;
+        union VU { VecT v; uint64_t w[NW]; };
         const uint64_t ntiles = nvec / WTILE;
         for (uint64_t t = gwarp; t < ntiles; t += warps) {
             const uint64_t v0 = t * WTILE + lane;
-            V16 x[kBU], y[kBU];
+            VU x[kBU], y[kBU];
 #pragma unroll
-            for (int u = 0; u < kBU; ++u) x[u] = ldg_stream(va + v0 + 32ull * u);
+            for (int u = 0; u < kBU; ++u) x[u].v = ldg_stream(va + v0 + 32ull * u);
             if (two) {
 #pragma unroll
-                for (int u = 0; u < kBU; ++u) y[u] = ldg_stream(vb + v0 + 32ull * u);
+                for (int u = 0; u < kBU; ++u) y[u].v = ldg_stream(vb + v0 + 32ull * u);
             }
 #pragma unroll
             for (int u = 0; u < kBU; ++u) {
-                V16 r;
-                r.x = bit_op(op, x[u].x, two ? y[u].x : (uint64_t)0);
-                r.y = bit_op(op, x[u].y, two ? y[u].y : (uint64_t)0);
-                stg_stream(vo + v0 + 32ull * u, r);
+                VU r;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) r.w[k] = bit_op(op, x[u].w[k], two ? y[u].w[k] : (uint64_t)0);
+                stg_stream(vo + v0 + 32ull * u, r.v);
             }
         }
         for (uint64_t v = ntiles * WTILE + (uint64_t)blockIdx.x * kBBlock + threadIdx.x; v < nvec;
              v += (uint64_t)gridDim.x * kBBlock) {
-            const V16 x = ldg_stream(va + v);
-            V16 y{0, 0};
-            if (two) y = ldg_stream(vb + v);
-            V16 r;
-            r.x = bit_op(op, x.x, y.x);
-            r.y = bit_op(op, x.y, y.y);
-            stg_stream(vo + v, r);
+            VU x, y, r;
+            x.v = ldg_stream(va + v);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) y.w[k] = 0;
+            if (two) y.v = ldg_stream(vb + v);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) r.w[k] = bit_op(op, x.w[k], y.w[k]);
+            stg_stream(vo + v, r.v);
         }
     }
-    // ---- byte path: output bytes [16*nvec, ceil(len/8)) ----
+    // ---- byte path: output bytes [sizeof(VecT)*nvec, ceil(len/8)) ----
     const uint64_t nbytes = (len + 7) >> 3;
-    for (uint64_t i = nvec * 16 + (uint64_t)blockIdx.x * kBBlock + threadIdx.x; i < nbytes;
+    for (uint64_t i = nvec * sizeof(VecT) + (uint64_t)blockIdx.x * kBBlock + threadIdx.x; i < nbytes;
          i += (uint64_t)gridDim.x * kBBlock) {
         const uint32_t x = fetch_byte(a, a_pos + 8 * i, a_nbytes);
         const uint32_t y = two ? fetch_byte(b, b_pos + 8 * i, b_nbytes) : 0u;
@@ -94,17 +98,19 @@ bits_op_kernel(int op, const uint8_t* __restrict__ a, uint64_t a_pos, uint64_t a
     }
 }
 
-static bool vec_eligible(const uint8_t* p, uint64_t pos) {
-    return (pos & 7) == 0 && ((reinterpret_cast<uintptr_t>(p) + (pos >> 3)) & 15u) == 0;
+static bool vec_eligible(const uint8_t* p, uint64_t pos, unsigned align = 16) {
+    return (pos & 7) == 0 && ((reinterpret_cast<uintptr_t>(p) + (pos >> 3)) & (align - 1)) == 0;
 }
 
 cudaError_t launch_bits_op(int op, const uint8_t* a, uint64_t a_pos, uint64_t a_total, const uint8_t* b, uint64_t b_pos,
                            uint64_t b_total, uint64_t len, uint8_t* out, cudaStream_t s) {
     if (len == 0) return cudaSuccess;
     const bool two = op <= B_XNOR;
-    const bool vec = vec_eligible(a, a_pos) && (!two || vec_eligible(b, b_pos)) &&
-                     (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-    const uint64_t nvec = vec ? (len >> 3) / 16 : 0;   // only whole bytes fully inside the window
+    auto elig = [&](unsigned al) {
+        return vec_eligible(a, a_pos, al) && (!two || vec_eligible(b, b_pos, al)) && (reinterpret_cast<uintptr_t>(out) & (al - 1)) == 0;
+    };
+    const unsigned vbytes = elig(32) ? 32 : elig(16) ? 16 : 0;   // 256-bit vectors when every window start allows it
+    const uint64_t nvec = vbytes ? (len >> 3) / vbytes : 0;      // only whole bytes fully inside the window
     const uint64_t nbytes = (len + 7) >> 3;
     uint64_t blocks;
     if (nvec) {
@@ -114,16 +120,22 @@ cudaError_t launch_bits_op(int op, const uint8_t* a, uint64_t a_pos, uint64_t a_
         blocks = (nbytes + kBBlock - 1) / kBBlock;
     }
     if (blocks < 1) blocks = 1;
-    if (blocks > (uint64_t)kSMs * 64) blocks = (uint64_t)kSMs * 64;
-    bits_op_kernel<<<(unsigned)blocks, kBBlock, 0, s>>>(op, a, a_pos, (a_total + 7) >> 3, b, b_pos, (b_total + 7) >> 3,
-                                                         len, out, nvec);
+    if (blocks > 0x7fffffffull) blocks = 0x7fffffffull;
+    if (vbytes == 32)
+        bits_op_kernel<V32><<<(unsigned)blocks, kBBlock, 0, s>>>(op, a, a_pos, (a_total + 7) >> 3, b, b_pos, (b_total + 7) >> 3,
+                                                                  len, out, nvec);
+    else
+        bits_op_kernel<V16><<<(unsigned)blocks, kBBlock, 0, s>>>(op, a, a_pos, (a_total + 7) >> 3, b, b_pos, (b_total + 7) >> 3,
+                                                                  len, out, nvec);
     return cudaGetLastError();
 }
 
 // Popcount of a window, optionally of (a xor b) — the latter answers all_eq (simd.rs:511-581) in one pass.
 __global__ void __launch_bounds__(kBBlock)
 bits_popcount_kernel(const uint8_t* __restrict__ a, uint64_t a_pos, uint64_t a_nbytes, const uint8_t* __restrict__ b,
-                     uint64_t b_pos, uint64_t b_nbytes, uint64_t len, uint64_t nvec, unsigned long long* __restrict__ result) {
+                     uint64_t b_pos, uint64_t b_nbytes, uint64_t len, uint64_t nvec, unsigned long long* __restrict__ partials,
+                     unsigned int* __restrict__ ticket, unsigned long long* __restrict__ result,
+                     unsigned long long* __restrict__ result_host) {
     const bool two = b != nullptr;
     unsigned long long acc = 0;
     if (nvec) {
@@ -164,22 +176,51 @@ bits_popcount_kernel(const uint8_t* __restrict__ a, uint64_t a_pos, uint64_t a_n
         if (i == nbytes - 1 && (len & 7)) x &= (1u << (uint32_t)(len & 7)) - 1u;
         acc += (unsigned)__popc(x);
     }
-    // block reduce (integer: order irrelevant) -> one atomic per block
+    // block sum -> one partial per block -> the last block to arrive (atomic ticket) adds the partials and stores the
+    // result (and, for the synchronous API, a second copy straight into mapped pinned host memory).
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     __shared__ unsigned long long sm[kBBlock / 32];
+    __shared__ bool is_last;
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
 #pragma unroll
         for (int w = 0; w < kBBlock / 32; ++w) t += sm[w];
-        if (t) atomicAdd(result, t);
+        partials[blockIdx.x] = t;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    unsigned long long t = 0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBBlock) {
+        unsigned long long v;
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(partials + i));
+        t += v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long r = 0;
+#pragma unroll
+        for (int w = 0; w < kBBlock / 32; ++w) r += sm[w];
+        *result = r;
+        if (result_host) { *result_host = r; __threadfence_system(); }
+        *ticket = 0;
     }
 }
 
+int popcount_max_grid() { return kSMs * 8; }
+
 cudaError_t launch_bits_popcount(const uint8_t* a, uint64_t a_pos, uint64_t a_total, const uint8_t* b, uint64_t b_pos,
-                                 uint64_t b_total, uint64_t len, unsigned long long* result, cudaStream_t s) {
+                                 uint64_t b_total, uint64_t len, unsigned long long* partials, unsigned int* ticket,
+                                 unsigned long long* result, unsigned long long* result_host, cudaStream_t s) {
     if (len == 0) return cudaSuccess;
     const bool vec = vec_eligible(a, a_pos) && (!b || vec_eligible(b, b_pos));
     const uint64_t nvec = vec ? (len >> 3) / 16 : 0;
@@ -194,7 +235,7 @@ cudaError_t launch_bits_popcount(const uint8_t* a, uint64_t a_pos, uint64_t a_to
     if (blocks < 1) blocks = 1;
     if (blocks > (uint64_t)kSMs * 8) blocks = (uint64_t)kSMs * 8;
     bits_popcount_kernel<<<(unsigned)blocks, kBBlock, 0, s>>>(a, a_pos, (a_total + 7) >> 3, b, b_pos, (b_total + 7) >> 3,
-                                                               len, nvec, result);
+                                                               len, nvec, partials, ticket, result, result_host);
     return cudaGetLastError();
 }
 

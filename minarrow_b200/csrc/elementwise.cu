@@ -1,20 +1,26 @@
 // Launch dispatch for the element-wise kernels (ew_kernels.cuh).
+//
+// This file is compiled once per element type (-DMNR_EW_DTYPE=<mnr_dtype code>, see the Makefile) so the template
+// instantiations build in parallel; -DMNR_EW_DTYPE=100 builds the type-independent front (dtype switch, promotion,
+// FMA).  Launch geometry comes from the on-device sweep (tools/sweep.cu, profiles/r01c_sweep.md):
+//   * cheap ops (add/sub/mul, incl. scalar broadcast): 256-bit vectors, 4 in flight per operand, 128-thread blocks,
+//     one warp tile per warp (grid covers the column)                       -> f64 masked add 7.08-7.12 TB/s
+//   * div / floordiv / rem / pow (ALU-heavy): 128-bit vectors, 2 in flight, 256 threads, <= 64 registers
+//     (4 blocks/SM), persistent grid of one resident wave                  -> f64 masked div 6.5 TB/s
 #include "ew_kernels.cuh"
 
 namespace mnr {
 
-constexpr int kEBlock = 256, kEU = 4;
-int g_ew_grid_cap = 0;   // 0: one warp tile per warp (grid covers the column); >0: persistent grid of that many blocks
+#if MNR_EW_DTYPE == 100
+int g_ew_grid_cap = 0;   // >0: cap every element-wise grid at this many blocks (tuning knob, mnr_ctx_set_option)
+#else
+extern int g_ew_grid_cap;
+#endif
 
-static unsigned ew_grid(uint64_t n, int vec) {
-    const uint64_t nvec = (n + vec - 1) / vec;
-    const uint64_t tiles = (nvec + 32ull * kEU - 1) / (32ull * kEU);
-    uint64_t blocks = (tiles + (kEBlock / 32) - 1) / (kEBlock / 32);
-    if (blocks < 1) blocks = 1;
-    if (g_ew_grid_cap > 0 && blocks > (uint64_t)g_ew_grid_cap) blocks = (uint64_t)g_ew_grid_cap;
-    if (blocks > 0x7fffffffull) blocks = 0x7fffffffull;
-    return (unsigned)blocks;
-}
+struct CfgCheap { static constexpr int BLOCK = 128, U = 4, MINB = 1; static constexpr bool RESIDENT = false; using Wide = V32; };
+struct CfgHeavy { static constexpr int BLOCK = 256, U = 2, MINB = 4; static constexpr bool RESIDENT = true; using Wide = V16; };
+template <int CLS> struct CfgOf { using type = CfgHeavy; };
+template <> struct CfgOf<CLS_CHEAP> { using type = CfgCheap; };
 
 static EwDev to_dev(const EwArgs& a) {
     EwDev d;
@@ -23,22 +29,40 @@ static EwDev to_dev(const EwArgs& a) {
     return d;
 }
 
+template <int BLOCK, int U, int MINB, bool RESIDENT>
+static unsigned ew_grid(uint64_t n, int vec) {
+    const uint64_t nvec = (n + vec - 1) / vec;
+    const uint64_t tiles = (nvec + 32ull * U - 1) / (32ull * U);
+    uint64_t blocks = (tiles + (BLOCK / 32) - 1) / (BLOCK / 32);
+    if (blocks < 1) blocks = 1;
+    if (RESIDENT && blocks > (uint64_t)kSMs * MINB) blocks = (uint64_t)kSMs * MINB;
+    if (g_ew_grid_cap > 0 && blocks > (uint64_t)g_ew_grid_cap) blocks = (uint64_t)g_ew_grid_cap;
+    if (blocks > 0x7fffffffull) blocks = 0x7fffffffull;
+    return (unsigned)blocks;
+}
+
 template <typename T, typename TL, typename TR, typename VecT, int CLS>
 static cudaError_t go(const EwArgs& a, cudaStream_t s) {
+    using Cfg = typename CfgOf<CLS>::type;
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     const bool masked = a.lmask || a.rmask;
-    const unsigned grid = ew_grid(a.n, VEC);
-    if (masked) ew_binary_kernel<T, TL, TR, VecT, CLS, true, kEBlock, kEU><<<grid, kEBlock, 0, s>>>(to_dev(a));
-    else ew_binary_kernel<T, TL, TR, VecT, CLS, false, kEBlock, kEU><<<grid, kEBlock, 0, s>>>(to_dev(a));
+    const unsigned grid = ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(a.n, VEC);
+    if (masked) ew_binary_kernel<T, TL, TR, VecT, CLS, true, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(to_dev(a));
+    else ew_binary_kernel<T, TL, TR, VecT, CLS, false, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(to_dev(a));
     return cudaGetLastError();
 }
 
+// Alignment tiers, like the reference's "64-byte aligned -> SIMD body, else scalar body" (dispatch.rs:86,108-111):
+// widest vector every operand pointer allows, else 128-bit, else element-wise loads.
 template <typename T, typename TL, typename TR, int CLS>
 static cudaError_t go_align(const EwArgs& a, cudaStream_t s) {
-    constexpr int VEC = 16 / sizeof(T);
+    using Wide = typename CfgOf<CLS>::type::Wide;
     auto ok = [](const void* p, size_t align) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % align) == 0; };
-    const bool vec_ok = ok(a.lhs, sizeof(TL) * VEC) && ok(a.rhs, sizeof(TR) * VEC) && ok(a.out, 16);
-    if (vec_ok) return go<T, TL, TR, V16, CLS>(a, s);
+    constexpr int VW = sizeof(Wide) / sizeof(T);
+    if (sizeof(Wide) > 16 && ok(a.lhs, sizeof(TL) * VW) && ok(a.rhs, sizeof(TR) * VW) && ok(a.out, sizeof(Wide)))
+        return go<T, TL, TR, Wide, CLS>(a, s);
+    constexpr int V = 16 / sizeof(T);
+    if (ok(a.lhs, sizeof(TL) * V) && ok(a.rhs, sizeof(TR) * V) && ok(a.out, 16)) return go<T, TL, TR, V16, CLS>(a, s);
     return go<T, TL, TR, T, CLS>(a, s);
 }
 
@@ -55,18 +79,54 @@ static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
     return cudaErrorInvalidValue;
 }
 
+#define MNR_EW_ENTRY(NAME, T) \
+    cudaError_t NAME(const EwArgs& a, cudaStream_t s) { return go_t<T>(a, s); }
+
+#if MNR_EW_DTYPE == 6
+MNR_EW_ENTRY(launch_ew_i8, int8_t)
+#elif MNR_EW_DTYPE == 7
+MNR_EW_ENTRY(launch_ew_u8, uint8_t)
+#elif MNR_EW_DTYPE == 8
+MNR_EW_ENTRY(launch_ew_i16, int16_t)
+#elif MNR_EW_DTYPE == 9
+MNR_EW_ENTRY(launch_ew_u16, uint16_t)
+#elif MNR_EW_DTYPE == 0
+MNR_EW_ENTRY(launch_ew_i32, int32_t)
+#elif MNR_EW_DTYPE == 1
+MNR_EW_ENTRY(launch_ew_u32, uint32_t)
+#elif MNR_EW_DTYPE == 2
+MNR_EW_ENTRY(launch_ew_i64, int64_t)
+#elif MNR_EW_DTYPE == 3
+MNR_EW_ENTRY(launch_ew_u64, uint64_t)
+#elif MNR_EW_DTYPE == 4
+MNR_EW_ENTRY(launch_ew_f32, float)
+#elif MNR_EW_DTYPE == 5
+MNR_EW_ENTRY(launch_ew_f64, double)
+#elif MNR_EW_DTYPE == 100
+
+cudaError_t launch_ew_i8(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_u8(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_i16(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_u16(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_i32(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_u32(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_i64(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_u64(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_f32(const EwArgs&, cudaStream_t);
+cudaError_t launch_ew_f64(const EwArgs&, cudaStream_t);
+
 cudaError_t launch_ew_binary(const EwArgs& a, cudaStream_t s) {
     switch (a.dtype) {
-        case MNR_I8: return go_t<int8_t>(a, s);
-        case MNR_U8: return go_t<uint8_t>(a, s);
-        case MNR_I16: return go_t<int16_t>(a, s);
-        case MNR_U16: return go_t<uint16_t>(a, s);
-        case MNR_I32: return go_t<int32_t>(a, s);
-        case MNR_U32: return go_t<uint32_t>(a, s);
-        case MNR_I64: return go_t<int64_t>(a, s);
-        case MNR_U64: return go_t<uint64_t>(a, s);
-        case MNR_F32: return go_t<float>(a, s);
-        case MNR_F64: return go_t<double>(a, s);
+        case MNR_I8: return launch_ew_i8(a, s);
+        case MNR_U8: return launch_ew_u8(a, s);
+        case MNR_I16: return launch_ew_i16(a, s);
+        case MNR_U16: return launch_ew_u16(a, s);
+        case MNR_I32: return launch_ew_i32(a, s);
+        case MNR_U32: return launch_ew_u32(a, s);
+        case MNR_I64: return launch_ew_i64(a, s);
+        case MNR_U64: return launch_ew_u64(a, s);
+        case MNR_F32: return launch_ew_f32(a, s);
+        case MNR_F64: return launch_ew_f64(a, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -93,23 +153,30 @@ cudaError_t launch_ew_promote(const EwArgs& a, mnr_dtype lt, mnr_dtype rt, cudaS
     return cudaErrorInvalidValue;
 }
 
+constexpr int kFBlock = 128, kFU = 2;
+
+template <typename T, typename VecT>
+static cudaError_t fma_v(const T* pa, const T* pb, const T* pc, const uint8_t* mask, T* po, uint8_t* out_mask, uint64_t n,
+                         cudaStream_t s) {
+    constexpr int VEC = sizeof(VecT) / sizeof(T);
+    const unsigned grid = ew_grid<kFBlock, kFU, 1, false>(n, VEC);
+    if (mask) ew_fma_kernel<T, VecT, true, kFBlock, kFU><<<grid, kFBlock, 0, s>>>(pa, pb, pc, mask, po, out_mask, n);
+    else ew_fma_kernel<T, VecT, false, kFBlock, kFU><<<grid, kFBlock, 0, s>>>(pa, pb, pc, mask, po, out_mask, n);
+    return cudaGetLastError();
+}
+
 template <typename T>
 static cudaError_t fma_t(const void* a, const void* b, const void* c, const uint8_t* mask, void* out, uint8_t* out_mask,
                          uint64_t n, cudaStream_t s) {
-    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    const bool vec_ok = al(a) && al(b) && al(c) && al(out);
-    const int vec = vec_ok ? 16 / (int)sizeof(T) : 1;
-    const unsigned grid = ew_grid(n, vec);
+    auto al = [&](unsigned m) {
+        return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                 reinterpret_cast<uintptr_t>(out)) & m) == 0;
+    };
     const T *pa = static_cast<const T*>(a), *pb = static_cast<const T*>(b), *pc = static_cast<const T*>(c);
     T* po = static_cast<T*>(out);
-    if (vec_ok) {
-        if (mask) ew_fma_kernel<T, V16, true, kEBlock, kEU><<<grid, kEBlock, 0, s>>>(pa, pb, pc, mask, po, out_mask, n);
-        else ew_fma_kernel<T, V16, false, kEBlock, kEU><<<grid, kEBlock, 0, s>>>(pa, pb, pc, mask, po, out_mask, n);
-    } else {
-        if (mask) ew_fma_kernel<T, T, true, kEBlock, kEU><<<grid, kEBlock, 0, s>>>(pa, pb, pc, mask, po, out_mask, n);
-        else ew_fma_kernel<T, T, false, kEBlock, kEU><<<grid, kEBlock, 0, s>>>(pa, pb, pc, mask, po, out_mask, n);
-    }
-    return cudaGetLastError();
+    if (al(31u)) return fma_v<T, V32>(pa, pb, pc, mask, po, out_mask, n, s);
+    if (al(15u)) return fma_v<T, V16>(pa, pb, pc, mask, po, out_mask, n, s);
+    return fma_v<T, T>(pa, pb, pc, mask, po, out_mask, n, s);
 }
 
 cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void* c, const uint8_t* mask, void* out,
@@ -118,5 +185,8 @@ cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void
     if (dt == MNR_F64) return fma_t<double>(a, b, c, mask, out, out_mask, n, s);
     return cudaErrorInvalidValue;
 }
+#else
+#error "compile elementwise.cu with -DMNR_EW_DTYPE=<0..9 | 100>"
+#endif
 
 }  // namespace mnr

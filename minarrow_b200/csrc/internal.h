@@ -11,8 +11,16 @@ struct AggRaw;
 
 // ---- kernel launchers (one per .cu) --------------------------------------------------------------------
 int reduce_max_grid();
+// out_host: optional mapped pinned host address that receives a second copy of the aggregate (NULL = none).
 cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
-                                AggRaw* partials, unsigned int* ticket, AggRaw* out, cudaStream_t s);
+                                AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s);
+// Batched form: one launch for `nseg` columns/chunks of one (dtype, alignment tier, masked) class.
+struct ReduceSeg;
+int reduce_tier(const void* data, bool minmax);
+uint32_t reduce_nblk(mnr_dtype dt, uint64_t n, int tier, bool minmax);
+cudaError_t launch_reduce_stats_batch(mnr_dtype dt, int tier, bool masked, bool minmax, const ReduceSeg* segs,
+                                      uint32_t nseg, uint32_t max_blk, AggRaw* partials, unsigned int* tickets,
+                                      AggRaw* outs, cudaStream_t s);
 
 // Element-wise binary op.  lhs/rhs: device pointers, or NULL for the side held in `scalar_bits`
 // (at most one).  lmask/rmask: NULL or validity bytes indexed from bit 0.  out_mask: required iff a mask is
@@ -42,10 +50,13 @@ cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void
 // slack bits of the last byte zero; reads stay inside [0, ceil(x_bits_total/8)).
 cudaError_t launch_bits_op(int op, const uint8_t* a, uint64_t a_bitpos, uint64_t a_total_bits, const uint8_t* b,
                            uint64_t b_bitpos, uint64_t b_total_bits, uint64_t len, uint8_t* out, cudaStream_t s);
-// Popcount of (a [xor b]) over len bits from the given bit positions; accumulates into *result (pre-zeroed).
+// Popcount of (a [xor b]) over len bits from the given bit positions -> *result (device) and, if non-NULL,
+// *result_host (mapped pinned host memory).  partials: >= popcount_max_grid() words; ticket: zeroed, re-armed by the kernel.
+int popcount_max_grid();
 cudaError_t launch_bits_popcount(const uint8_t* a, uint64_t a_bitpos, uint64_t a_total_bits, const uint8_t* b,
-                                 uint64_t b_bitpos, uint64_t b_total_bits, uint64_t len,
-                                 unsigned long long* result, cudaStream_t s);
+                                 uint64_t b_bitpos, uint64_t b_total_bits, uint64_t len, unsigned long long* partials,
+                                 unsigned int* ticket, unsigned long long* result, unsigned long long* result_host,
+                                 cudaStream_t s);
 
 }  // namespace mnr
 
@@ -68,6 +79,14 @@ struct mnr_ctx {
     size_t host_chunk_rows = (size_t)1 << 22;
     mnr::AggRaw* chunk_aggs = nullptr;     // one aggregate per chunk of mnr_stats_host
     size_t chunk_aggs_cap = 0;
+    // batched reductions: per-segment partials / descriptors (double-buffered) / tickets
+    void* batch_partials = nullptr;
+    size_t batch_partials_bytes = 0;
+    void* batch_segs = nullptr;
+    size_t batch_segs_bytes = 0;
+    void* batch_tickets = nullptr;
+    size_t batch_tickets_bytes = 0;
+    int batch_flip = 0;
 };
 
 struct mnr_buf {

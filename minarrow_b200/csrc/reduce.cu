@@ -4,60 +4,121 @@
 
 namespace mnr {
 
-// Library configuration, chosen from the on-device sweep in profiles/ (tools/sweep_kernels.cu):
-// 256-thread blocks, >= 4 resident blocks per SM (<= 64 registers), 4 x 128-bit loads in flight per lane.
-// Grid = min(tiles, 148 SMs x 4 blocks): one resident wave, every warp owns the same number of tiles.
-constexpr int kRBlock = 256, kRMinB = 4, kRU = 4;
+// Launch geometry from the on-device sweep (tools/sweep.cu, profiles/r01c_sweep.md), 1e9-row masked i64:
+//   sum + count      : 128-bit loads, 4 in flight per lane, 256 threads, 4 blocks/SM (64 regs)  -> 7.35 TB/s
+//   + min / max      : 256-bit loads, 2 in flight per lane, same block shape                     -> 6.67 TB/s (128-bit: 5.6)
+// Grid = min(tiles, 148 SMs x resident blocks): a function of (len, dtype, alignment tier) only — never an
+// occupancy query — so a float sum is bit-reproducible run to run and device to device.
+constexpr int kRBlock = 256;
+template <typename T> struct RMinB { static constexpr int value = sizeof(T) >= 4 ? 4 : 2; };   // narrow types carry 8-32 slots
+template <typename VecT, bool MINMAX> struct RU { static constexpr int value = (sizeof(VecT) == 32) ? 2 : 4; };
 
-int reduce_max_grid() { return kSMs * kRMinB; }
+int reduce_max_grid() { return kSMs * 4; }
 
-template <typename T, typename VecT, bool MASKED, bool MINMAX>
-static cudaError_t launch_one(const void* data, const uint8_t* mask, uint64_t n, AggRaw* partials,
-                              unsigned int* ticket, AggRaw* out, cudaStream_t s) {
+// tier: 0 = element loads, 1 = 128-bit, 2 = 256-bit (only used with min/max)
+int reduce_tier(const void* data, bool minmax) {
+    const uintptr_t p = reinterpret_cast<uintptr_t>(data);
+    if (minmax && (p & 31u) == 0) return 2;
+    return (p & 15u) == 0 ? 1 : 0;
+}
+
+template <typename T, typename VecT, bool MINMAX> static uint32_t nblk_of(uint64_t n) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     const uint64_t nvec = n / VEC;
-    const uint64_t tile = (uint64_t)kRBlock * kRU;
-    // Narrow types carry 8-16 slot accumulators per lane: give them 128 registers (2 blocks/SM) instead of 64.
-    constexpr int MINB = sizeof(T) >= 4 ? kRMinB : 2;
-    const uint64_t cap = (uint64_t)kSMs * MINB;
+    const uint64_t tile = (uint64_t)kRBlock * RU<VecT, MINMAX>::value;
+    const uint64_t cap = (uint64_t)kSMs * RMinB<T>::value;
     uint64_t blocks = (nvec + tile - 1) / tile;
     if (blocks < 1) blocks = 1;
     if (blocks > cap) blocks = cap;
-    reduce_stats_kernel<T, VecT, MASKED, MINMAX, kRBlock, MINB, kRU>
-        <<<(unsigned)blocks, kRBlock, 0, s>>>(static_cast<const T*>(data), mask, n, partials, ticket, out);
+    return (uint32_t)blocks;
+}
+
+template <typename T, typename VecT, bool MASKED, bool MINMAX>
+static cudaError_t launch_one(const void* data, const uint8_t* mask, uint64_t n, AggRaw* partials, unsigned int* ticket,
+                              AggRaw* out, AggRaw* out_host, cudaStream_t s) {
+    reduce_stats_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>
+        <<<nblk_of<T, VecT, MINMAX>(n), kRBlock, 0, s>>>(static_cast<const T*>(data), mask, n, partials, ticket, out, out_host);
     return cudaGetLastError();
 }
 
-template <typename T>
-static cudaError_t launch_t(const void* data, const uint8_t* mask, uint64_t n, bool minmax, AggRaw* partials,
-                            unsigned int* ticket, AggRaw* out, cudaStream_t s) {
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(data) & 15u) == 0;
-#define MNR_GO(V)                                                                                         \
-    do {                                                                                                  \
-        if (mask) return minmax ? launch_one<T, V, true, true>(data, mask, n, partials, ticket, out, s)   \
-                                : launch_one<T, V, true, false>(data, mask, n, partials, ticket, out, s); \
-        return minmax ? launch_one<T, V, false, true>(data, mask, n, partials, ticket, out, s)            \
-                      : launch_one<T, V, false, false>(data, mask, n, partials, ticket, out, s);          \
-    } while (0)
-    if (vec_ok) MNR_GO(V16);
-    MNR_GO(T);
-#undef MNR_GO
+template <typename T, typename VecT, bool MASKED, bool MINMAX>
+static cudaError_t launch_batch_one(const ReduceSeg* segs, uint32_t nseg, uint32_t max_blk, AggRaw* partials,
+                                    unsigned int* tickets, AggRaw* outs, cudaStream_t s) {
+    reduce_stats_batch_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>
+        <<<dim3(max_blk, nseg, 1), kRBlock, 0, s>>>(segs, partials, tickets, outs, max_blk);
+    return cudaGetLastError();
 }
 
-cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
-                                AggRaw* partials, unsigned int* ticket, AggRaw* out, cudaStream_t s) {
-    switch (dt) {
-        case MNR_I8: return launch_t<int8_t>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_U8: return launch_t<uint8_t>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_I16: return launch_t<int16_t>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_U16: return launch_t<uint16_t>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_I32: return launch_t<int32_t>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_U32: return launch_t<uint32_t>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_I64: return launch_t<int64_t>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_U64: return launch_t<uint64_t>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_F32: return launch_t<float>(data, mask, n, minmax, partials, ticket, out, s);
-        case MNR_F64: return launch_t<double>(data, mask, n, minmax, partials, ticket, out, s);
+// (tier, masked, minmax) -> instantiation.  The 256-bit tier exists only with min/max.
+#define MNR_REDUCE_DISPATCH(CALL)                                        \
+    do {                                                                 \
+        if (minmax) {                                                    \
+            if (tier == 2) { if (masked) CALL(V32, true, true); else CALL(V32, false, true); } \
+            if (tier == 1) { if (masked) CALL(V16, true, true); else CALL(V16, false, true); } \
+            if (masked) CALL(T, true, true); else CALL(T, false, true);  \
+        } else {                                                         \
+            if (tier >= 1) { if (masked) CALL(V16, true, false); else CALL(V16, false, false); } \
+            if (masked) CALL(T, true, false); else CALL(T, false, false); \
+        }                                                                \
+    } while (0)
+
+template <typename T>
+static cudaError_t launch_t(const void* data, const uint8_t* mask, uint64_t n, bool minmax, AggRaw* partials,
+                            unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s) {
+    const int tier = reduce_tier(data, minmax);
+    const bool masked = mask != nullptr;
+#define CALL1(V, M, X) return launch_one<T, V, M, X>(data, mask, n, partials, ticket, out, out_host, s)
+    MNR_REDUCE_DISPATCH(CALL1);
+#undef CALL1
+}
+
+template <typename T>
+static uint32_t nblk_t(uint64_t n, int tier, bool minmax) {
+    if (minmax) {
+        if (tier == 2) return nblk_of<T, V32, true>(n);
+        if (tier == 1) return nblk_of<T, V16, true>(n);
+        return nblk_of<T, T, true>(n);
     }
+    return tier >= 1 ? nblk_of<T, V16, false>(n) : nblk_of<T, T, false>(n);
+}
+
+template <typename T>
+static cudaError_t batch_t(int tier, bool masked, bool minmax, const ReduceSeg* segs, uint32_t nseg, uint32_t max_blk,
+                           AggRaw* partials, unsigned int* tickets, AggRaw* outs, cudaStream_t s) {
+#define CALLB(V, M, X) return launch_batch_one<T, V, M, X>(segs, nseg, max_blk, partials, tickets, outs, s)
+    MNR_REDUCE_DISPATCH(CALLB);
+#undef CALLB
+}
+
+#define MNR_DTYPE_SWITCH(dt, EXPR)                      \
+    switch (dt) {                                       \
+        case MNR_I8: { using T = int8_t; EXPR; }        \
+        case MNR_U8: { using T = uint8_t; EXPR; }       \
+        case MNR_I16: { using T = int16_t; EXPR; }      \
+        case MNR_U16: { using T = uint16_t; EXPR; }     \
+        case MNR_I32: { using T = int32_t; EXPR; }      \
+        case MNR_U32: { using T = uint32_t; EXPR; }     \
+        case MNR_I64: { using T = int64_t; EXPR; }      \
+        case MNR_U64: { using T = uint64_t; EXPR; }     \
+        case MNR_F32: { using T = float; EXPR; }        \
+        case MNR_F64: { using T = double; EXPR; }       \
+    }
+
+cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
+                                AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s) {
+    MNR_DTYPE_SWITCH(dt, return launch_t<T>(data, mask, n, minmax, partials, ticket, out, out_host, s));
+    return cudaErrorInvalidValue;
+}
+
+uint32_t reduce_nblk(mnr_dtype dt, uint64_t n, int tier, bool minmax) {
+    MNR_DTYPE_SWITCH(dt, return nblk_t<T>(n, tier, minmax));
+    return 1;
+}
+
+cudaError_t launch_reduce_stats_batch(mnr_dtype dt, int tier, bool masked, bool minmax, const ReduceSeg* segs,
+                                      uint32_t nseg, uint32_t max_blk, AggRaw* partials, unsigned int* tickets,
+                                      AggRaw* outs, cudaStream_t s) {
+    MNR_DTYPE_SWITCH(dt, return batch_t<T>(tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, s));
     return cudaErrorInvalidValue;
 }
 

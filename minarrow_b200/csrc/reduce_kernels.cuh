@@ -174,10 +174,14 @@ __device__ __forceinline__ AggRaw load_partial(const AggRaw* p) {   // L2-cohere
     return r;
 }
 
-template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MINB, int U>
-__global__ void __launch_bounds__(BLOCK, MINB)
-reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
-                    AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket, AggRaw* __restrict__ out) {
+// Body shared by the single-column kernel and the batched (one launch, many chunks) kernel.  `bid` / `nblk` are the
+// block's index and the number of blocks working on THIS column; nblk is a function of (len, dtype) only, so a column
+// reduced inside a batch gives the same bits as the same column reduced alone.
+template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int U>
+__device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
+                                                  AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                  AggRaw* __restrict__ out, AggRaw* __restrict__ out_host,
+                                                  const unsigned int bid, const unsigned int nblk) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     using A = typename Traits<T>::Acc;
     using P = Partial<T, MINMAX>;
@@ -193,8 +197,8 @@ reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask
     const uint64_t nvec = n / VEC;
     constexpr uint64_t WTILE = 32ull * U;                       // vectors per warp tile
     const uint64_t ntiles = nvec / WTILE;
-    const uint64_t warps = (uint64_t)gridDim.x * (BLOCK / 32);
-    const uint64_t gwarp = (uint64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    const uint64_t warps = (uint64_t)nblk * (BLOCK / 32);
+    const uint64_t gwarp = (uint64_t)bid * (BLOCK / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
 
     for (uint64_t t = gwarp; t < ntiles; t += warps) {
@@ -212,8 +216,8 @@ reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask
     }
     // Vectors past the last full warp tile (< 32*U of them), spread over the grid's first threads.
     {
-        const uint64_t gtid = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
-        for (uint64_t v = ntiles * WTILE + gtid; v < nvec; v += (uint64_t)gridDim.x * BLOCK) {
+        const uint64_t gtid = (uint64_t)bid * BLOCK + threadIdx.x;
+        for (uint64_t v = ntiles * WTILE + gtid; v < nvec; v += (uint64_t)nblk * BLOCK) {
             uint32_t b = 0;
             if constexpr (MASKED) b = load_valid_bits<VEC>(mask, v * VEC);
             accum_vec<T, VecT, MASKED, MINMAX>(ldg_stream(vp + v), b, slot, p);
@@ -240,26 +244,60 @@ reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask
 
     p = block_combine<P, BLOCK>(p, smem);
     if (threadIdx.x == 0) {
-        partials[blockIdx.x] = p.raw();
+        partials[bid] = p.raw();
         __threadfence();
         const unsigned int done = atomicAdd(ticket, 1u);
-        is_last = (done == gridDim.x - 1);
+        is_last = (done == nblk - 1);
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
     P q; q.init();
     bool first = true;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += BLOCK) {
+    for (unsigned int i = threadIdx.x; i < nblk; i += BLOCK) {
         P t; t.from_raw(load_partial(partials + i));
         if (first) { q = t; first = false; } else q.merge(t);
     }
     q = block_combine<P, BLOCK>(q, smem);
     if (threadIdx.x == 0) {
         if constexpr (!MASKED) q.cnt = n;
-        *out = q.raw();
+        const AggRaw r = q.raw();
+        *out = r;
+        if (out_host) {   // optional second copy straight into mapped pinned host memory (synchronous APIs: no D2H memcpy)
+            *out_host = r;
+            __threadfence_system();
+        }
         *ticket = 0;   // re-arm for the next launch on this stream
     }
+}
+
+template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MINB, int U>
+__global__ void __launch_bounds__(BLOCK, MINB)
+reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
+                    AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket, AggRaw* __restrict__ out,
+                    AggRaw* __restrict__ out_host) {
+    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(data, mask, n, partials, ticket, out, out_host, blockIdx.x, gridDim.x);
+}
+
+// One launch, many columns/chunks (SuperArray / SuperTable fan-out, broadcast/super_table.rs:38-73 walks them one
+// by one): blockIdx.y selects the segment, blockIdx.x the block inside it; blocks beyond a segment's own count exit.
+struct ReduceSeg {
+    const void* data;
+    const uint8_t* mask;
+    uint64_t n;
+    uint32_t nblk;      // blocks working on this segment ( = the single-launch grid for this length)
+    uint32_t out_index; // slot in `outs`
+};
+
+template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MINB, int U>
+__global__ void __launch_bounds__(BLOCK, MINB)
+reduce_stats_batch_kernel(const ReduceSeg* __restrict__ segs, AggRaw* __restrict__ partials, unsigned int* __restrict__ tickets,
+                          AggRaw* __restrict__ outs, uint32_t max_blk) {
+    const ReduceSeg s = segs[blockIdx.y];
+    if (blockIdx.x >= s.nblk) return;
+    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(static_cast<const T*>(s.data), s.mask, s.n,
+                                                        partials + (size_t)blockIdx.y * max_blk, tickets + blockIdx.y,
+                                                        outs + s.out_index, nullptr, blockIdx.x, s.nblk);
 }
 
 }  // namespace mnr

@@ -165,3 +165,30 @@ def reduce_stats_async(ctx: Context, buf: DeviceBuffer, validity: Optional[Devic
                        out_device_ptr: int) -> None:
     """Writes the 32-byte `mnr_agg` partial to device memory on the context stream (no sync)."""
     check(ctx.lib.mnr_reduce_stats_async(ctx.h, buf.h, _h(validity), int(with_minmax), C.c_void_p(out_device_ptr)))
+
+
+def _handle_array(items):
+    arr = (C.c_void_p * len(items))()
+    for i, x in enumerate(items):
+        arr[i] = None if x is None else x.h
+    return arr
+
+
+def reduce_stats_batch(ctx: Context, bufs, validities=None, with_minmax: bool = True) -> list:
+    """{sum, min, max, count, mean} of many device columns/chunks with one launch per (dtype, alignment, masked)
+    class (the per-chunk / per-column loops of broadcast/super_array.rs:180-249 and table.rs:31-62 in one call)."""
+    n = len(bufs)
+    if n == 0:
+        return []
+    aggs = (_lib.Agg * n)()
+    vals = None if validities is None else _handle_array(list(validities))
+    check(ctx.lib.mnr_reduce_stats_batch(ctx.h, n, _handle_array(list(bufs)), vals, int(with_minmax), aggs))
+    return [_agg_dict(b.dtype, a, ctx.lib) for b, a in zip(bufs, aggs)]
+
+
+def reduce_stats_batch_async(ctx: Context, bufs, validities, with_minmax: bool, out_device_ptr: int) -> None:
+    """Writes len(bufs) x 32-byte `mnr_agg` to device memory on the context stream (no sync)."""
+    n = len(bufs)
+    vals = None if validities is None else _handle_array(list(validities))
+    check(ctx.lib.mnr_reduce_stats_batch_async(ctx.h, n, _handle_array(list(bufs)), vals, int(with_minmax),
+                                               C.c_void_p(out_device_ptr)))
