@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-rows", type=int, default=1 << 28, help="rows of the bounded CPU sample")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-supertable", action="store_true", help="skip the 73 GiB configs[4] part of the secondary set")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -270,7 +271,7 @@ def event_time_ms(torch, fn, iters, warmup=3):
     return ts[len(ts) // 2], ts[0]
 
 
-def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows):
+def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows, supertable=True):
     """The other BASELINE configs, each kernel timed alone (median of 20, inputs >> L2)."""
     import numpy as np
     devops = mnr.device_ops
@@ -332,6 +333,94 @@ def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows):
     entry("bitmask_not_4Gbit", nb * 2 / 8, lambda: devops.bits_not_into(ctx, Ab, 0, nb, Rb))
     entry("bitmask_popcount_4Gbit", nb / 8, lambda: devops.bits_popcount(ctx, Ab, 0, nb), iters=10)
     del Ab, Bb, Rb, a, b, r
+    torch.cuda.empty_cache()
+
+    # configs[0]: IntegerArray<i64> sum of 1 000 elements, averaged over 1 000 runs (hotloop_benchmark_simd shape).
+    # 8 KB is launch-latency-bound on any GPU: report us/call honestly, plus the batched form (1 000 arrays, 1 launch).
+    small = np.arange(1000, dtype=np.int64)
+    S = mnr.DeviceBuffer.upload(ctx, small)
+    assert devops.reduce_sum(ctx, S)[0] == 499500
+    t0 = time.perf_counter()
+    for _ in range(1000):
+        devops.reduce_sum(ctx, S)
+    dev_us = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    for _ in range(1000):
+        mnr.kernels.reduce.stats(small, None, False, ctx)
+    host_us = (time.perf_counter() - t0) * 1e3
+    many = [S] * 1000
+    devops.reduce_stats_batch(ctx, many, None, False)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        res = devops.reduce_stats_batch(ctx, many, None, False)
+    batch_us = (time.perf_counter() - t0) / 20 * 1e6
+    assert all(r["sum"] == 499500 for r in res)
+    out["c1_i64_1000_sum"] = {"device_resident_us_per_call": round(dev_us, 2), "host_slice_us_per_call": round(host_us, 2),
+                              "batched_1000_arrays_us_per_array": round(batch_us / 1000, 3),
+                              "published_cpu_ns": {"Vec64<i64>": 55, "IntegerArray direct": 88, "Array enum": 170},
+                              "note": "roofline N/A (8 KB): one kernel launch + one stream sync per call; result 499500 checked"}
+
+    if not supertable:
+        return out
+    # configs[4]: SuperTable of 64 batches x 16 Mi rows x {i32, i64, f32, f64}: per-column sum/min/max(+count) over all
+    # chunks in ONE batched call (4 launches), then table * table and per-column scalar broadcast, chunk by chunk.
+    nb, rows_b = 64, 1 << 24
+    cols = [(np.int32, torch.int32), (np.int64, torch.int64), (np.float32, torch.float32), (np.float64, torch.float64)]
+    tabs = []
+    for which in range(2):
+        t = []
+        for npdt, tdt in cols:
+            if tdt.is_floating_point:
+                d = torch.randn(nb * rows_b, dtype=tdt, device=dev, generator=g)
+            else:
+                d = torch.randint(-1000, 1000, (nb * rows_b,), dtype=tdt, device=dev, generator=g)
+            v = torch.randint(0, 256, (nb * rows_b // 8,), dtype=torch.uint8, device=dev, generator=g) | \
+                torch.randint(0, 256, (nb * rows_b // 8,), dtype=torch.uint8, device=dev, generator=g)
+            t.append((npdt, d, v))
+        tabs.append(t)
+    outs = [(torch.empty_like(d), torch.empty_like(v)) for _, d, v in tabs[0]]
+
+    def chunks(t):
+        bufs, vals = [], []
+        for npdt, d, v in t:
+            es = d.element_size()
+            for k in range(nb):
+                bufs.append(mnr.DeviceBuffer.wrap(ctx, npdt, d.data_ptr() + k * rows_b * es, rows_b, d))
+                vals.append(mnr.DeviceBitmask.wrap(ctx, v.data_ptr() + k * rows_b // 8, rows_b, v))
+        return bufs, vals
+    lb, lv = chunks(tabs[0])
+    rb, rv = chunks(tabs[1])
+    ob = chunks([(npdt, o, om) for (npdt, _, _), (o, om) in zip(tabs[0], outs)])
+    row_bytes = sum(d.element_size() for _, d, _ in tabs[0])          # 24 B/row
+    nrows = nb * rows_b
+    agg_dev = torch.zeros(len(lb), 4, dtype=torch.int64, device=dev)
+    entry("supertable_64x16Mi_4col_sum_min_max_batched", nrows * (row_bytes + 4 / 8),
+          lambda: devops.reduce_stats_batch_async(ctx, lb, lv, True, agg_dev.data_ptr()), iters=10)
+    entry("supertable_64x16Mi_4col_sum_count_batched", nrows * (row_bytes + 4 / 8),
+          lambda: devops.reduce_stats_batch_async(ctx, lb, lv, False, agg_dev.data_ptr()), iters=10)
+
+    def one_by_one():
+        for k in range(len(lb)):
+            devops.reduce_stats_async(ctx, lb[k], lv[k], True, agg_dev[k].data_ptr())
+    entry("supertable_64x16Mi_4col_sum_min_max_per_chunk_launches", nrows * (row_bytes + 4 / 8), one_by_one, iters=5)
+    # spot check one column's total against torch
+    torch.cuda.synchronize()
+    a_host = agg_dev.cpu().numpy()
+    d0, v0 = tabs[0][0][1], tabs[0][0][2]
+    vb0 = ((v0[: rows_b // 8].to(torch.int32).view(-1, 1) >> torch.arange(8, device=dev, dtype=torch.int32)) & 1).bool().view(-1)
+    assert int(a_host[0, 0]) == int((d0[:rows_b].to(torch.int64) * vb0).sum()) and int(a_host[0, 3]) == int(vb0.sum())
+
+    def table_mul():
+        for k in range(len(lb)):
+            devops.ew_binary_into(ctx, A.Multiply, lb[k], rb[k], lv[k], rv[k], mnr.MaskMode.Or, ob[0][k], ob[1][k])
+    entry("supertable_64x16Mi_4col_table_mul_table", nrows * (3 * row_bytes + 4 * 3 / 8), table_mul, iters=5)
+    scal = [3, 3, 2.5, 2.5]
+
+    def table_scalar():
+        for k in range(len(lb)):
+            devops.ew_scalar_into(ctx, A.Add if k < 2 * nb else A.Multiply, lb[k], scal[k // nb], False, lv[k], ob[0][k], ob[1][k])
+    entry("supertable_64x16Mi_4col_scalar_broadcast", nrows * (2 * row_bytes + 4 * 2 / 8), table_scalar, iters=5)
+    del lb, lv, rb, rv, ob, tabs, outs
     torch.cuda.empty_cache()
     return out
 
@@ -494,7 +583,7 @@ def run_b200(args):
 
     sec = None
     if rank == 0 and world == 1 and not args.no_secondary:
-        sec = secondary(torch, mnr, ctx, dev, peak, buf, rows)
+        sec = secondary(torch, mnr, ctx, dev, peak, buf, rows, not args.no_supertable)
 
     if rank == 0:
         line = {

@@ -11,7 +11,7 @@ echo "== bench reference arm"; timeout 600 python bench.py --impl reference --st
 echo "== bench"; timeout 900 python bench.py 2>&1 | tail -5 | tee $OUT/bench.json
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"reduce_stats|ew_binary|ew_fma|bits_|clear_trailing" -c 400 \
-    --csv --log-file $OUT/launches.csv python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_launches.log 2>&1
+    --csv --log-file $OUT/launches.csv python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --no-supertable > $OUT/ncu_launches.log 2>&1
 tail -2 $OUT/ncu_launches.log
 echo "== ncu full: reduce"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:reduce_stats -s 3 -c 2 -f -o $OUT/prof_reduce \
@@ -19,6 +19,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:redu
 tail -2 $OUT/ncu_reduce.log
 echo "== ncu full: ew f64 masked add"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ew_binary -s 3 -c 2 -f -o $OUT/prof_ew \
-    python bench.py --steps 3 --warmup 3 --rows 67108864 --no-e2e --no-cpu > $OUT/ncu_ew.log 2>&1
+    python bench.py --steps 3 --warmup 3 --rows 67108864 --no-e2e --no-cpu --no-supertable > $OUT/ncu_ew.log 2>&1
 tail -2 $OUT/ncu_ew.log
 ls -la $OUT
