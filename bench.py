@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=1_000_000_000)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1 finish: fused = one kernel (reduce + P2P mailbox all-gather + combine); nccl = kernel + all-gather")
     ap.add_argument("--cpu-rows", type=int, default=1 << 28, help="rows of the bounded CPU sample")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-supertable", action="store_true", help="skip the 73 GiB configs[4] part of the secondary set")
@@ -459,9 +461,22 @@ def run_b200(args):
     partial = torch.zeros(4, dtype=torch.int64, device=dev)           # mnr_agg image: sum, min, max, count
     gathered = torch.zeros(world, 4, dtype=torch.int64, device=dev)
 
+    fused = world > 1 and args.exchange == "fused"
+    fx = None
+    if fused:
+        from minarrow_b200.sharded import FusedExchange
+        fx = FusedExchange(ctx)
+    total = torch.zeros(4, dtype=torch.int64, device=dev)             # fused path: the combined aggregate on every rank
+
+    def reduce_step():
+        if fused:
+            fx.reduce_stats_async(buf, val, False, total.data_ptr())
+        else:
+            devops.reduce_stats_async(ctx, buf, val, False, partial.data_ptr())
+
     def step():
-        devops.reduce_stats_async(ctx, buf, val, False, partial.data_ptr())
-        if world > 1:
+        reduce_step()
+        if world > 1 and not fused:
             dist.all_gather_into_tensor(gathered.view(-1), partial)
 
     def barrier():
@@ -484,9 +499,9 @@ def run_b200(args):
     t0.record()
     for k in range(K):
         kev[k][0].record()
-        devops.reduce_stats_async(ctx, buf, val, False, partial.data_ptr())
+        reduce_step()
         kev[k][1].record()
-        if world > 1:
+        if world > 1 and not fused:
             dist.all_gather_into_tensor(gathered.view(-1), partial)
     t1.record()
     barrier()
@@ -500,7 +515,7 @@ def run_b200(args):
     ms_total, kernel_ms_max = float(tmax[0]), float(tmax[1])
 
     # result of the last step: per-GPU partials combined in rank order (integer sums wrap; order-free)
-    parts = (gathered if world > 1 else partial.view(1, 4)).cpu().numpy()
+    parts = (total.view(1, 4) if fused else gathered if world > 1 else partial.view(1, 4)).cpu().numpy()
     tot_sum = int(np.sum(parts[:, 0].astype(np.uint64), dtype=np.uint64).astype(np.int64))
     tot_cnt = int(parts[:, 3].sum())
     exp = torch.tensor([exp_sum, exp_cnt], dtype=torch.int64, device=dev)
@@ -592,6 +607,8 @@ def run_b200(args):
             "scaling": args.scaling, "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": "configs[1]: 1B-row IntegerArray<i64> null-aware sum/avg, 10% nulls, "
                                    "SuperArray shards over GPUs + NCCL all-gather of 32-byte partials",
+                       "exchange": ("fused kernel: reduce + P2P mailbox all-gather over NVLink + rank-order combine" if fused
+                                    else "NCCL all-gather of 32-byte partials" if world > 1 else "none (1 GPU)"),
                        "rows_per_gpu": rows, "total_rows": total_rows, "bytes_per_row": BYTES_PER_ROW,
                        "l2": "inputs (8.1 GB per GPU) far larger than the 126 MB L2; no flush needed",
                        "values": "i64 uniform in [-2^31, 2^31), seeded per rank", "p_valid": P_VALID},

@@ -37,6 +37,7 @@ extern "C" {
 typedef struct mnr_ctx mnr_ctx;   /* device + stream + scratch                                          */
 typedef struct mnr_buf mnr_buf;   /* device-resident values buffer: the Vec64<T>/Buffer<T> analogue      */
 typedef struct mnr_bits mnr_bits; /* device-resident bit-packed mask: the Bitmask analogue               */
+typedef struct mnr_xchg mnr_xchg; /* cross-GPU mailbox set for the fused reduction + exchange kernel      */
 
 /* Element types of IntegerArray<T> / FloatArray<T> (src/structs/variants/{integer,float}.rs);
  * 8/16-bit integers are the reference's `extended_numeric_types` feature (dispatch.rs:380-387). */
@@ -224,6 +225,22 @@ int mnr_reduce_stats_batch(mnr_ctx* ctx, size_t n, const mnr_buf* const* bufs, c
                            int with_minmax, mnr_agg* out_host);                                      /* syncs */
 int mnr_reduce_stats_batch_async(mnr_ctx* ctx, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
                                  int with_minmax, void* out_device);
+/* ---- fused reduction + cross-GPU exchange (SuperArray shards over the GPUs of one box) -----------------------
+ * One process per GPU.  Each rank creates a mailbox, publishes its 64-byte CUDA IPC handle (any transport: the
+ * harness all-gathers them with torch.distributed), and connects to its peers' mailboxes once.  After that
+ * mnr_reduce_stats_exchange is ONE kernel per call: the shard's null-aware aggregate, P2P stores of the 32-byte
+ * partial into every peer's mailbox through NVLink/NVSwitch, a flag wait, and the rank-order combine — every rank
+ * ends with the same global aggregate (bit-identical, floats included) in `out_device`.  Collective: every rank of
+ * the group must make the same sequence of calls.  world <= 16. */
+#define MNR_IPC_HANDLE_BYTES 64
+int mnr_xchg_create(mnr_ctx* ctx, int world, int rank, mnr_xchg** out);
+int mnr_xchg_local_handle(mnr_xchg* x, uint8_t* handle64);
+int mnr_xchg_connect(mnr_xchg* x, const uint8_t* handles /* world x MNR_IPC_HANDLE_BYTES, rank order */);
+void mnr_xchg_destroy(mnr_xchg* x);
+int mnr_reduce_stats_exchange(mnr_ctx* ctx, mnr_xchg* x, const mnr_buf* buf, const mnr_bits* validity, int with_minmax,
+                              void* out_device);
+int mnr_reduce_stats_exchange_sync(mnr_ctx* ctx, mnr_xchg* x, const mnr_buf* buf, const mnr_bits* validity,
+                                   int with_minmax, mnr_agg* out_host);
 /* mean = (double)sum / (double)count on the host from a (combined) aggregate; NaN when count == 0. */
 double mnr_agg_mean(mnr_dtype dtype, const mnr_agg* agg);
 /* Combine per-chunk / per-GPU partials in index order (the documented rank-order float add). */

@@ -83,6 +83,12 @@ SIGNATURES = {
     "mnr_reduce_stats_async": (c_int, [c_ctx, c_buf, c_bits, c_int, c_vp]),
     "mnr_reduce_stats_batch": (c_int, [c_ctx, c_sz, PP, PP, c_int, C.POINTER(Agg)]),
     "mnr_reduce_stats_batch_async": (c_int, [c_ctx, c_sz, PP, PP, c_int, c_vp]),
+    "mnr_xchg_create": (c_int, [c_ctx, c_int, c_int, PP]),
+    "mnr_xchg_local_handle": (c_int, [c_vp, c_vp]),
+    "mnr_xchg_connect": (c_int, [c_vp, c_vp]),
+    "mnr_xchg_destroy": (None, [c_vp]),
+    "mnr_reduce_stats_exchange": (c_int, [c_ctx, c_vp, c_buf, c_bits, c_int, c_vp]),
+    "mnr_reduce_stats_exchange_sync": (c_int, [c_ctx, c_vp, c_buf, c_bits, c_int, C.POINTER(Agg)]),
     "mnr_agg_mean": (C.c_double, [c_int, C.POINTER(Agg)]),
     "mnr_agg_combine": (c_int, [c_int, C.POINTER(Agg), c_sz, C.POINTER(Agg)]),
     "mnr_apply_host": (c_int, [c_ctx, c_int, c_int, c_vp, c_sz, c_vp, c_sz, c_vp, c_vp, c_vp]),

@@ -759,6 +759,103 @@ int mnr_reduce_stats_batch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, con
     return MNR_OK;
 }
 
+// ---- fused reduction + cross-GPU exchange (one process per GPU; peers' mailboxes mapped through CUDA IPC) ----------------
+struct mnr_xchg {
+    mnr_ctx* ctx = nullptr;
+    int world = 0, rank = 0;
+    unsigned long long epoch = 0;
+    char* mailbox = nullptr;                 // own mailbox (cudaMalloc: IPC-exportable)
+    char* peers[kMaxPeers] = {};             // every rank's mailbox as mapped here (peers[rank] == mailbox)
+    bool opened[kMaxPeers] = {};
+    unsigned int* err = nullptr;             // device word: a peer's flag never arrived
+    bool connected = false;
+};
+static constexpr size_t kMailboxBytes = 2 * kMaxPeers * 64;
+
+int mnr_xchg_create(mnr_ctx* c, int world, int rank, mnr_xchg** out) {
+    REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, MNR_ERR_INVALID_ARGUMENTS,
+            "world %d / rank %d out of range (max %d peers)", world, rank, kMaxPeers);
+    CU(cudaSetDevice(c->device));
+    mnr_xchg* x = new mnr_xchg();
+    x->ctx = c; x->world = world; x->rank = rank;
+    CU(cudaMalloc(&x->mailbox, kMailboxBytes));
+    CU(cudaMemset(x->mailbox, 0, kMailboxBytes));
+    CU(cudaMalloc(&x->err, 64));
+    CU(cudaMemset(x->err, 0, 64));
+    CU(cudaDeviceSynchronize());
+    x->peers[rank] = x->mailbox;
+    x->connected = world == 1;
+    *out = x;
+    return MNR_OK;
+}
+
+int mnr_xchg_local_handle(mnr_xchg* x, uint8_t* handle64) {
+    REQUIRE(x && handle64, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MNR_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(x->ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, x->mailbox));
+    memcpy(handle64, &h, sizeof h);
+    return MNR_OK;
+}
+
+int mnr_xchg_connect(mnr_xchg* x, const uint8_t* handles) {
+    REQUIRE(x && handles, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    CU(cudaSetDevice(x->ctx->device));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank || x->opened[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * MNR_IPC_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peers[r] = static_cast<char*>(p);
+        x->opened[r] = true;
+    }
+    x->connected = true;
+    return MNR_OK;
+}
+
+void mnr_xchg_destroy(mnr_xchg* x) {
+    if (!x) return;
+    cudaSetDevice(x->ctx->device);
+    cudaStreamSynchronize(x->ctx->stream);
+    for (int r = 0; r < x->world; ++r) if (x->opened[r]) cudaIpcCloseMemHandle(x->peers[r]);
+    cudaFree(x->mailbox);
+    cudaFree(x->err);
+    delete x;
+}
+
+int mnr_reduce_stats_exchange(mnr_ctx* c, mnr_xchg* x, const mnr_buf* b, const mnr_bits* v, int with_minmax, void* out_device) {
+    int rc = check_reduce(c, b, v);
+    if (rc) return rc;
+    REQUIRE(x && x->ctx == c, MNR_ERR_INVALID_ARGUMENTS, "exchange handle belongs to another context");
+    REQUIRE(x->connected, MNR_ERR_INVALID_ARGUMENTS, "mnr_xchg_connect has not been called");
+    REQUIRE(out_device && (reinterpret_cast<uintptr_t>(out_device) & 15u) == 0, MNR_ERR_INVALID_ARGUMENTS,
+            "out_device must be a 16-byte aligned device pointer");
+    CU(cudaSetDevice(c->device));
+    XchgDev d{};
+    d.world = x->world; d.rank = x->rank; d.epoch = ++x->epoch; d.err = x->err;
+    for (int r = 0; r < x->world; ++r) d.mailbox[r] = x->peers[r];
+    CU(launch_reduce_stats_xchg(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, with_minmax != 0, c->partials[3], c->ticket[3],
+                                static_cast<AggRaw*>(out_device), nullptr, d, c->stream));
+    c->launches++;
+    return MNR_OK;
+}
+
+int mnr_reduce_stats_exchange_sync(mnr_ctx* c, mnr_xchg* x, const mnr_buf* b, const mnr_bits* v, int with_minmax, mnr_agg* out_host) {
+    REQUIRE(out_host, MNR_ERR_INVALID_ARGUMENTS, "out is NULL");
+    int rc = mnr_reduce_stats_exchange(c, x, b, v, with_minmax, c->d_agg);
+    if (rc) return rc;
+    unsigned int* herr = reinterpret_cast<unsigned int*>(static_cast<char*>(c->h_scratch) + 128);
+    CU(cudaMemcpyAsync(c->h_scratch, c->d_agg, sizeof(AggRaw), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(herr, x->err, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (*herr) return fail(MNR_ERR_CUDA, "fused exchange timed out waiting for a peer's partial (epoch %llu)", x->epoch);
+    memcpy(out_host, c->h_scratch, sizeof(mnr_agg));
+    return MNR_OK;
+}
+
 static int dtype_kind(mnr_dtype dt) {   // 0 signed, 1 unsigned, 2 float
     switch (dt) {
         case MNR_F32: case MNR_F64: return 2;

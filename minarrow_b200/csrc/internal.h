@@ -14,6 +14,11 @@ int reduce_max_grid();
 // out_host: optional mapped pinned host address that receives a second copy of the aggregate (NULL = none).
 cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
                                 AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s);
+// Fused reduction + cross-GPU exchange over peer memory (reduce_kernels.cuh "fused cross-GPU finish").
+struct XchgDev;
+cudaError_t launch_reduce_stats_xchg(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
+                                     AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host,
+                                     const XchgDev& x, cudaStream_t s);
 // Batched form: one launch for `nseg` columns/chunks of one (dtype, alignment tier, masked) class.
 struct ReduceSeg;
 int reduce_tier(const void* data, bool minmax);

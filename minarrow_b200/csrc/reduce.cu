@@ -13,14 +13,7 @@ constexpr int kRBlock = 256;
 template <typename T> struct RMinB { static constexpr int value = sizeof(T) >= 4 ? 4 : 2; };   // narrow types carry 8-32 slots
 template <typename VecT, bool MINMAX> struct RU { static constexpr int value = (sizeof(VecT) == 32) ? 2 : 4; };
 
-int reduce_max_grid() { return kSMs * 4; }
-
-// tier: 0 = element loads, 1 = 128-bit, 2 = 256-bit (only used with min/max)
-int reduce_tier(const void* data, bool minmax) {
-    const uintptr_t p = reinterpret_cast<uintptr_t>(data);
-    if (minmax && (p & 31u) == 0) return 2;
-    return (p & 15u) == 0 ? 1 : 0;
-}
+int reduce_tier(const void* data, bool minmax);
 
 template <typename T, typename VecT, bool MINMAX> static uint32_t nblk_of(uint64_t n) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
@@ -35,9 +28,9 @@ template <typename T, typename VecT, bool MINMAX> static uint32_t nblk_of(uint64
 
 template <typename T, typename VecT, bool MASKED, bool MINMAX>
 static cudaError_t launch_one(const void* data, const uint8_t* mask, uint64_t n, AggRaw* partials, unsigned int* ticket,
-                              AggRaw* out, AggRaw* out_host, cudaStream_t s) {
+                              AggRaw* out, AggRaw* out_host, const XchgDev& x, cudaStream_t s) {
     reduce_stats_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>
-        <<<nblk_of<T, VecT, MINMAX>(n), kRBlock, 0, s>>>(static_cast<const T*>(data), mask, n, partials, ticket, out, out_host);
+        <<<nblk_of<T, VecT, MINMAX>(n), kRBlock, 0, s>>>(static_cast<const T*>(data), mask, n, partials, ticket, out, out_host, x);
     return cudaGetLastError();
 }
 
@@ -64,10 +57,10 @@ static cudaError_t launch_batch_one(const ReduceSeg* segs, uint32_t nseg, uint32
 
 template <typename T>
 static cudaError_t launch_t(const void* data, const uint8_t* mask, uint64_t n, bool minmax, AggRaw* partials,
-                            unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s) {
+                            unsigned int* ticket, AggRaw* out, AggRaw* out_host, const XchgDev& x, cudaStream_t s) {
     const int tier = reduce_tier(data, minmax);
     const bool masked = mask != nullptr;
-#define CALL1(V, M, X) return launch_one<T, V, M, X>(data, mask, n, partials, ticket, out, out_host, s)
+#define CALL1(V, M, X) return launch_one<T, V, M, X>(data, mask, n, partials, ticket, out, out_host, x, s)
     MNR_REDUCE_DISPATCH(CALL1);
 #undef CALL1
 }
@@ -90,36 +83,99 @@ static cudaError_t batch_t(int tier, bool masked, bool minmax, const ReduceSeg* 
 #undef CALLB
 }
 
-#define MNR_DTYPE_SWITCH(dt, EXPR)                      \
-    switch (dt) {                                       \
-        case MNR_I8: { using T = int8_t; EXPR; }        \
-        case MNR_U8: { using T = uint8_t; EXPR; }       \
-        case MNR_I16: { using T = int16_t; EXPR; }      \
-        case MNR_U16: { using T = uint16_t; EXPR; }     \
-        case MNR_I32: { using T = int32_t; EXPR; }      \
-        case MNR_U32: { using T = uint32_t; EXPR; }     \
-        case MNR_I64: { using T = int64_t; EXPR; }      \
-        case MNR_U64: { using T = uint64_t; EXPR; }     \
-        case MNR_F32: { using T = float; EXPR; }        \
-        case MNR_F64: { using T = double; EXPR; }       \
+// This file is compiled once per element type (-DMNR_RED_DTYPE=<mnr_dtype code>) plus a front (-DMNR_RED_DTYPE=100)
+// that switches on the runtime dtype; see the Makefile.
+#define MNR_RED_DECL(NAME)                                                                                                   \
+    cudaError_t reduce_single_##NAME(const void*, const uint8_t*, uint64_t, bool, AggRaw*, unsigned int*, AggRaw*, AggRaw*, \
+                                     const XchgDev&, cudaStream_t);                                                          \
+    uint32_t reduce_nblk_##NAME(uint64_t, int, bool);                                                                        \
+    cudaError_t reduce_batch_##NAME(int, bool, bool, const ReduceSeg*, uint32_t, uint32_t, AggRaw*, unsigned int*, AggRaw*,  \
+                                    cudaStream_t);
+#define MNR_RED_DEF(NAME, T)                                                                                                  \
+    cudaError_t reduce_single_##NAME(const void* data, const uint8_t* mask, uint64_t n, bool minmax, AggRaw* partials,       \
+                                     unsigned int* ticket, AggRaw* out, AggRaw* out_host, const XchgDev& x, cudaStream_t s) { \
+        return launch_t<T>(data, mask, n, minmax, partials, ticket, out, out_host, x, s);                                    \
+    }                                                                                                                         \
+    uint32_t reduce_nblk_##NAME(uint64_t n, int tier, bool minmax) { return nblk_t<T>(n, tier, minmax); }                    \
+    cudaError_t reduce_batch_##NAME(int tier, bool masked, bool minmax, const ReduceSeg* segs, uint32_t nseg,                \
+                                    uint32_t max_blk, AggRaw* partials, unsigned int* tickets, AggRaw* outs, cudaStream_t s) { \
+        return batch_t<T>(tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, s);                            \
     }
+
+#if MNR_RED_DTYPE == 0
+MNR_RED_DEF(i32, int32_t)
+#elif MNR_RED_DTYPE == 1
+MNR_RED_DEF(u32, uint32_t)
+#elif MNR_RED_DTYPE == 2
+MNR_RED_DEF(i64, int64_t)
+#elif MNR_RED_DTYPE == 3
+MNR_RED_DEF(u64, uint64_t)
+#elif MNR_RED_DTYPE == 4
+MNR_RED_DEF(f32, float)
+#elif MNR_RED_DTYPE == 5
+MNR_RED_DEF(f64, double)
+#elif MNR_RED_DTYPE == 6
+MNR_RED_DEF(i8, int8_t)
+#elif MNR_RED_DTYPE == 7
+MNR_RED_DEF(u8, uint8_t)
+#elif MNR_RED_DTYPE == 8
+MNR_RED_DEF(i16, int16_t)
+#elif MNR_RED_DTYPE == 9
+MNR_RED_DEF(u16, uint16_t)
+#elif MNR_RED_DTYPE == 100
+MNR_RED_DECL(i8) MNR_RED_DECL(u8) MNR_RED_DECL(i16) MNR_RED_DECL(u16) MNR_RED_DECL(i32)
+MNR_RED_DECL(u32) MNR_RED_DECL(i64) MNR_RED_DECL(u64) MNR_RED_DECL(f32) MNR_RED_DECL(f64)
+
+#define MNR_DTYPE_SWITCH(dt, FN, ...)                      \
+    switch (dt) {                                          \
+        case MNR_I8: return FN##_i8(__VA_ARGS__);          \
+        case MNR_U8: return FN##_u8(__VA_ARGS__);          \
+        case MNR_I16: return FN##_i16(__VA_ARGS__);        \
+        case MNR_U16: return FN##_u16(__VA_ARGS__);        \
+        case MNR_I32: return FN##_i32(__VA_ARGS__);        \
+        case MNR_U32: return FN##_u32(__VA_ARGS__);        \
+        case MNR_I64: return FN##_i64(__VA_ARGS__);        \
+        case MNR_U64: return FN##_u64(__VA_ARGS__);        \
+        case MNR_F32: return FN##_f32(__VA_ARGS__);        \
+        case MNR_F64: return FN##_f64(__VA_ARGS__);        \
+    }
+
+int reduce_max_grid() { return kSMs * 4; }
+
+// tier: 0 = element loads, 1 = 128-bit, 2 = 256-bit (only used with min/max)
+int reduce_tier(const void* data, bool minmax) {
+    const uintptr_t p = reinterpret_cast<uintptr_t>(data);
+    if (minmax && (p & 31u) == 0) return 2;
+    return (p & 15u) == 0 ? 1 : 0;
+}
 
 cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
                                 AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s) {
-    MNR_DTYPE_SWITCH(dt, return launch_t<T>(data, mask, n, minmax, partials, ticket, out, out_host, s));
+    const XchgDev none{};
+    MNR_DTYPE_SWITCH(dt, reduce_single, data, mask, n, minmax, partials, ticket, out, out_host, none, s);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_reduce_stats_xchg(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
+                                     AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host,
+                                     const XchgDev& x, cudaStream_t s) {
+    MNR_DTYPE_SWITCH(dt, reduce_single, data, mask, n, minmax, partials, ticket, out, out_host, x, s);
     return cudaErrorInvalidValue;
 }
 
 uint32_t reduce_nblk(mnr_dtype dt, uint64_t n, int tier, bool minmax) {
-    MNR_DTYPE_SWITCH(dt, return nblk_t<T>(n, tier, minmax));
+    MNR_DTYPE_SWITCH(dt, reduce_nblk, n, tier, minmax);
     return 1;
 }
 
 cudaError_t launch_reduce_stats_batch(mnr_dtype dt, int tier, bool masked, bool minmax, const ReduceSeg* segs,
                                       uint32_t nseg, uint32_t max_blk, AggRaw* partials, unsigned int* tickets,
                                       AggRaw* outs, cudaStream_t s) {
-    MNR_DTYPE_SWITCH(dt, return batch_t<T>(tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, s));
+    MNR_DTYPE_SWITCH(dt, reduce_batch, tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, s);
     return cudaErrorInvalidValue;
 }
+#else
+#error "compile reduce.cu with -DMNR_RED_DTYPE=<0..9 | 100>"
+#endif
 
 }  // namespace mnr

@@ -52,29 +52,18 @@ template <> struct MinMax<double> {
     __device__ static double max_identity() { return __longlong_as_double(0x7ff8000000000000ll); }
 };
 
-// min/max combine.  Integers: plain.  Floats: NaN never wins (NaN doubles as "empty"), -0.0 < +0.0 so
-// the result does not depend on the order in which equal zeros are met.
+// min/max combine.  Integers: plain.  Floats: NaN never wins (NaN doubles as "empty") and -0.0 < +0.0, so the result
+// does not depend on the order in which equal zeros are met.  That is exactly the hardware's IEEE-754 minNum/maxNum
+// (FMNMX / DMNMX: the non-NaN operand wins, -0.0 orders below +0.0), one instruction instead of four compares.
 template <typename T> __device__ __forceinline__ T comb_min(T a, T b) {
-    if constexpr (Traits<T>::is_float) {
-        if (b != b) return a;
-        if (a != a) return b;
-        if (b < a) return b;
-        if (b == a && signbit(b)) return b;
-        return a;
-    } else {
-        return b < a ? b : a;
-    }
+    if constexpr (std::is_same<T, float>::value) return fminf(a, b);
+    else if constexpr (std::is_same<T, double>::value) return fmin(a, b);
+    else return b < a ? b : a;
 }
 template <typename T> __device__ __forceinline__ T comb_max(T a, T b) {
-    if constexpr (Traits<T>::is_float) {
-        if (b != b) return a;
-        if (a != a) return b;
-        if (b > a) return b;
-        if (b == a && !signbit(b)) return b;
-        return a;
-    } else {
-        return b > a ? b : a;
-    }
+    if constexpr (std::is_same<T, float>::value) return fmaxf(a, b);
+    else if constexpr (std::is_same<T, double>::value) return fmax(a, b);
+    else return b > a ? b : a;
 }
 
 template <typename A> __device__ __forceinline__ uint64_t acc_bits(A v) {
@@ -160,7 +149,13 @@ __device__ __forceinline__ void accum_vec(const VecT& v, uint32_t bits, typename
         if constexpr (Traits<T>::is_float) slot[k] = slot[k] + (ok ? (A)x : (A)0);
         else slot[k] = (A)((uint64_t)slot[k] + (ok ? (uint64_t)(A)x : 0ull));
         if constexpr (MINMAX) {
-            if (ok) { p.mn = comb_min(p.mn, x); p.mx = comb_max(p.mx, x); }
+            if constexpr (Traits<T>::is_float) {   // invalid row -> NaN, which minNum/maxNum skip: no branch, no predicate
+                const T xm = ok ? x : MinMax<T>::min_identity();
+                p.mn = comb_min(p.mn, xm); p.mx = comb_max(p.mx, xm);
+            } else {
+                p.mn = comb_min(p.mn, ok ? x : MinMax<T>::min_identity());
+                p.mx = comb_max(p.mx, ok ? x : MinMax<T>::max_identity());
+            }
         }
     }
     if constexpr (MASKED) p.cnt += (uint64_t)__popc(bits);
@@ -174,6 +169,42 @@ __device__ __forceinline__ AggRaw load_partial(const AggRaw* p) {   // L2-cohere
     return r;
 }
 
+// ---- fused cross-GPU finish over NVLink peer memory ------------------------------------------------------------
+// Every rank owns a 2 KB mailbox (cudaMalloc + CUDA IPC, mapped into every peer process).  Slot (parity p, source rank
+// s) = 64 bytes at ((p * kMaxPeers) + s) * 64: bytes 0..31 the source's AggRaw, bytes 32..39 a flag holding the epoch.
+// The finishing block of rank r's reduction kernel stores its aggregate + flag into slot (epoch & 1, r) of EVERY
+// rank's mailbox (P2P stores through NVSwitch), then waits until the `world` slots of its own mailbox carry this
+// epoch and folds them in rank order — the same fold on every rank, so all ranks hold identical bits.  One kernel:
+// the reduction, the all-gather of partials and the combine; no NCCL call, no host round trip.
+// Parity double-buffering is race-free: a rank can only complete epoch e+1 after every peer has finished epoch e
+// (it needs their e+1 flags, which stream order places after their epoch-e kernel).
+constexpr int kMaxPeers = 16;
+struct XchgDev {
+    int world;                 // 0 = no exchange (plain single-GPU finish)
+    int rank;
+    unsigned long long epoch;  // 1, 2, 3, ... identical sequence on every rank
+    unsigned int* err;         // device word, set to 1 if a peer's flag never arrives (bounded spin)
+    char* mailbox[kMaxPeers];  // mailbox[r]: rank r's mailbox as mapped in this process
+};
+
+__device__ __forceinline__ void st_sys_v2(void* p, uint64_t a, uint64_t b) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(void* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const void* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ AggRaw ld_sys_agg(const void* p) {
+    AggRaw r;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.sum), "=l"(r.mn) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.mx), "=l"(r.count) : "l"(static_cast<const char*>(p) + 16) : "memory");
+    return r;
+}
+
 // Body shared by the single-column kernel and the batched (one launch, many chunks) kernel.  `bid` / `nblk` are the
 // block's index and the number of blocks working on THIS column; nblk is a function of (len, dtype) only, so a column
 // reduced inside a batch gives the same bits as the same column reduced alone.
@@ -181,7 +212,7 @@ template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int U>
 __device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
                                                   AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket,
                                                   AggRaw* __restrict__ out, AggRaw* __restrict__ out_host,
-                                                  const unsigned int bid, const unsigned int nblk) {
+                                                  const unsigned int bid, const unsigned int nblk, const XchgDev& x) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     using A = typename Traits<T>::Acc;
     using P = Partial<T, MINMAX>;
@@ -259,8 +290,40 @@ __device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, co
         if (first) { q = t; first = false; } else q.merge(t);
     }
     q = block_combine<P, BLOCK>(q, smem);
-    if (threadIdx.x == 0) {
+    if (x.world > 0) {   // fused cross-GPU finish (block-uniform branch; only the finishing block gets here)
+        __shared__ AggRaw mine;
+        __shared__ AggRaw got[kMaxPeers];
+        if (threadIdx.x == 0) {
+            if constexpr (!MASKED) q.cnt = n;
+            mine = q.raw();
+        }
+        __syncthreads();
+        const size_t par = (size_t)(x.epoch & 1ull) * kMaxPeers;
+        if (threadIdx.x < (unsigned)x.world) {
+            char* dst = x.mailbox[threadIdx.x] + (par + (size_t)x.rank) * 64;
+            st_sys_v2(dst, mine.sum, mine.mn);
+            st_sys_v2(dst + 16, mine.mx, mine.count);
+            __threadfence_system();
+            st_release_sys(dst + 32, x.epoch);
+            const char* src = x.mailbox[x.rank] + (par + threadIdx.x) * 64;
+            const long long t0 = clock64();
+            bool ok = true;
+            while (ld_acquire_sys(src + 32) != x.epoch) {
+                if (clock64() - t0 > (20ll << 30)) { ok = false; break; }   // ~10 s: a peer never launched
+            }
+            if (!ok) atomicExch(x.err, 1u);
+            got[threadIdx.x] = ld_sys_agg(src);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            P acc; acc.from_raw(got[0]);
+            for (int r = 1; r < x.world; ++r) { P t; t.from_raw(got[r]); acc.merge(t); }   // rank order
+            q = acc;
+        }
+    } else if (threadIdx.x == 0) {
         if constexpr (!MASKED) q.cnt = n;
+    }
+    if (threadIdx.x == 0) {
         const AggRaw r = q.raw();
         *out = r;
         if (out_host) {   // optional second copy straight into mapped pinned host memory (synchronous APIs: no D2H memcpy)
@@ -275,8 +338,8 @@ template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MI
 __global__ void __launch_bounds__(BLOCK, MINB)
 reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
                     AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket, AggRaw* __restrict__ out,
-                    AggRaw* __restrict__ out_host) {
-    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(data, mask, n, partials, ticket, out, out_host, blockIdx.x, gridDim.x);
+                    AggRaw* __restrict__ out_host, const XchgDev x) {
+    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(data, mask, n, partials, ticket, out, out_host, blockIdx.x, gridDim.x, x);
 }
 
 // One launch, many columns/chunks (SuperArray / SuperTable fan-out, broadcast/super_table.rs:38-73 walks them one
@@ -297,7 +360,7 @@ reduce_stats_batch_kernel(const ReduceSeg* __restrict__ segs, AggRaw* __restrict
     if (blockIdx.x >= s.nblk) return;
     reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(static_cast<const T*>(s.data), s.mask, s.n,
                                                         partials + (size_t)blockIdx.y * max_blk, tickets + blockIdx.y,
-                                                        outs + s.out_index, nullptr, blockIdx.x, s.nblk);
+                                                        outs + s.out_index, nullptr, blockIdx.x, s.nblk, XchgDev{});
 }
 
 }  // namespace mnr

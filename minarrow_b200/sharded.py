@@ -114,14 +114,14 @@ class ShardedColumn:
         return cls(ctx, dtype, bufs, vals)
 
     def local_partial(self, with_minmax: bool = True):
-        """One `mnr_agg` for this rank: per-chunk partials (one kernel launch each, asynchronous, written straight to
-        a device array) folded in chunk order.  Returns a torch int64[4] tensor on this rank's GPU."""
+        """One `mnr_agg` for this rank: per-chunk partials (batched launch, asynchronous, written straight to a device
+        array) folded in chunk order.  Returns a torch int64[4] tensor on this rank's GPU."""
         import torch
         from . import device_ops as dev
         n = max(1, len(self.chunks))
         parts = torch.zeros(n, 4, dtype=torch.int64, device=torch.device("cuda", self.ctx.device))
-        for k, (b, v) in enumerate(zip(self.chunks, self.validities)):
-            dev.reduce_stats_async(self.ctx, b, v, with_minmax, parts[k].data_ptr())
+        if self.chunks:   # all local chunks in one batched call (one launch per dtype/alignment/masked class)
+            dev.reduce_stats_batch_async(self.ctx, self.chunks, self.validities, with_minmax, parts.data_ptr())
         self.ctx.synchronize()
         if not self.chunks:
             return None
@@ -150,3 +150,56 @@ class ShardedColumn:
         if not keep:
             raise KernelError("InvalidArguments", "empty SuperArray")
         return combine_partials(self.dtype, keep)
+
+
+class FusedExchange:
+    """Mailboxes for the fused reduction + cross-GPU exchange kernel (`mnr_reduce_stats_exchange`): ONE kernel per
+    reduction does the shard's aggregate, the P2P all-gather of the 32-byte partials over NVLink and the rank-order
+    combine.  torch.distributed only carries the 64-byte CUDA IPC handles once, at construction."""
+
+    def __init__(self, ctx, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx = ctx
+        if dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:
+            self.world, self.rank = 1, 0
+        h = C.c_void_p()
+        check(ctx.lib.mnr_xchg_create(ctx.h, self.world, self.rank, C.byref(h)))
+        self.h = h
+        if self.world > 1:
+            mine = (C.c_uint8 * 64)()
+            check(ctx.lib.mnr_xchg_local_handle(self.h, mine))
+            dev_ = torch.device("cuda", ctx.device)
+            local = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev_)
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev_)
+            dist.all_gather_into_tensor(allh, local, group=group)
+            raw = bytes(allh.cpu().numpy().tobytes())
+            buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+            check(ctx.lib.mnr_xchg_connect(self.h, buf))
+            dist.barrier(group=group)      # every rank has mapped every mailbox before the first kernel uses them
+
+    def reduce_stats_async(self, buf, validity, with_minmax: bool, out_device_ptr: int) -> None:
+        """Global aggregate of the sharded column -> 32 bytes at `out_device_ptr` on this rank (no sync, no NCCL)."""
+        check(self.ctx.lib.mnr_reduce_stats_exchange(self.ctx.h, self.h, buf.h, None if validity is None else validity.h,
+                                                     int(with_minmax), C.c_void_p(out_device_ptr)))
+
+    def reduce_stats(self, buf, validity=None, with_minmax: bool = True) -> dict:
+        agg = _lib.Agg()
+        check(self.ctx.lib.mnr_reduce_stats_exchange_sync(self.ctx.h, self.h, buf.h, None if validity is None else validity.h,
+                                                          int(with_minmax), C.byref(agg)))
+        f = {"i": "i64", "u": "u64", "f": "f64"}[buf.dtype.kind]
+        return {"sum": getattr(agg.sum, f), "min": getattr(agg.min, f), "max": getattr(agg.max, f), "count": int(agg.count),
+                "mean": float(self.ctx.lib.mnr_agg_mean(dtype_code(buf.dtype), C.byref(agg)))}
+
+    def close(self) -> None:
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.mnr_xchg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -57,6 +57,44 @@ def main():
             m = orc.Bits(chunks[i].null_mask.bits, rows)
             ed, em = orc.apply(chunks[i].data, chunks[i].data, orc.MUL, m)
             assert ob.download().tobytes() == ed.tobytes() and np.array_equal(om.download().bits, em.bits), (dt, i)
+    # fused reduction + exchange kernel (P2P mailboxes): every rank reduces its window of one big column and must end
+    # with the oracle's aggregate of the WHOLE column, bit-identical on all ranks, over many back-to-back epochs.
+    fx = sh.FusedExchange(ctx)
+    n = 3_000_017
+    for dt in (np.int64, np.int32, np.float64, np.float32):
+        if np.dtype(dt).kind == "f":
+            whole = (rng.standard_normal(n) * 100).astype(dt)
+        else:
+            whole = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, n, dtype=dt, endpoint=True)
+        valid = rng.random(n) < 0.9
+        off, ln = sh.shard_rows(n, world)[rank]
+        B = mnr.DeviceBuffer.upload(ctx, whole[off:off + ln])
+        V = mnr.DeviceBitmask.upload(ctx, mnr.Bitmask.from_bools(valid[off:off + ln]))
+        exp = orc.stats(whole, orc.Bits.from_bools(valid))
+        for rep in range(25):
+            for mm in (True, False):
+                got = fx.reduce_stats(B, V, mm)
+                assert got["count"] == exp["count"], (dt, rep, got, exp)
+                if mm:
+                    assert got["min"] == exp["min"] and got["max"] == exp["max"], (dt, rep, got, exp)
+                if np.dtype(dt).kind == "f":
+                    assert abs(got["sum"] - exp["sum"]) <= 1e-12 * np.abs(whole[valid].astype(np.float64)).sum()
+                else:
+                    assert got["sum"] == exp["sum"], (dt, rep, got, exp)
+        bits = int(np.float64(got["sum"]).view(np.int64)) if np.dtype(dt).kind == "f" else \
+            (int(got["sum"]) + 2 ** 63) % 2 ** 64 - 2 ** 63
+        t = torch.tensor([bits], dtype=torch.int64, device="cuda")
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        assert all(int(x) == int(t) for x in g), "fused exchange: ranks disagree"
+        # asynchronous form, 200 epochs back to back without host synchronisation
+        outd = torch.zeros(4, dtype=torch.int64, device="cuda")
+        ctx.synchronize()
+        for _ in range(200):
+            fx.reduce_stats_async(B, V, False, outd.data_ptr())
+        ctx.synchronize()
+        assert int(outd[3]) == exp["count"]
+    fx.close()
     dist.barrier()
     if rank == 0:
         print(f"multigpu_check ok: world={world}, {n_chunks} chunks x {rows} rows, 5 dtypes")
