@@ -351,12 +351,14 @@ def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows, supertable=True):
         mnr.kernels.reduce.stats(small, None, False, ctx)
     host_us = (time.perf_counter() - t0) * 1e3
     many = [S] * 1000
-    devops.reduce_stats_batch(ctx, many, None, False)
+    harr = devops._handle_array(many)
+    aggs = (mnr._lib.Agg * 1000)()
+    ctx.lib.mnr_reduce_stats_batch(ctx.h, 1000, harr, None, 0, aggs)
     t0 = time.perf_counter()
     for _ in range(20):
-        res = devops.reduce_stats_batch(ctx, many, None, False)
+        mnr.core.check(ctx.lib.mnr_reduce_stats_batch(ctx.h, 1000, harr, None, 0, aggs))     # one C ABI call, one launch
     batch_us = (time.perf_counter() - t0) / 20 * 1e6
-    assert all(r["sum"] == 499500 for r in res)
+    assert all(a.sum.i64 == 499500 and a.count == 1000 for a in aggs)
     out["c1_i64_1000_sum"] = {"device_resident_us_per_call": round(dev_us, 2), "host_slice_us_per_call": round(host_us, 2),
                               "batched_1000_arrays_us_per_array": round(batch_us / 1000, 3),
                               "published_cpu_ns": {"Vec64<i64>": 55, "IntegerArray direct": 88, "Array enum": 170},
@@ -415,13 +417,23 @@ def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows, supertable=True):
     def table_mul():
         for k in range(len(lb)):
             devops.ew_binary_into(ctx, A.Multiply, lb[k], rb[k], lv[k], rv[k], mnr.MaskMode.Or, ob[0][k], ob[1][k])
-    entry("supertable_64x16Mi_4col_table_mul_table", nrows * (3 * row_bytes + 4 * 3 / 8), table_mul, iters=5)
+    entry("supertable_64x16Mi_4col_table_mul_table_per_chunk_launches", nrows * (3 * row_bytes + 4 * 3 / 8), table_mul, iters=5)
+    plan = devops.EwBatchPlan(lb, rb, lv, rv, ob[0], ob[1])
+    entry("supertable_64x16Mi_4col_table_mul_table_batched", nrows * (3 * row_bytes + 4 * 3 / 8),
+          lambda: devops.ew_binary_batch_into(ctx, A.Multiply, lb, rb, lv, rv, mnr.MaskMode.Or, ob[0], ob[1], plan), iters=10)
+    # spot check: i32 chunk 0 of the product against torch (wrapping multiply, OR-union validity as the SuperArray route)
+    torch.cuda.synchronize()
+    l0, r0 = tabs[0][0][1][:1 << 20], tabs[1][0][1][:1 << 20]
+    vo = tabs[0][0][2][: 1 << 17] | tabs[1][0][2][: 1 << 17]
+    vbo = ((vo.to(torch.int32).view(-1, 1) >> torch.arange(8, device=dev, dtype=torch.int32)) & 1).bool().view(-1)
+    assert torch.equal(outs[0][0][:1 << 20], torch.where(vbo, l0 * r0, torch.zeros((), dtype=torch.int32, device=dev)))
+    assert torch.equal(outs[0][1][: 1 << 17], vo)
     scal = [3, 3, 2.5, 2.5]
-
-    def table_scalar():
-        for k in range(len(lb)):
-            devops.ew_scalar_into(ctx, A.Add if k < 2 * nb else A.Multiply, lb[k], scal[k // nb], False, lv[k], ob[0][k], ob[1][k])
-    entry("supertable_64x16Mi_4col_scalar_broadcast", nrows * (2 * row_bytes + 4 * 2 / 8), table_scalar, iters=5)
+    half = 2 * nb       # integer columns: + 3 ; float columns: * 2.5   (one typed scalar per column)
+    entry("supertable_64x16Mi_4col_scalar_broadcast_batched", nrows * (2 * row_bytes + 4 * 2 / 8),
+          lambda: (devops.ew_scalar_batch_into(ctx, A.Add, lb[:half], [3] * half, False, lv[:half], ob[0][:half], ob[1][:half]),
+                   devops.ew_scalar_batch_into(ctx, A.Multiply, lb[half:], [2.5] * half, False, lv[half:], ob[0][half:], ob[1][half:])),
+          iters=10)
     del lb, lv, rb, rv, ob, tabs, outs
     torch.cuda.empty_cache()
     return out

@@ -168,6 +168,21 @@ int mnr_ew_fma_into(mnr_ctx* ctx, const mnr_buf* a, const mnr_buf* b, const mnr_
 int mnr_ew_binary_promote(mnr_ctx* ctx, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lhs_mask,
                           const mnr_bits* rhs_mask, mnr_mask_mode mode, mnr_buf** out, mnr_bits** out_mask);
 
+/* Batched fan-out of the container routes: route_super_array_broadcast walks chunk pairs one leaf call at a time
+ * (src/kernels/broadcast/super_array.rs:180-249, "TODO: Parallelise" :193; Table / SuperTable routes table.rs:31-62,
+ * super_table.rs:38-73).  These take the whole chunk list: per-chunk length check as in super_array.rs:203-213, then
+ * ONE launch per (dtype, alignment, masked) class.  Chunk i's result is bit-identical to mnr_ew_binary(lhs[i], rhs[i]).
+ * Mask arrays may be NULL or hold NULL entries.  `scalars[i]` points at one host element of arrs[i]'s dtype. */
+int mnr_ew_binary_batch(mnr_ctx* ctx, mnr_op op, size_t n, const mnr_buf* const* lhs, const mnr_buf* const* rhs,
+                        const mnr_bits* const* lhs_mask, const mnr_bits* const* rhs_mask, mnr_mask_mode mode,
+                        mnr_buf** out, mnr_bits** out_mask);
+int mnr_ew_binary_batch_into(mnr_ctx* ctx, mnr_op op, size_t n, const mnr_buf* const* lhs, const mnr_buf* const* rhs,
+                             const mnr_bits* const* lhs_mask, const mnr_bits* const* rhs_mask, mnr_mask_mode mode,
+                             mnr_buf* const* out, mnr_bits* const* out_mask);
+int mnr_ew_scalar_batch_into(mnr_ctx* ctx, mnr_op op, size_t n, const mnr_buf* const* arrs, const void* const* scalars,
+                             int scalar_is_lhs, const mnr_bits* const* masks, mnr_buf* const* out,
+                             mnr_bits* const* out_mask);
+
 /* ---- bitmask kernels, device-resident (src/kernels/bitmask/dispatch.rs) ---------------------------------
  * Windows are BitmaskVT = (&Bitmask, offset, len).  Like the reference (bitmask_window_bytes,
  * src/kernels/bitmask/mod.rs:124-128) binop/not start at BYTE offset/8: sub-byte offsets are floored. */

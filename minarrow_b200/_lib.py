@@ -67,6 +67,9 @@ SIGNATURES = {
     "mnr_ew_fma": (c_int, [c_ctx, c_buf, c_buf, c_buf, c_bits, PP, PP]),
     "mnr_ew_fma_into": (c_int, [c_ctx, c_buf, c_buf, c_buf, c_bits, c_buf, c_bits]),
     "mnr_ew_binary_promote": (c_int, [c_ctx, c_int, c_buf, c_buf, c_bits, c_bits, c_int, PP, PP]),
+    "mnr_ew_binary_batch": (c_int, [c_ctx, c_int, c_sz, PP, PP, PP, PP, c_int, PP, PP]),
+    "mnr_ew_binary_batch_into": (c_int, [c_ctx, c_int, c_sz, PP, PP, PP, PP, c_int, PP, PP]),
+    "mnr_ew_scalar_batch_into": (c_int, [c_ctx, c_int, c_sz, PP, PP, c_int, PP, PP, PP]),
     "mnr_bits_binop": (c_int, [c_ctx, c_int, c_bits, c_sz, c_bits, c_sz, c_sz, PP]),
     "mnr_bits_binop_into": (c_int, [c_ctx, c_int, c_bits, c_sz, c_bits, c_sz, c_sz, c_bits]),
     "mnr_bits_not": (c_int, [c_ctx, c_bits, c_sz, c_sz, PP]),

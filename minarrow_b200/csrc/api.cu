@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "ew_kernels.cuh"
 #include "reduce_kernels.cuh"
 
 namespace mnr {
@@ -122,6 +123,7 @@ void mnr_ctx_destroy(mnr_ctx* c) {
     }
     for (int i = 0; i < 4; ++i) { cudaFree(c->partials[i]); cudaFree(c->ticket[i]); }
     if (c->chunk_aggs) cudaFree(c->chunk_aggs);
+    if (c->ew_segs) cudaFree(c->ew_segs);
     if (c->batch_partials) cudaFree(c->batch_partials);
     if (c->batch_segs) cudaFree(c->batch_segs);
     if (c->batch_tickets) cudaFree(c->batch_tickets);
@@ -432,6 +434,149 @@ int mnr_ew_binary_promote(mnr_ctx* c, mnr_op op, const mnr_buf* lhs, const mnr_b
     a.lmask = lm ? lm->ptr : nullptr; a.rmask = rm ? rm->ptr : nullptr; a.mask_or = mode == MNR_MASK_OR;
     a.out = (*out)->ptr; a.out_mask = (lm || rm) ? (*out_mask)->ptr : nullptr; a.n = lhs->len;
     return drop_outputs(run_ew(c, a, c->stream, true, l, r), out, out_mask);
+}
+
+// ---- batched element-wise fan-out -------------------------------------------------------------------------------------
+static int ensure_ew_segs(mnr_ctx* c, size_t bytes) {
+    if (c->ew_segs_bytes < bytes * 2) {
+        if (c->ew_segs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->ew_segs)); c->ew_segs = nullptr; }
+        CU(cudaMalloc(&c->ew_segs, bytes * 2));
+        c->ew_segs_bytes = bytes * 2;
+    }
+    return MNR_OK;
+}
+
+// items: fully validated EwArgs (one per chunk).  Aligned items of one (dtype, masked, tier) class share a launch;
+// the rest go one by one.  Dense integer division keeps the reference's panic as ONE error for the whole batch.
+static int run_ew_batch(mnr_ctx* c, std::vector<EwArgs>& items) {
+    if (items.empty()) return MNR_OK;
+    CU(cudaSetDevice(c->device));
+    unsigned int* flag = c->ticket[0] + 8;
+    bool any_dense_int_div = false;
+    for (auto& a : items) {
+        a.div0_flag = flag;
+        if (!a.lmask && !a.rmask && !is_float_dtype(a.dtype) && (a.op == MNR_DIV || a.op == MNR_REM || a.op == MNR_FLOORDIV))
+            any_dense_int_div = true;
+    }
+    if (any_dense_int_div) CU(cudaMemsetAsync(flag, 0, 4, c->stream));
+    struct Key { int dtype, tier, masked; };
+    std::vector<Key> keys;
+    std::vector<std::vector<EwDev>> groups;
+    std::vector<uint64_t> max_n;
+    for (const auto& a : items) {
+        if (a.n == 0) continue;
+        const int tier = ew_batch_tier(a.dtype, a.op, a.lhs, a.rhs, a.out);
+        if (tier == 0) {
+            CU(launch_ew_binary(a, c->stream));
+            c->launches++;
+            continue;
+        }
+        const Key k{(int)a.dtype, tier, (a.lmask || a.rmask) ? 1 : 0};
+        size_t g = 0;
+        for (; g < keys.size(); ++g) if (keys[g].dtype == k.dtype && keys[g].tier == k.tier && keys[g].masked == k.masked) break;
+        if (g == keys.size()) { keys.push_back(k); groups.emplace_back(); max_n.push_back(0); }
+        EwDev d;
+        d.lhs = a.lhs; d.rhs = a.rhs; d.scalar_bits = a.scalar_bits; d.lmask = a.lmask; d.rmask = a.rmask; d.mask_or = a.mask_or;
+        d.out = a.out; d.out_mask = a.out_mask; d.n = a.n; d.div0_flag = a.div0_flag; d.op = a.op;
+        groups[g].push_back(d);
+        max_n[g] = std::max<uint64_t>(max_n[g], a.n);
+    }
+    for (size_t g = 0; g < groups.size(); ++g) {
+        for (size_t off = 0; off < groups[g].size(); off += 65535) {
+            const size_t cnt = std::min<size_t>(65535, groups[g].size() - off);
+            int rc = ensure_ew_segs(c, std::min<size_t>(65535, groups[g].size()) * sizeof(EwDev));
+            if (rc) return rc;
+            char* dst = static_cast<char*>(c->ew_segs) + (c->ew_flip ? c->ew_segs_bytes / 2 : 0);
+            c->ew_flip ^= 1;
+            CU(cudaMemcpyAsync(dst, groups[g].data() + off, cnt * sizeof(EwDev), cudaMemcpyHostToDevice, c->stream));
+            CU(launch_ew_batch((mnr_dtype)keys[g].dtype, items[0].op, keys[g].tier, keys[g].masked != 0,
+                               reinterpret_cast<const EwDev*>(dst), (uint32_t)cnt, max_n[g], c->stream));
+            c->launches++;
+        }
+    }
+    if (any_dense_int_div) {
+        unsigned int* h = static_cast<unsigned int*>(c->h_scratch);
+        CU(cudaMemcpyAsync(h, flag, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (*h) return fail(MNR_ERR_DIVIDE_BY_ZERO, "division by zero in dense integer kernel (the reference panics here)");
+    }
+    return MNR_OK;
+}
+
+int mnr_ew_binary_batch_into(mnr_ctx* c, mnr_op op, size_t n, const mnr_buf* const* lhs, const mnr_buf* const* rhs,
+                             const mnr_bits* const* lmask, const mnr_bits* const* rmask, mnr_mask_mode mode,
+                             mnr_buf* const* out, mnr_bits* const* out_mask) {
+    REQUIRE(c && (n == 0 || (lhs && rhs && out)), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(op >= MNR_ADD && op <= MNR_FLOORDIV, MNR_ERR_OPERATOR_MISMATCH, "unknown operator %d", (int)op);
+    std::vector<EwArgs> items(n);
+    for (size_t i = 0; i < n; ++i) {
+        const mnr_buf *l = lhs[i], *r = rhs[i];
+        const mnr_bits* lm = lmask ? lmask[i] : nullptr;
+        const mnr_bits* rm = rmask ? rmask[i] : nullptr;
+        mnr_bits* om = out_mask ? out_mask[i] : nullptr;
+        REQUIRE(l && r && out[i], MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: NULL buffer", i);
+        // per-chunk length check of the SuperArray route (broadcast/super_array.rs:203-213)
+        REQUIRE(l->len == r->len, MNR_ERR_LENGTH_MISMATCH, "chunk %zu: length mismatch (lhs: %zu, rhs: %zu)", i, l->len, r->len);
+        REQUIRE(l->dtype == r->dtype, MNR_ERR_UNSUPPORTED_TYPE,
+                "chunk %zu: Unsupported array type combination for arithmetic operations (dtypes %d, %d)", i, (int)l->dtype, (int)r->dtype);
+        REQUIRE(out[i]->dtype == l->dtype && out[i]->len == l->len, MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: output shape/dtype mismatch", i);
+        const bool masked = lm || rm;
+        REQUIRE(!masked || (om && om->len == l->len), MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: masked call needs an output mask of %zu bits", i, l->len);
+        int rc = check_masks(lm, rm, l->len);
+        if (rc) return rc;
+        EwArgs& a = items[i];
+        a = EwArgs{};
+        a.dtype = l->dtype; a.op = op; a.lhs = l->ptr; a.rhs = r->ptr;
+        a.lmask = lm ? lm->ptr : nullptr; a.rmask = rm ? rm->ptr : nullptr; a.mask_or = mode == MNR_MASK_OR;
+        a.out = out[i]->ptr; a.out_mask = masked ? om->ptr : nullptr; a.n = l->len;
+    }
+    return run_ew_batch(c, items);
+}
+
+int mnr_ew_scalar_batch_into(mnr_ctx* c, mnr_op op, size_t n, const mnr_buf* const* arrs, const void* const* scalars,
+                             int scalar_is_lhs, const mnr_bits* const* masks, mnr_buf* const* out, mnr_bits* const* out_mask) {
+    REQUIRE(c && (n == 0 || (arrs && scalars && out)), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(op >= MNR_ADD && op <= MNR_FLOORDIV, MNR_ERR_OPERATOR_MISMATCH, "unknown operator %d", (int)op);
+    std::vector<EwArgs> items(n);
+    for (size_t i = 0; i < n; ++i) {
+        const mnr_buf* arr = arrs[i];
+        const mnr_bits* m = masks ? masks[i] : nullptr;
+        mnr_bits* om = out_mask ? out_mask[i] : nullptr;
+        REQUIRE(arr && scalars[i] && out[i], MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: NULL argument", i);
+        REQUIRE(out[i]->dtype == arr->dtype && out[i]->len == arr->len, MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: output shape/dtype mismatch", i);
+        REQUIRE(!m || (om && om->len == arr->len), MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: masked call needs an output mask of %zu bits", i, arr->len);
+        int rc = check_masks(m, nullptr, arr->len);
+        if (rc) return rc;
+        EwArgs& a = items[i];
+        a = EwArgs{};
+        a.dtype = arr->dtype; a.op = op;
+        a.lhs = scalar_is_lhs ? nullptr : arr->ptr;
+        a.rhs = scalar_is_lhs ? arr->ptr : nullptr;
+        a.scalar_bits = scalar_to_bits(arr->dtype, scalars[i]);
+        a.lmask = m ? m->ptr : nullptr; a.out = out[i]->ptr; a.out_mask = m ? om->ptr : nullptr; a.n = arr->len;
+    }
+    return run_ew_batch(c, items);
+}
+
+// Fresh outputs for every chunk (the reference returns a new SuperArray), then the batched launch.
+int mnr_ew_binary_batch(mnr_ctx* c, mnr_op op, size_t n, const mnr_buf* const* lhs, const mnr_buf* const* rhs,
+                        const mnr_bits* const* lmask, const mnr_bits* const* rmask, mnr_mask_mode mode, mnr_buf** out,
+                        mnr_bits** out_mask) {
+    REQUIRE(c && (n == 0 || (lhs && rhs && out && out_mask)), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    for (size_t i = 0; i < n; ++i) { out[i] = nullptr; out_mask[i] = nullptr; }
+    int rc = MNR_OK;
+    for (size_t i = 0; i < n && !rc; ++i) {
+        if (!lhs[i] || !rhs[i]) { rc = fail(MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: NULL buffer", i); break; }
+        if (lhs[i]->len != rhs[i]->len) {
+            rc = fail(MNR_ERR_LENGTH_MISMATCH, "chunk %zu: length mismatch (lhs: %zu, rhs: %zu)", i, lhs[i]->len, rhs[i]->len);
+            break;
+        }
+        const bool masked = (lmask && lmask[i]) || (rmask && rmask[i]);
+        rc = alloc_outputs(c, lhs[i]->dtype, lhs[i]->len, masked, &out[i], &out_mask[i]);
+    }
+    if (!rc) rc = mnr_ew_binary_batch_into(c, op, n, lhs, rhs, lmask, rmask, mode, out, out_mask);
+    if (rc) for (size_t i = 0; i < n; ++i) { mnr_buf_free(out[i]); mnr_bits_free(out_mask[i]); out[i] = nullptr; out_mask[i] = nullptr; }
+    return rc;
 }
 
 // ---- bitmask kernels ------------------------------------------------------------------------------------------------

@@ -52,6 +52,37 @@ static cudaError_t go(const EwArgs& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+template <typename T, typename VecT, int CLS>
+static cudaError_t go_batch(bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
+    using Cfg = typename CfgOf<CLS>::type;
+    constexpr int VEC = sizeof(VecT) / sizeof(T);
+    const dim3 grid(ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(max_n, VEC), nseg, 1);
+    if (masked) ew_binary_batch_kernel<T, T, T, VecT, CLS, true, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(segs);
+    else ew_binary_batch_kernel<T, T, T, VecT, CLS, false, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(segs);
+    return cudaGetLastError();
+}
+
+// tier 2 = the class's wide vector (256-bit for cheap ops), tier 1 = 128-bit.  Unaligned items are launched one by one.
+template <typename T, int CLS>
+static cudaError_t go_batch_tier(int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
+    using Wide = typename CfgOf<CLS>::type::Wide;
+    if (tier == 2) return go_batch<T, Wide, CLS>(masked, segs, nseg, max_n, s);
+    return go_batch<T, V16, CLS>(masked, segs, nseg, max_n, s);
+}
+
+template <typename T>
+static cudaError_t go_batch_t(int op, int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
+    switch (op_class(Traits<T>::is_float, op)) {
+        case CLS_CHEAP: return go_batch_tier<T, CLS_CHEAP>(tier, masked, segs, nseg, max_n, s);
+        case CLS_DIV: return go_batch_tier<T, CLS_DIV>(tier, masked, segs, nseg, max_n, s);
+        case CLS_POW: return go_batch_tier<T, CLS_POW>(tier, masked, segs, nseg, max_n, s);
+        case CLS_REM:
+            if constexpr (Traits<T>::is_float) return go_batch_tier<T, CLS_REM>(tier, masked, segs, nseg, max_n, s);
+            break;
+    }
+    return cudaErrorInvalidValue;
+}
+
 // Alignment tiers, like the reference's "64-byte aligned -> SIMD body, else scalar body" (dispatch.rs:86,108-111):
 // widest vector every operand pointer allows, else 128-bit, else element-wise loads.
 template <typename T, typename TL, typename TR, int CLS>
@@ -79,8 +110,12 @@ static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
     return cudaErrorInvalidValue;
 }
 
-#define MNR_EW_ENTRY(NAME, T) \
-    cudaError_t NAME(const EwArgs& a, cudaStream_t s) { return go_t<T>(a, s); }
+#define MNR_EW_ENTRY(NAME, T)                                                                                         \
+    cudaError_t NAME(const EwArgs& a, cudaStream_t s) { return go_t<T>(a, s); }                                       \
+    cudaError_t NAME##_batch(int op, int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n,         \
+                             cudaStream_t s) {                                                                        \
+        return go_batch_t<T>(op, tier, masked, segs, nseg, max_n, s);                                                 \
+    }
 
 #if MNR_EW_DTYPE == 6
 MNR_EW_ENTRY(launch_ew_i8, int8_t)
@@ -104,16 +139,39 @@ MNR_EW_ENTRY(launch_ew_f32, float)
 MNR_EW_ENTRY(launch_ew_f64, double)
 #elif MNR_EW_DTYPE == 100
 
-cudaError_t launch_ew_i8(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_u8(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_i16(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_u16(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_i32(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_u32(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_i64(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_u64(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_f32(const EwArgs&, cudaStream_t);
-cudaError_t launch_ew_f64(const EwArgs&, cudaStream_t);
+#define MNR_EW_DECL(NAME)                                 \
+    cudaError_t NAME(const EwArgs&, cudaStream_t);         \
+    cudaError_t NAME##_batch(int, int, bool, const EwDev*, uint32_t, uint64_t, cudaStream_t);
+MNR_EW_DECL(launch_ew_i8) MNR_EW_DECL(launch_ew_u8) MNR_EW_DECL(launch_ew_i16) MNR_EW_DECL(launch_ew_u16)
+MNR_EW_DECL(launch_ew_i32) MNR_EW_DECL(launch_ew_u32) MNR_EW_DECL(launch_ew_i64) MNR_EW_DECL(launch_ew_u64)
+MNR_EW_DECL(launch_ew_f32) MNR_EW_DECL(launch_ew_f64)
+
+// 2: every pointer allows the op class's wide vector; 1: 128-bit; 0: element loads (not batched).
+int ew_batch_tier(mnr_dtype dt, int op, const void* lhs, const void* rhs, const void* out) {
+    const bool is_float = dt == MNR_F32 || dt == MNR_F64;
+    const unsigned wide = op_class(is_float, op) == CLS_CHEAP ? 32u : 16u;
+    auto ok = [](const void* p, unsigned al) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (al - 1)) == 0; };
+    if (wide > 16 && ok(lhs, wide) && ok(rhs, wide) && ok(out, wide)) return 2;
+    if (ok(lhs, 16) && ok(rhs, 16) && ok(out, 16)) return wide == 16 ? 2 : 1;
+    return 0;
+}
+
+cudaError_t launch_ew_batch(mnr_dtype dt, int op, int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n,
+                            cudaStream_t s) {
+    switch (dt) {
+        case MNR_I8: return launch_ew_i8_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_U8: return launch_ew_u8_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_I16: return launch_ew_i16_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_U16: return launch_ew_u16_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_I32: return launch_ew_i32_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_U32: return launch_ew_u32_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_I64: return launch_ew_i64_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_U64: return launch_ew_u64_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_F32: return launch_ew_f32_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_F64: return launch_ew_f64_batch(op, tier, masked, segs, nseg, max_n, s);
+    }
+    return cudaErrorInvalidValue;
+}
 
 cudaError_t launch_ew_binary(const EwArgs& a, cudaStream_t s) {
     switch (a.dtype) {

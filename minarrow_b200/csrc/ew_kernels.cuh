@@ -166,8 +166,8 @@ __device__ __forceinline__ uint32_t merged_bits(const EwDev& a, uint64_t row0) {
 }
 
 // Element-wise binary kernel.  TL/TR: stored operand types (== T except for the cast-on-load promotion).
-template <typename T, typename TL, typename TR, typename VecT, int CLS, bool MASKED, int BLOCK, int U, int MINB = 1>
-__global__ void __launch_bounds__(BLOCK, MINB) ew_binary_kernel(const EwDev a) {
+template <typename T, typename TL, typename TR, typename VecT, int CLS, bool MASKED, int BLOCK, int U>
+__device__ __forceinline__ void ew_binary_body(const EwDev& a) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     // Operand vectors carry VEC elements of their own (possibly narrower) type.
     struct alignas(sizeof(TL) * VEC) LV { TL e[VEC]; };
@@ -280,6 +280,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) ew_binary_kernel(const EwDev a) {
     if constexpr (!MASKED && !Traits<T>::is_float && CLS == CLS_DIV) {
         if (div0) *a.div0_flag = 1u;
     }
+}
+
+template <typename T, typename TL, typename TR, typename VecT, int CLS, bool MASKED, int BLOCK, int U, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB) ew_binary_kernel(const __grid_constant__ EwDev a) {
+    ew_binary_body<T, TL, TR, VecT, CLS, MASKED, BLOCK, U>(a);
+}
+
+// One launch, many chunks (SuperArray / SuperTable fan-out): blockIdx.y selects the descriptor, which is staged in
+// shared memory so the body reads it exactly like kernel parameters.  Blocks beyond a short segment's tiles fall
+// through the grid-stride loops without touching memory.
+template <typename T, typename TL, typename TR, typename VecT, int CLS, bool MASKED, int BLOCK, int U, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB) ew_binary_batch_kernel(const EwDev* __restrict__ segs) {
+    __shared__ EwDev a;
+    static_assert(sizeof(EwDev) % 8 == 0, "EwDev is copied as 64-bit words");
+    if (threadIdx.x < sizeof(EwDev) / 8)
+        reinterpret_cast<uint64_t*>(&a)[threadIdx.x] = reinterpret_cast<const uint64_t*>(segs + blockIdx.y)[threadIdx.x];
+    __syncthreads();
+    ew_binary_body<T, TL, TR, VecT, CLS, MASKED, BLOCK, U>(a);
 }
 
 // FMA: out = fma(a, b, c) with one rounding (apply_fma_*, dispatch.rs:211-290; simd.rs:620,714).

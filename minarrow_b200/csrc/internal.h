@@ -47,6 +47,11 @@ struct EwArgs {
 cudaError_t launch_ew_binary(const EwArgs& a, cudaStream_t s);
 // I32 operand promoted on load against an F32/F64 operand (routing/arithmetic.rs:244-269).
 cudaError_t launch_ew_promote(const EwArgs& a, mnr_dtype lhs_dtype, mnr_dtype rhs_dtype, cudaStream_t s);
+// Batched element-wise launch: `segs` = device array of EwDev descriptors of one (dtype, op class, masked, tier) class.
+struct EwDev;
+int ew_batch_tier(mnr_dtype dt, int op, const void* lhs, const void* rhs, const void* out);
+cudaError_t launch_ew_batch(mnr_dtype dt, int op, int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n,
+                            cudaStream_t s);
 cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void* c, const uint8_t* mask, void* out,
                           uint8_t* out_mask, uint64_t n, cudaStream_t s);
 
@@ -92,6 +97,9 @@ struct mnr_ctx {
     void* batch_tickets = nullptr;
     size_t batch_tickets_bytes = 0;
     int batch_flip = 0;
+    void* ew_segs = nullptr;               // batched element-wise descriptors (double-buffered)
+    size_t ew_segs_bytes = 0;
+    int ew_flip = 0;
 };
 
 struct mnr_buf {

@@ -192,3 +192,41 @@ def reduce_stats_batch_async(ctx: Context, bufs, validities, with_minmax: bool, 
     vals = None if validities is None else _handle_array(list(validities))
     check(ctx.lib.mnr_reduce_stats_batch_async(ctx.h, n, _handle_array(list(bufs)), vals, int(with_minmax),
                                                C.c_void_p(out_device_ptr)))
+
+
+def ew_binary_batch(ctx: Context, op: int, lhs, rhs, lhs_masks=None, rhs_masks=None, mode: int = MaskMode.And):
+    """Chunk-wise `lhs[i] op rhs[i]` for a whole SuperArray / SuperTable in one call: fresh outputs per chunk, one launch
+    per (dtype, alignment, masked) class.  Returns ([DeviceBuffer], [DeviceBitmask | None])."""
+    n = len(lhs)
+    ob, om = (C.c_void_p * n)(), (C.c_void_p * n)()
+    lm = None if lhs_masks is None else _handle_array(list(lhs_masks))
+    rm = None if rhs_masks is None else _handle_array(list(rhs_masks))
+    check(ctx.lib.mnr_ew_binary_batch(ctx.h, int(op), n, _handle_array(list(lhs)), _handle_array(list(rhs)), lm, rm, int(mode),
+                                      ob, om))
+    return ([DeviceBuffer(ctx, C.c_void_p(ob[i])) for i in range(n)],
+            [DeviceBitmask(ctx, C.c_void_p(om[i])) if om[i] else None for i in range(n)])
+
+
+class EwBatchPlan:
+    """Pre-marshalled argument arrays for a repeated batched call (the ctypes arrays are built once)."""
+
+    def __init__(self, *lists):
+        self.arrays = [None if x is None else _handle_array(list(x)) for x in lists]
+        self.keep = lists
+
+
+def ew_binary_batch_into(ctx: Context, op: int, lhs, rhs, lhs_masks, rhs_masks, mode, out, out_masks, plan: EwBatchPlan = None):
+    p = plan or EwBatchPlan(lhs, rhs, lhs_masks, rhs_masks, out, out_masks)
+    a = p.arrays
+    check(ctx.lib.mnr_ew_binary_batch_into(ctx.h, int(op), len(p.keep[0]), a[0], a[1], a[2], a[3], int(mode), a[4], a[5]))
+    return p
+
+
+def ew_scalar_batch_into(ctx: Context, op: int, arrs, scalars, scalar_is_lhs: bool, masks, out, out_masks):
+    """`arrs[i] op scalars[i]` (or the reverse) for every chunk in one call; `scalars[i]` is cast to arrs[i]'s dtype."""
+    n = len(arrs)
+    keep = [np.array([s], dtype=a.dtype) for a, s in zip(arrs, scalars)]
+    sp = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
+    check(ctx.lib.mnr_ew_scalar_batch_into(ctx.h, int(op), n, _handle_array(list(arrs)), sp, int(scalar_is_lhs),
+                                           None if masks is None else _handle_array(list(masks)),
+                                           _handle_array(list(out)), None if out_masks is None else _handle_array(list(out_masks))))

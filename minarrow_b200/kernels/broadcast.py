@@ -37,6 +37,9 @@ def route_super_array_broadcast(op: ArithmeticOperator, lhs: SuperArray, rhs: Su
     masks, else the one present mask (super_array.rs:214-230) — fused into the kernel (MaskMode.Or)."""
     ctx = ctx or default_context()
     out = SuperArray()
+    # Chunk pairs that can share one batched launch (same dtype and length, at least one mask, no override):
+    # upload them all, one mnr_ew_binary_batch call, download.  Everything else takes the per-chunk router.
+    slots, bl, br, blm, brm = [], [], [], [], []
     for i, lc in enumerate(lhs.chunks):
         rc = rhs.chunks[i]
         if len(lc) != len(rc):
@@ -57,10 +60,16 @@ def route_super_array_broadcast(op: ArithmeticOperator, lhs: SuperArray, rhs: Su
                 merged = union(lm, rm, ctx)
             out.chunks.append(resolve_binary_arithmetic(op, lc, rc, merged, ctx))
             continue
-        ob, om = dev.ew_binary(ctx, op, DeviceBuffer.upload(ctx, ld), DeviceBuffer.upload(ctx, rd),
-                               None if lm is None else DeviceBitmask.upload(ctx, lm),
-                               None if rm is None else DeviceBitmask.upload(ctx, rm), MaskMode.Or)
-        out.chunks.append(make_array(ob.download(), om.download()))
+        slots.append(len(out.chunks))
+        out.chunks.append(None)
+        bl.append(DeviceBuffer.upload(ctx, ld))
+        br.append(DeviceBuffer.upload(ctx, rd))
+        blm.append(None if lm is None else DeviceBitmask.upload(ctx, lm))
+        brm.append(None if rm is None else DeviceBitmask.upload(ctx, rm))
+    if slots:
+        obs, oms = dev.ew_binary_batch(ctx, op, bl, br, blm, brm, MaskMode.Or)
+        for slot, ob, om in zip(slots, obs, oms):
+            out.chunks[slot] = make_array(ob.download(), om.download())
     return out
 
 

@@ -136,3 +136,70 @@ def test_batched_reductions_equal_one_by_one(mnr, gpu_ctx):
             else:
                 sel = d if hv is None else d[hv]
                 assert abs(g["sum"] - ex["sum"]) <= 1e-12 * max(1.0, np.abs(sel.astype(np.float64)).sum()), i
+
+
+def test_batched_elementwise_equals_one_by_one(mnr, gpu_ctx):
+    """mnr_ew_binary_batch / mnr_ew_scalar_batch_into over a mixed chunk list (dtypes, lengths incl. 0 and ragged,
+    one/two/no masks, unaligned views) == the oracle leaf per chunk, for a cheap op and a divide (integer zero
+    divisors null the row); dense integer division by zero anywhere in the batch is the reference's panic."""
+    dev = mnr.device_ops
+    rng = np.random.default_rng(34)
+    for op in (orc.ADD, orc.MUL, orc.DIV, orc.REM):
+        L, R, LM, RM, host = [], [], [], [], []
+        for dt in (np.int32, np.int64, np.uint64, np.float32, np.float64, np.uint8):
+            is_f = np.dtype(dt).kind == "f"
+            for n in (0, 1, 63, 4096, 100_003):
+                if is_f:
+                    a, b = (rng.standard_normal(n) * 9).astype(dt), (rng.standard_normal(n) * 9).astype(dt)
+                else:
+                    info = np.iinfo(dt)
+                    a = rng.integers(info.min, info.max, n, dtype=dt, endpoint=True)
+                    b = rng.integers(max(info.min, -4), min(info.max, 4), n, dtype=dt, endpoint=True)
+                A, B = mnr.DeviceBuffer.upload(gpu_ctx, a), mnr.DeviceBuffer.upload(gpu_ctx, b)
+                for kind in ("two", "lhs", "rhs"):
+                    la, lb = rng.random(n) < 0.9, rng.random(n) < 0.9
+                    L.append(A); R.append(B)
+                    LM.append(mnr.DeviceBitmask.upload(gpu_ctx, mnr.Bitmask.from_bools(la)) if kind != "rhs" else None)
+                    RM.append(mnr.DeviceBitmask.upload(gpu_ctx, mnr.Bitmask.from_bools(lb)) if kind != "lhs" else None)
+                    merged = la & lb if kind == "two" else la if kind == "lhs" else lb
+                    host.append((a, b, merged))
+                if n > 100:   # unaligned views (element-load tier, launched one by one inside the batch call)
+                    m = rng.random(n - 9) < 0.9
+                    L.append(A.slice(3, n - 9)); R.append(B.slice(1, n - 9))
+                    LM.append(mnr.DeviceBitmask.upload(gpu_ctx, mnr.Bitmask.from_bools(m))); RM.append(None)
+                    host.append((a[3:n - 6], b[1:n - 8], m))
+        obs, oms = dev.ew_binary_batch(gpu_ctx, op, L, R, LM, RM, mnr.MaskMode.And)
+        assert len(obs) == len(L)
+        for i, (a, b, merged) in enumerate(host):
+            exp, em = orc.apply(a, b, op, orc.Bits.from_bools(merged))
+            assert _bits_equal(obs[i].download(), exp), (op, i, a.dtype, a.size)
+            assert np.array_equal(oms[i].download().bits, em.bits), (op, i)
+        # scalar broadcast over the same chunks, both operand orders
+        outs = [mnr.DeviceBuffer.alloc(gpu_ctx, x.dtype, len(x)) for x in L]
+        outm = [mnr.DeviceBitmask.alloc(gpu_ctx, len(x)) for x in L]
+        for s_lhs in (False, True):
+            dev.ew_scalar_batch_into(gpu_ctx, op, L, [3] * len(L), s_lhs, LM if all(m is not None for m in LM) else
+                                     [m if m is not None else r for m, r in zip(LM, RM)], outs, outm)
+            for i, (a, b, merged) in enumerate(host):
+                mask_used = LM[i] if LM[i] is not None else RM[i]
+                mb = mask_used.download().to_bools()
+                full = np.full(a.size, 3, dtype=a.dtype)
+                l, r = (full, a) if s_lhs else (a, full)
+                exp, em = orc.apply(l, r, op, orc.Bits.from_bools(mb))
+                assert _bits_equal(outs[i].download(), exp), (op, s_lhs, i)
+                assert np.array_equal(outm[i].download().bits, em.bits), (op, s_lhs, i)
+    # dense integer chunks, one zero divisor in the third chunk -> DivideByZero for the batch
+    a = [mnr.DeviceBuffer.upload(gpu_ctx, np.arange(1, 1001, dtype=np.int64)) for _ in range(4)]
+    d = np.ones(1000, dtype=np.int64)
+    bs = [mnr.DeviceBuffer.upload(gpu_ctx, d) for _ in range(4)]
+    obs, oms = dev.ew_binary_batch(gpu_ctx, orc.DIV, a, bs)
+    assert all(m is None for m in oms) and _bits_equal(obs[0].download(), np.arange(1, 1001, dtype=np.int64))
+    d2 = d.copy(); d2[777] = 0
+    bs[2] = mnr.DeviceBuffer.upload(gpu_ctx, d2)
+    with pytest.raises(mnr.KernelError) as ei:
+        dev.ew_binary_batch(gpu_ctx, orc.DIV, a, bs)
+    assert ei.value.kind == "DivideByZero"
+    # ragged pair -> LengthMismatch, like the SuperArray route's per-chunk check (broadcast/super_array.rs:203-213)
+    with pytest.raises(mnr.KernelError) as ei:
+        dev.ew_binary_batch(gpu_ctx, orc.ADD, [a[0]], [mnr.DeviceBuffer.upload(gpu_ctx, np.ones(7, dtype=np.int64))])
+    assert ei.value.kind == "LengthMismatch"
