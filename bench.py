@@ -563,6 +563,15 @@ def run_b200(args):
             return None
 
         e2e_step()
+        # the PCIe roofline of this step: the same bytes as one plain pinned H2D copy
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        data.copy_(host_data, non_blocking=True)
+        bits.copy_(host_bits, non_blocking=True)
+        c1.record()
+        c1.synchronize()
+        h2d_gbs = (rows * 8 + bits.numel()) / (c0.elapsed_time(c1) * 1e-3) / 1e9
         barrier()
         l0 = ctx.launch_count
         w0 = time.perf_counter()
@@ -585,7 +594,9 @@ def run_b200(args):
                "ms_per_step": round(float(tsec[0]) * 1e3, 3), "steps": args.e2e_steps,
                "api": "mnr_stats_host (C ABI, pinned host column + validity -> 32-byte aggregate)",
                "timer": "host wall clock around synchronous calls, max over ranks",
-               "gpu_launches": int(e2e_launches)}
+               "gpu_launches": int(e2e_launches), "pcie_h2d_copy_GBps_per_gpu": round(h2d_gbs, 2),
+               "frac_of_pcie_copy": round(rows * BYTES_PER_ROW / float(tsec[0]) / 1e9 / h2d_gbs, 4),
+               "note": "bound by the host->device link: the same bytes as one plain pinned cudaMemcpy take 1/frac of this"}
 
     # ---- CPU baseline: bounded sample on this box's host cores (rank 0, N = 1 only) ------------------------------
     cpu = None

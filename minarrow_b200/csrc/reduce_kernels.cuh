@@ -274,22 +274,27 @@ __device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, co
     }
 
     p = block_combine<P, BLOCK>(p, smem);
-    if (threadIdx.x == 0) {
-        partials[bid] = p.raw();
+    P q;
+    if (nblk == 1) {
+        q = p;   // small column: the only block is the finishing block — no partials, no ticket, no fences
+    } else {
+        if (threadIdx.x == 0) {
+            partials[bid] = p.raw();
+            __threadfence();
+            const unsigned int done = atomicAdd(ticket, 1u);
+            is_last = (done == nblk - 1);
+        }
+        __syncthreads();
+        if (!is_last) return;
         __threadfence();
-        const unsigned int done = atomicAdd(ticket, 1u);
-        is_last = (done == nblk - 1);
+        q.init();
+        bool first = true;
+        for (unsigned int i = threadIdx.x; i < nblk; i += BLOCK) {
+            P t; t.from_raw(load_partial(partials + i));
+            if (first) { q = t; first = false; } else q.merge(t);
+        }
+        q = block_combine<P, BLOCK>(q, smem);
     }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    P q; q.init();
-    bool first = true;
-    for (unsigned int i = threadIdx.x; i < nblk; i += BLOCK) {
-        P t; t.from_raw(load_partial(partials + i));
-        if (first) { q = t; first = false; } else q.merge(t);
-    }
-    q = block_combine<P, BLOCK>(q, smem);
     if (x.world > 0) {   // fused cross-GPU finish (block-uniform branch; only the finishing block gets here)
         __shared__ AggRaw mine;
         __shared__ AggRaw got[kMaxPeers];
@@ -330,7 +335,7 @@ __device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, co
             *out_host = r;
             __threadfence_system();
         }
-        *ticket = 0;   // re-arm for the next launch on this stream
+        if (nblk > 1) *ticket = 0;   // re-arm for the next launch on this stream
     }
 }
 
