@@ -544,6 +544,15 @@ def run_b200(args):
     e2e = None
     host_data = host_bits = None
     if not args.no_e2e:
+        # page-locking is bounded by what the box has: at most a quarter of MemAvailable over all ranks
+        try:
+            with open("/proc/meminfo") as f:
+                avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable"))
+        except Exception:  # noqa: BLE001
+            avail = 64 << 30
+        if rows * 8.125 * world > avail / 4:
+            raise SystemExit(f"bench.py: {rows} rows x {world} ranks of pinned host memory do not fit a quarter of "
+                             f"MemAvailable ({avail >> 30} GiB); rerun with --no-e2e or fewer --rows")
         host_data = torch.empty(rows, dtype=torch.int64, pin_memory=True)
         host_bits = torch.empty(bits.numel(), dtype=torch.uint8, pin_memory=True)
         host_data.copy_(data)
