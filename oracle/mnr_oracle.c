@@ -561,6 +561,14 @@ DEF_STATS_FLOAT(f32) DEF_STATS_FLOAT(f64)
  * (par_chunks(1<<20) -> per-chunk sum -> combine; benchmark_parallel_simd.rs:81-89) so that it can
  * serve as the timed CPU baseline.  Validity is consumed a u64 word at a time (chunks are 2^20 rows,
  * a multiple of 64).  All host threads via OpenMP when threads > 1. */
+#if defined(__AVX2__)
+#include <immintrin.h>
+#define NL(b) ((b) ? -1ll : 0ll)
+#define NIB(k) {{NL((k) & 1), NL((k) & 2), NL((k) & 4), NL((k) & 8)}}
+static const union { long long q[4]; __m256i v; } NIBBLE_LANES_U[16] = {NIB(0), NIB(1), NIB(2), NIB(3), NIB(4), NIB(5), NIB(6), NIB(7),
+                                                                        NIB(8), NIB(9), NIB(10), NIB(11), NIB(12), NIB(13), NIB(14), NIB(15)};
+#define NIBBLE_LANES(k) (NIBBLE_LANES_U[(k)].v)
+#endif
 void orc_par_masked_sum_i64(const i64 *d, size_t n, const uint8_t *validity, int threads,
                             i64 *out_sum, u64 *out_count) {
     size_t nchunks = (n + PAR_CHUNK - 1) / PAR_CHUNK;
@@ -577,6 +585,27 @@ void orc_par_masked_sum_i64(const i64 *d, size_t n, const uint8_t *validity, int
             cn = hi - lo;
         } else {
             size_t i = lo;
+#if defined(__AVX2__)
+            /* 4 x i64 lanes like the reference's Simd<i64, 4> (benchmark_parallel_simd.rs:44-60); a validity nibble
+             * selects the lanes through a 16-entry table of lane masks. */
+            __m256i a0 = _mm256_setzero_si256(), a1 = a0, a2 = a0, a3 = a0;
+            for (; i + 64 <= hi; i += 64) {
+                u64 w; memcpy(&w, validity + i / 8, 8);
+                cn += (u64)__builtin_popcountll(w);
+                const __m256i *p = (const __m256i *)(d + i);
+                for (int q = 0; q < 16; q += 4) {
+                    a0 = _mm256_add_epi64(a0, _mm256_and_si256(_mm256_loadu_si256(p + q), NIBBLE_LANES((w >> (4 * q)) & 15)));
+                    a1 = _mm256_add_epi64(a1, _mm256_and_si256(_mm256_loadu_si256(p + q + 1), NIBBLE_LANES((w >> (4 * q + 4)) & 15)));
+                    a2 = _mm256_add_epi64(a2, _mm256_and_si256(_mm256_loadu_si256(p + q + 2), NIBBLE_LANES((w >> (4 * q + 8)) & 15)));
+                    a3 = _mm256_add_epi64(a3, _mm256_and_si256(_mm256_loadu_si256(p + q + 3), NIBBLE_LANES((w >> (4 * q + 12)) & 15)));
+                }
+            }
+            {
+                u64 t[4];
+                _mm256_storeu_si256((__m256i *)t, _mm256_add_epi64(_mm256_add_epi64(a0, a1), _mm256_add_epi64(a2, a3)));
+                s0 += t[0]; s1 += t[1]; s2 += t[2]; s3 += t[3];
+            }
+#endif
             for (; i + 64 <= hi; i += 64) {
                 u64 w; memcpy(&w, validity + i / 8, 8);
                 cn += (u64)__builtin_popcountll(w);
