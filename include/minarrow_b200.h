@@ -217,6 +217,11 @@ int mnr_bits_all_eq(mnr_ctx* ctx, const mnr_bits* a, size_t a_offset, const mnr_
 int mnr_bits_in(mnr_ctx* ctx, const mnr_bits* lhs, size_t lhs_offset, const mnr_bits* rhs, size_t rhs_offset,
                 size_t len, int negate, mnr_bits** out);
 
+/* simd_eq_mask_u8 / _u16 / _u32 / _u64 (src/kernels/bitmask/simd.rs:741-788): typed compare -> bitmask,
+ * bit i = ((data[i] & *field_mask) == *target); `field_mask` / `target` point at one host element of data's dtype
+ * (any integer dtype: the compare is on the raw lanes). */
+int mnr_eq_mask(mnr_ctx* ctx, const mnr_buf* data, const void* field_mask, const void* target, mnr_bits** out);
+
 /* ---- reductions, device-resident -------------------------------------------------------------------------
  * Sum follows the benches that define it in the reference (benches/benchmark_parallel_simd.rs:44-97,
  * benches/hotloop_benchmark_simd.rs:56-174): integer sums wrap and are bit-exact in any order; float sums
@@ -297,6 +302,35 @@ int mnr_host_unregister(void* ptr);
 /* Pinned host allocation (the download side of SharedBuffer::from_owner, src/structs/shared_buffer/mod.rs:187). */
 int mnr_host_alloc(size_t bytes, void** out);
 void mnr_host_free(void* ptr);
+
+/* ---- Arrow C Data Interface <-> device buffers ----------------------------------------------------------------
+ * The reference's own C ABI (src/ffi/arrow_c_ffi.rs:87-98,121-133; export_to_c :432-470 with buffers =
+ * [validity | NULL, values], n_buffers = 2, :481-490; import_from_c :640).  Struct layouts are the Arrow spec's. */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+    const char* format; const char* name; const char* metadata; int64_t flags; int64_t n_children;
+    struct ArrowSchema** children; struct ArrowSchema* dictionary;
+    void (*release)(struct ArrowSchema*); void* private_data;
+};
+struct ArrowArray {
+    int64_t length; int64_t null_count; int64_t offset; int64_t n_buffers; int64_t n_children;
+    const void** buffers; struct ArrowArray** children; struct ArrowArray* dictionary;
+    void (*release)(struct ArrowArray*); void* private_data;
+};
+#endif
+/* Upload a HOST ArrowArray of a Minarrow numeric type (formats c C s S i I l L f g) or boolean (b).  `offset` is
+ * honoured: element offset for values, an arbitrary BIT offset for validity / boolean data (shifted on the device).
+ * Numeric: *values is set, data_bits may be NULL.  Boolean: *data_bits is set, values may be NULL.  *validity is
+ * NULL when the array has no validity buffer or null_count == 0.  The array is borrowed: release stays with the caller. */
+int mnr_arrow_import(mnr_ctx* ctx, const struct ArrowArray* array, const struct ArrowSchema* schema, mnr_buf** values,
+                     mnr_bits** data_bits, mnr_bits** validity);
+/* Download into a fresh host ArrowArray (64-byte aligned buffers, offset 0, null_count filled in) that the consumer
+ * releases through array->release, like export_to_c.  `out_schema` may be NULL. */
+int mnr_arrow_export(mnr_ctx* ctx, const mnr_buf* values, const mnr_bits* validity, struct ArrowArray* out_array,
+                     struct ArrowSchema* out_schema);
+int mnr_arrow_export_bool(mnr_ctx* ctx, const mnr_bits* data_bits, const mnr_bits* validity,
+                          struct ArrowArray* out_array, struct ArrowSchema* out_schema);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ from . import _lib
 
 _lib.load()
 
-from . import device_ops, kernels  # noqa: E402
+from . import arrow, device_ops, kernels, sharded  # noqa: E402
 from .core import (ArithmeticOperator, Bitmask, BooleanArray, Context, DeviceBitmask, DeviceBuffer, FloatArray,  # noqa: E402
                    IntegerArray, KernelError, LogicalOperator, MaskMode, ShapeError, default_context)
 from .kernels.arithmetic import (apply_float_f32, apply_float_f64, apply_fma_f32, apply_fma_f64, apply_int_i32,  # noqa: E402

@@ -81,6 +81,7 @@ SIGNATURES = {
     "mnr_bits_eq": (c_int, [c_ctx, c_bits, c_sz, c_bits, c_sz, c_sz, c_int, PP]),
     "mnr_bits_all_eq": (c_int, [c_ctx, c_bits, c_sz, c_bits, c_sz, c_sz, C.POINTER(c_int)]),
     "mnr_bits_in": (c_int, [c_ctx, c_bits, c_sz, c_bits, c_sz, c_sz, c_int, PP]),
+    "mnr_eq_mask": (c_int, [c_ctx, c_buf, c_vp, c_vp, PP]),
     "mnr_reduce_stats": (c_int, [c_ctx, c_buf, c_bits, C.POINTER(Agg)]),
     "mnr_reduce_sum": (c_int, [c_ctx, c_buf, c_bits, C.POINTER(Scalar64), C.POINTER(C.c_uint64)]),
     "mnr_reduce_stats_async": (c_int, [c_ctx, c_buf, c_bits, c_int, c_vp]),
@@ -104,6 +105,9 @@ SIGNATURES = {
     "mnr_apply_fma_host": (c_int, [c_ctx, c_int, c_vp, c_sz, c_vp, c_sz, c_vp, c_sz, c_vp, c_vp, c_vp]),
     "mnr_stats_host": (c_int, [c_ctx, c_int, c_vp, c_sz, c_vp, c_int, C.POINTER(Agg)]),
     "mnr_bitmask_binop_host": (c_int, [c_ctx, c_int, c_vp, c_sz, c_vp, c_sz, c_sz, c_vp]),
+    "mnr_arrow_import": (c_int, [c_ctx, c_vp, c_vp, PP, PP, PP]),
+    "mnr_arrow_export": (c_int, [c_ctx, c_buf, c_bits, c_vp, c_vp]),
+    "mnr_arrow_export_bool": (c_int, [c_ctx, c_bits, c_bits, c_vp, c_vp]),
     "mnr_host_register": (c_int, [c_vp, c_sz]),
     "mnr_host_unregister": (c_int, [c_vp]),
     "mnr_host_alloc": (c_int, [c_sz, PP]),

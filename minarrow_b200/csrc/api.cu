@@ -56,6 +56,10 @@ static bool is_float_dtype(int d) { return d == MNR_F32 || d == MNR_F64; }
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 static size_t mask_bytes(size_t bits) { return (bits + 7) >> 3; }
 
+namespace mnr {
+int fail_public(int code, const char* msg) { return fail(code, "%s", msg); }   // error reporting for the other translation units
+}  // namespace mnr
+
 extern "C" {
 
 int mnr_abi_version(void) { return MNR_ABI_VERSION; }
@@ -763,6 +767,20 @@ int mnr_bits_in(mnr_ctx* c, const mnr_bits* lhs, size_t lo, const mnr_bits* rhs,
         r = nr;
     }
     *out = r;
+    return MNR_OK;
+}
+
+int mnr_eq_mask(mnr_ctx* c, const mnr_buf* data, const void* field_mask, const void* target, mnr_bits** out) {
+    REQUIRE(c && data && field_mask && target && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(!is_float_dtype(data->dtype), MNR_ERR_UNSUPPORTED_TYPE, "eq_mask works on integer lanes (u8/u16/u32/u64 and their signed twins)");
+    *out = nullptr;
+    int rc = mnr_bits_alloc(c, data->len, out);
+    if (rc) return rc;
+    if (data->len == 0) return MNR_OK;
+    CU(cudaSetDevice(c->device));
+    CU(launch_eq_mask((int)dtype_size(data->dtype), data->ptr, data->len, scalar_to_bits(data->dtype, field_mask),
+                      scalar_to_bits(data->dtype, target), (*out)->ptr, c->stream));
+    c->launches++;
     return MNR_OK;
 }
 

@@ -1,0 +1,182 @@
+// Arrow C Data Interface <-> device buffers.
+//
+// The reference's only existing C ABI is the Arrow C Data Interface (src/ffi/arrow_c_ffi.rs:87-98 ArrowArray, :121-133
+// ArrowSchema; export_to_c :432-470 writes buffers = [validity | NULL, values], n_buffers = 2, :481-490; import_from_c
+// :640).  These entry points let any Arrow producer (PyArrow, arrow-rs, polars, Minarrow itself) feed the GPU path
+// without a Minarrow-specific copy: a numeric or boolean array in HOST memory is uploaded honouring `offset` — an
+// element offset for values, an arbitrary BIT offset for validity / boolean data (shifted on the device; the reference's
+// bitmask_binop floors sub-byte offsets, src/kernels/bitmask/mod.rs:124-128, simd_mask handles them, src/utils.rs:230-239)
+// — and device results are exported back as a host ArrowArray with a release callback.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "internal.h"
+
+using namespace mnr;
+
+namespace mnr {
+int fail_public(int code, const char* msg);   // api.cu: sets the thread-local error string
+}
+
+namespace {
+
+struct FmtMap { const char* fmt; mnr_dtype dt; };
+const FmtMap kFmt[] = {{"c", MNR_I8}, {"C", MNR_U8}, {"s", MNR_I16}, {"S", MNR_U16}, {"i", MNR_I32},
+                       {"I", MNR_U32}, {"l", MNR_I64}, {"L", MNR_U64}, {"f", MNR_F32}, {"g", MNR_F64}};
+
+const char* fmt_of(mnr_dtype dt) {
+    for (const auto& f : kFmt) if (f.dt == dt) return f.fmt;
+    return nullptr;
+}
+
+// Exported arrays own one host block: [ArrowArray buffers[2]] + 64-byte aligned validity + values.
+struct ExportPriv {
+    const void* buffers[2];
+    void* validity;
+    void* values;
+};
+
+void release_array(struct ArrowArray* a) {
+    if (!a || !a->release) return;
+    ExportPriv* p = static_cast<ExportPriv*>(a->private_data);
+    if (p) { free(p->validity); free(p->values); delete p; }
+    a->release = nullptr;
+    a->private_data = nullptr;
+}
+
+void release_schema(struct ArrowSchema* s) {
+    if (!s || !s->release) return;
+    s->release = nullptr;
+}
+
+void* alloc64(size_t bytes) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 64, (bytes + 63) / 64 * 64 + 64) != 0) return nullptr;   // Vec64-style 64-byte alignment
+    return p;
+}
+
+#define AFAIL(code, msg) return mnr::fail_public(code, msg)
+
+// Upload bits [bit_offset, bit_offset + len) of a host bitmap as a fresh device mask starting at bit 0.
+int upload_bits_window(mnr_ctx* c, const uint8_t* host, int64_t bit_offset, int64_t len, mnr_bits** out) {
+    int rc = mnr_bits_alloc(c, (size_t)len, out);
+    if (rc || len == 0) return rc;
+    const size_t first = (size_t)bit_offset >> 3, shift = (size_t)bit_offset & 7;
+    const size_t nbytes = (shift + (size_t)len + 7) >> 3;
+    if (shift == 0) {
+        if (cudaMemcpyAsync((*out)->ptr, host + first, (size_t)(len + 7) >> 3, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+            AFAIL(MNR_ERR_CUDA, "arrow import: validity upload failed");
+        // clear the slack bits of the last byte (Bitmask::mask_trailing_bits)
+        if (launch_bits_op(5, (*out)->ptr, 0, (uint64_t)len, nullptr, 0, 0, (uint64_t)len, (*out)->ptr, c->stream) != cudaSuccess)
+            AFAIL(MNR_ERR_CUDA, "arrow import: trailing-bit clear failed");
+        c->launches++;
+    } else {
+        void* tmp = nullptr;
+        if (cudaMallocAsync(&tmp, nbytes + 16, c->stream) != cudaSuccess) AFAIL(MNR_ERR_OUT_OF_MEMORY, "arrow import: staging allocation failed");
+        if (cudaMemcpyAsync(tmp, host + first, nbytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+            AFAIL(MNR_ERR_CUDA, "arrow import: validity upload failed");
+        if (launch_bits_op(5, static_cast<const uint8_t*>(tmp), shift, nbytes * 8, nullptr, 0, 0, (uint64_t)len, (*out)->ptr, c->stream) != cudaSuccess)
+            AFAIL(MNR_ERR_CUDA, "arrow import: bit shift failed");
+        c->launches++;
+        cudaFreeAsync(tmp, c->stream);
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) AFAIL(MNR_ERR_CUDA, "arrow import: synchronize failed");
+    return MNR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mnr_arrow_import(mnr_ctx* c, const struct ArrowArray* a, const struct ArrowSchema* s, mnr_buf** values, mnr_bits** data_bits,
+                     mnr_bits** validity) {
+    if (!c || !a || !s || !validity) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow import: NULL argument");
+    if (values) *values = nullptr;
+    if (data_bits) *data_bits = nullptr;
+    *validity = nullptr;
+    if (!s->format) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow import: schema has no format string");
+    if (a->n_buffers != 2 || !a->buffers) AFAIL(MNR_ERR_UNSUPPORTED_TYPE, "arrow import: only fixed-width primitive / boolean layouts (n_buffers == 2)");
+    if (a->length < 0 || a->offset < 0) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow import: negative length / offset");
+    if (a->dictionary || a->n_children != 0) AFAIL(MNR_ERR_UNSUPPORTED_TYPE, "arrow import: nested / dictionary arrays are outside this path");
+    if (cudaSetDevice(c->device) != cudaSuccess) AFAIL(MNR_ERR_CUDA, "arrow import: cudaSetDevice failed");
+    const uint8_t* vbuf = static_cast<const uint8_t*>(a->buffers[0]);
+    const uint8_t* dbuf = static_cast<const uint8_t*>(a->buffers[1]);
+    if (!dbuf && a->length > 0) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow import: values buffer is NULL");
+    int rc = MNR_OK;
+    if (!strcmp(s->format, "b")) {
+        if (!data_bits) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow import: boolean array needs data_bits");
+        rc = upload_bits_window(c, dbuf, a->offset, a->length, data_bits);
+    } else {
+        const FmtMap* f = nullptr;
+        for (const auto& k : kFmt) if (!strcmp(k.fmt, s->format)) f = &k;
+        if (!f) AFAIL(MNR_ERR_UNSUPPORTED_TYPE, "arrow import: format is not a Minarrow numeric type (c C s S i I l L f g b)");
+        if (!values) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow import: numeric array needs values");
+        rc = mnr_buf_upload(c, f->dt, dbuf ? dbuf + (size_t)a->offset * dtype_size(f->dt) : nullptr, (size_t)a->length, values);
+    }
+    if (rc) return rc;
+    if (vbuf && a->null_count != 0) {   // null_count == 0 => the producer promises all-valid; -1 = unknown
+        rc = upload_bits_window(c, vbuf, a->offset, a->length, validity);
+        if (rc) {
+            if (values) { mnr_buf_free(*values); *values = nullptr; }
+            if (data_bits) { mnr_bits_free(*data_bits); *data_bits = nullptr; }
+        }
+    }
+    return rc;
+}
+
+static int export_common(mnr_ctx* c, const char* fmt, size_t len, const void* dev_values, size_t value_bytes, const mnr_bits* validity,
+                         struct ArrowArray* out_array, struct ArrowSchema* out_schema) {
+    if (cudaSetDevice(c->device) != cudaSuccess) AFAIL(MNR_ERR_CUDA, "arrow export: cudaSetDevice failed");
+    ExportPriv* p = new ExportPriv();
+    p->values = alloc64(value_bytes ? value_bytes : 1);
+    p->validity = validity ? alloc64((len + 7) / 8 ? (len + 7) / 8 : 1) : nullptr;
+    if (!p->values || (validity && !p->validity)) { free(p->values); free(p->validity); delete p; AFAIL(MNR_ERR_OUT_OF_MEMORY, "arrow export: host allocation failed"); }
+    bool ok = true;
+    if (value_bytes) ok &= cudaMemcpyAsync(p->values, dev_values, value_bytes, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    if (validity && len) ok &= cudaMemcpyAsync(p->validity, validity->ptr, (len + 7) / 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    uint64_t ones = len;
+    ok &= cudaStreamSynchronize(c->stream) == cudaSuccess;
+    if (!ok) { free(p->values); free(p->validity); delete p; AFAIL(MNR_ERR_CUDA, "arrow export: download failed"); }
+    if (validity && len) {
+        ones = 0;
+        const uint8_t* vb = static_cast<const uint8_t*>(p->validity);
+        for (size_t i = 0; i < (len + 7) / 8; ++i) ones += (uint64_t)__builtin_popcount(vb[i]);
+    }
+    p->buffers[0] = p->validity;
+    p->buffers[1] = p->values;
+    memset(out_array, 0, sizeof *out_array);
+    out_array->length = (int64_t)len;
+    out_array->null_count = (int64_t)(len - ones);
+    out_array->offset = 0;
+    out_array->n_buffers = 2;
+    out_array->buffers = p->buffers;
+    out_array->release = release_array;
+    out_array->private_data = p;
+    if (out_schema) {
+        memset(out_schema, 0, sizeof *out_schema);
+        out_schema->format = fmt;          // static strings
+        out_schema->name = "";
+        out_schema->flags = validity ? 2 : 0;   // ARROW_FLAG_NULLABLE
+        out_schema->release = release_schema;
+    }
+    return MNR_OK;
+}
+
+int mnr_arrow_export(mnr_ctx* c, const mnr_buf* values, const mnr_bits* validity, struct ArrowArray* out_array,
+                     struct ArrowSchema* out_schema) {
+    if (!c || !values || !out_array) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow export: NULL argument");
+    if (validity && validity->len < values->len) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow export: validity shorter than values");
+    const char* fmt = fmt_of(values->dtype);
+    if (!fmt) AFAIL(MNR_ERR_UNSUPPORTED_TYPE, "arrow export: unknown dtype");
+    return export_common(c, fmt, values->len, values->ptr, values->len * dtype_size(values->dtype), validity, out_array, out_schema);
+}
+
+int mnr_arrow_export_bool(mnr_ctx* c, const mnr_bits* data_bits, const mnr_bits* validity, struct ArrowArray* out_array,
+                          struct ArrowSchema* out_schema) {
+    if (!c || !data_bits || !out_array) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow export: NULL argument");
+    if (validity && validity->len < data_bits->len) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow export: validity shorter than data");
+    return export_common(c, "b", data_bits->len, data_bits->ptr, (data_bits->len + 7) / 8, validity, out_array, out_schema);
+}
+
+}  // extern "C"

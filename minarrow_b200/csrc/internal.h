@@ -60,6 +60,9 @@ cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void
 // slack bits of the last byte zero; reads stay inside [0, ceil(x_bits_total/8)).
 cudaError_t launch_bits_op(int op, const uint8_t* a, uint64_t a_bitpos, uint64_t a_total_bits, const uint8_t* b,
                            uint64_t b_bitpos, uint64_t b_total_bits, uint64_t len, uint8_t* out, cudaStream_t s);
+// Typed compare -> bitmask (compare.cu): bit i = ((data[i] & field_mask) == target), elements of 1/2/4/8 bytes.
+cudaError_t launch_eq_mask(int elem_bytes, const void* data, uint64_t n, uint64_t field_mask, uint64_t target, uint8_t* out,
+                           cudaStream_t s);
 // Popcount of (a [xor b]) over len bits from the given bit positions -> *result (device) and, if non-NULL,
 // *result_host (mapped pinned host memory).  partials: >= popcount_max_grid() words; ticket: zeroed, re-armed by the kernel.
 int popcount_max_grid();

@@ -230,3 +230,11 @@ def ew_scalar_batch_into(ctx: Context, op: int, arrs, scalars, scalar_is_lhs: bo
     check(ctx.lib.mnr_ew_scalar_batch_into(ctx.h, int(op), n, _handle_array(list(arrs)), sp, int(scalar_is_lhs),
                                            None if masks is None else _handle_array(list(masks)),
                                            _handle_array(list(out)), None if out_masks is None else _handle_array(list(out_masks))))
+
+
+def eq_mask(ctx: Context, data: DeviceBuffer, field_mask, target) -> DeviceBitmask:
+    """simd_eq_mask_u{8,16,32,64} (bitmask/simd.rs:741-788): bit i = ((data[i] & field_mask) == target)."""
+    fm, tg = np.array([field_mask], dtype=data.dtype), np.array([target], dtype=data.dtype)
+    o = C.c_void_p()
+    check(ctx.lib.mnr_eq_mask(ctx.h, data.h, fm.ctypes.data_as(C.c_void_p), tg.ctypes.data_as(C.c_void_p), C.byref(o)))
+    return DeviceBitmask(ctx, o)

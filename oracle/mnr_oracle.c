@@ -638,6 +638,16 @@ void orc_par_apply_float_f64(const f64 *lhs, const f64 *rhs, size_t n, int op, c
     }
 }
 
+/* simd_eq_mask_u8/_u16/_u32/_u64, src/kernels/bitmask/simd.rs:741-788: bit j = ((data[j] & field_mask) == target);
+ * the SIMD body and the scalar tail compute the same predicate, so one loop restates both. */
+#define DEF_EQ_MASK(T)                                                                          \
+    void orc_simd_eq_mask_##T(const T *data, size_t n, T field_mask, T target, uint8_t *out) {  \
+        memset(out, 0, (n + 7) / 8);                                                            \
+        for (size_t j = 0; j < n; ++j)                                                          \
+            if ((T)(data[j] & field_mask) == target) out[j / 8] |= (uint8_t)(1u << (j % 8));    \
+    }
+DEF_EQ_MASK(u8) DEF_EQ_MASK(u16) DEF_EQ_MASK(u32) DEF_EQ_MASK(u64)
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -424,5 +424,18 @@ def par_apply_float_f64(lhs, rhs, op: int, mask: Optional[Bits], threads: int, o
     return out, (Bits(om, n) if om is not None else None)
 
 
+def simd_eq_mask(data, field_mask, target) -> Bits:
+    """simd_eq_mask_u{8,16,32,64}(data, field_mask, target) -> Bitmask (bitmask/simd.rs:741-788)."""
+    d = np.ascontiguousarray(data)
+    name = {1: "u8", 2: "u16", 4: "u32", 8: "u64"}[d.dtype.itemsize]
+    ut = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[d.dtype.itemsize]
+    ct = {1: C.c_uint8, 2: C.c_uint16, 4: C.c_uint32, 8: C.c_uint64}[d.dtype.itemsize]
+    out = np.zeros((d.size + 7) // 8, dtype=np.uint8)
+    fm = int(np.array([field_mask], dtype=d.dtype).view(ut)[0])
+    tg = int(np.array([target], dtype=d.dtype).view(ut)[0])
+    getattr(lib(), f"orc_simd_eq_mask_{name}")(_p(d), _sz(d.size), ct(fm), ct(tg), _p(out))
+    return Bits(out, int(d.size))
+
+
 def max_threads() -> int:
     return int(lib().orc_max_threads())
