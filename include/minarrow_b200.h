@@ -217,6 +217,15 @@ int mnr_bits_all_eq(mnr_ctx* ctx, const mnr_bits* a, size_t a_offset, const mnr_
 int mnr_bits_in(mnr_ctx* ctx, const mnr_bits* lhs, size_t lhs_offset, const mnr_bits* rhs, size_t rhs_offset,
                 size_t len, int negate, mnr_bits** out);
 
+/* Bitmask::slice_clone (src/structs/bitmask.rs:604-626): bits [offset, offset + len) as a fresh mask from bit 0. */
+int mnr_bits_slice(mnr_ctx* ctx, const mnr_bits* src, size_t offset, size_t len, mnr_bits** out);
+/* Device consolidate: SuperArray::consolidate / Array::concat = append_array over all chunks in row order
+ * (src/traits/consolidate.rs:61-69, src/macros.rs:311-341; the building block of rechunk, super_array.rs:674-787).
+ * Values are appended; validity is gathered at bit granularity; a chunk without a mask counts as all valid and
+ * *out_validity is NULL iff no chunk has a mask.  All chunks must share a dtype (else MNR_ERR_TYPE_MISMATCH).
+ * Re-splitting is zero-copy for values (mnr_buf_slice) and mnr_bits_slice for validity. */
+int mnr_concat(mnr_ctx* ctx, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities, mnr_buf** out,
+               mnr_bits** out_validity);
 /* simd_eq_mask_u8 / _u16 / _u32 / _u64 (src/kernels/bitmask/simd.rs:741-788): typed compare -> bitmask,
  * bit i = ((data[i] & *field_mask) == *target); `field_mask` / `target` point at one host element of data's dtype
  * (any integer dtype: the compare is on the raw lanes). */

@@ -81,6 +81,8 @@ SIGNATURES = {
     "mnr_bits_eq": (c_int, [c_ctx, c_bits, c_sz, c_bits, c_sz, c_sz, c_int, PP]),
     "mnr_bits_all_eq": (c_int, [c_ctx, c_bits, c_sz, c_bits, c_sz, c_sz, C.POINTER(c_int)]),
     "mnr_bits_in": (c_int, [c_ctx, c_bits, c_sz, c_bits, c_sz, c_sz, c_int, PP]),
+    "mnr_bits_slice": (c_int, [c_ctx, c_bits, c_sz, c_sz, PP]),
+    "mnr_concat": (c_int, [c_ctx, c_sz, PP, PP, PP, PP]),
     "mnr_eq_mask": (c_int, [c_ctx, c_buf, c_vp, c_vp, PP]),
     "mnr_reduce_stats": (c_int, [c_ctx, c_buf, c_bits, C.POINTER(Agg)]),
     "mnr_reduce_sum": (c_int, [c_ctx, c_buf, c_bits, C.POINTER(Scalar64), C.POINTER(C.c_uint64)]),

@@ -770,6 +770,53 @@ int mnr_bits_in(mnr_ctx* c, const mnr_bits* lhs, size_t lo, const mnr_bits* rhs,
     return MNR_OK;
 }
 
+int mnr_bits_slice(mnr_ctx* c, const mnr_bits* src, size_t offset, size_t len, mnr_bits** out) {
+    REQUIRE(c && src && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    *out = nullptr;
+    REQUIRE(offset <= src->len && len <= src->len - offset, MNR_ERR_OUT_OF_BOUNDS, "slice [%zu, %zu) out of bounds for %zu bits",
+            offset, offset + len, src->len);
+    int rc = mnr_bits_alloc(c, len, out);
+    if (rc || len == 0) return rc;
+    CU(cudaSetDevice(c->device));
+    CU(launch_bits_op(5, src->ptr, offset, src->len, nullptr, 0, 0, len, (*out)->ptr, c->stream));
+    c->launches++;
+    return MNR_OK;
+}
+
+int mnr_concat(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities, mnr_buf** out,
+               mnr_bits** out_validity) {
+    REQUIRE(c && out && out_validity && (bufs || n == 0), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    *out = nullptr; *out_validity = nullptr;
+    REQUIRE(n >= 1, MNR_ERR_INVALID_ARGUMENTS, "concat needs at least one chunk (the dtype comes from the chunks)");
+    std::vector<ConcatSeg> segs(n);
+    uint64_t total = 0, max_rows = 0;
+    bool any_mask = false;
+    for (size_t i = 0; i < n; ++i) {
+        REQUIRE(bufs[i], MNR_ERR_INVALID_ARGUMENTS, "chunk %zu is NULL", i);
+        REQUIRE(bufs[i]->dtype == bufs[0]->dtype, MNR_ERR_TYPE_MISMATCH, "chunk %zu has dtype %d, chunk 0 has %d", i,
+                (int)bufs[i]->dtype, (int)bufs[0]->dtype);
+        const mnr_bits* v = validities ? validities[i] : nullptr;
+        REQUIRE(!v || v->len >= bufs[i]->len, MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: validity has %zu bits, need %zu", i, v->len, bufs[i]->len);
+        segs[i] = ConcatSeg{bufs[i]->ptr, v ? v->ptr : nullptr, bufs[i]->len, total};
+        total += bufs[i]->len;
+        max_rows = std::max<uint64_t>(max_rows, bufs[i]->len);
+        any_mask |= v != nullptr;
+    }
+    int rc = alloc_outputs(c, bufs[0]->dtype, total, any_mask, out, out_validity);
+    if (rc) return rc;
+    if (total == 0) return MNR_OK;
+    CU(cudaSetDevice(c->device));
+    rc = ensure_ew_segs(c, n * sizeof(ConcatSeg));
+    if (rc) return drop_outputs(rc, out, out_validity);
+    char* dst = static_cast<char*>(c->ew_segs) + (c->ew_flip ? c->ew_segs_bytes / 2 : 0);
+    c->ew_flip ^= 1;
+    CU(cudaMemcpyAsync(dst, segs.data(), n * sizeof(ConcatSeg), cudaMemcpyHostToDevice, c->stream));
+    CU(launch_concat((int)dtype_size(bufs[0]->dtype), reinterpret_cast<const ConcatSeg*>(dst), (uint32_t)n, max_rows, total,
+                     (*out)->ptr, any_mask ? (*out_validity)->ptr : nullptr, c->stream));
+    c->launches += any_mask ? 2 : 1;
+    return MNR_OK;
+}
+
 int mnr_eq_mask(mnr_ctx* c, const mnr_buf* data, const void* field_mask, const void* target, mnr_bits** out) {
     REQUIRE(c && data && field_mask && target && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
     REQUIRE(!is_float_dtype(data->dtype), MNR_ERR_UNSUPPORTED_TYPE, "eq_mask works on integer lanes (u8/u16/u32/u64 and their signed twins)");

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "../../include/minarrow_b200.h"
 
@@ -60,6 +61,15 @@ cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void
 // slack bits of the last byte zero; reads stay inside [0, ceil(x_bits_total/8)).
 cudaError_t launch_bits_op(int op, const uint8_t* a, uint64_t a_bitpos, uint64_t a_total_bits, const uint8_t* b,
                            uint64_t b_bitpos, uint64_t b_total_bits, uint64_t len, uint8_t* out, cudaStream_t s);
+// Device consolidate (concat.cu): chunks in row order -> one contiguous column (+ validity gathered at bit granularity).
+struct ConcatSeg {
+    const void* data;
+    const uint8_t* mask;   // NULL = all valid
+    uint64_t rows;
+    uint64_t row0;         // destination row offset (prefix sum of rows)
+};
+cudaError_t launch_concat(int elem_bytes, const ConcatSeg* segs, uint32_t nseg, uint64_t max_rows, uint64_t total_rows, void* out,
+                          uint8_t* out_mask, cudaStream_t s);
 // Typed compare -> bitmask (compare.cu): bit i = ((data[i] & field_mask) == target), elements of 1/2/4/8 bytes.
 cudaError_t launch_eq_mask(int elem_bytes, const void* data, uint64_t n, uint64_t field_mask, uint64_t target, uint8_t* out,
                            cudaStream_t s);

@@ -238,3 +238,38 @@ def eq_mask(ctx: Context, data: DeviceBuffer, field_mask, target) -> DeviceBitma
     o = C.c_void_p()
     check(ctx.lib.mnr_eq_mask(ctx.h, data.h, fm.ctypes.data_as(C.c_void_p), tg.ctypes.data_as(C.c_void_p), C.byref(o)))
     return DeviceBitmask(ctx, o)
+
+
+def bits_slice(ctx: Context, src: DeviceBitmask, offset: int, length: int) -> DeviceBitmask:
+    """Bitmask::slice_clone (bitmask.rs:604-626) on the device: exact bit offset, result starts at bit 0."""
+    o = C.c_void_p()
+    check(ctx.lib.mnr_bits_slice(ctx.h, src.h, offset, length, C.byref(o)))
+    return DeviceBitmask(ctx, o)
+
+
+def concat(ctx: Context, bufs, validities=None):
+    """consolidate(): all chunks -> one contiguous device column (+ validity iff any chunk has one)."""
+    n = len(bufs)
+    ob, om = C.c_void_p(), C.c_void_p()
+    vals = None if validities is None else _handle_array(list(validities))
+    check(ctx.lib.mnr_concat(ctx.h, n, _handle_array(list(bufs)), vals, C.byref(ob), C.byref(om)))
+    return DeviceBuffer(ctx, ob), (DeviceBitmask(ctx, om) if om.value else None)
+
+
+def rechunk(ctx: Context, bufs, validities, chunk_rows: int):
+    """SuperArray::rechunk(Count(chunk_rows)) on the device (super_array.rs:674-787): chunks of exactly `chunk_rows` rows
+    plus one remainder chunk.  One consolidate (two launches), then value chunks are zero-copy windows of the
+    consolidated buffer and validity chunks are bit-offset slices."""
+    if chunk_rows <= 0:
+        from .core import KernelError
+        raise KernelError("OutOfBounds", "Count chunk size must be greater than 0")
+    total = sum(len(b) for b in bufs)
+    if not bufs or total == 0:
+        return list(bufs), list(validities) if validities is not None else [None] * len(bufs)
+    whole, wmask = concat(ctx, bufs, validities)
+    out_b, out_v = [], []
+    for r0 in range(0, total, chunk_rows):
+        ln = min(chunk_rows, total - r0)
+        out_b.append(whole.slice(r0, ln))
+        out_v.append(None if wmask is None else bits_slice(ctx, wmask, r0, ln))
+    return out_b, out_v
