@@ -120,6 +120,7 @@ class ShardedColumn:
         from . import device_ops as dev
         n = max(1, len(self.chunks))
         parts = torch.zeros(n, 4, dtype=torch.int64, device=torch.device("cuda", self.ctx.device))
+        torch.cuda.current_stream(parts.device).synchronize()   # torch filled it on ITS stream; the context has its own
         if self.chunks:   # all local chunks in one batched call (one launch per dtype/alignment/masked class)
             dev.reduce_stats_batch_async(self.ctx, self.chunks, self.validities, with_minmax, parts.data_ptr())
         self.ctx.synchronize()

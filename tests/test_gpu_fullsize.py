@@ -24,10 +24,15 @@ def env(gpu_ctx):
 
 
 def _wrap_buf(mnr, ctx, t, npdt):
+    # torch fills its tensors on torch's stream; the context launches on its own: order them here
+    import torch
+    torch.cuda.synchronize()
     return mnr.DeviceBuffer.wrap(ctx, npdt, t.data_ptr(), t.numel(), t)
 
 
 def _wrap_bits(mnr, ctx, t, nbits):
+    import torch
+    torch.cuda.synchronize()
     return mnr.DeviceBitmask.wrap(ctx, t.data_ptr(), nbits, t)
 
 
@@ -52,6 +57,7 @@ def test_c2_one_billion_row_i64_sum(env):
     assert (s1 + s0) % 2 ** 64 == 499_999_999_500_000_000
     # full-range values: the sum wraps exactly like the oracle's on a 2^26-row sample, and the two halves add up
     data.random_(-2 ** 63, 2 ** 63 - 1, generator=g)
+    torch.cuda.synchronize()
     sa, _ = dev.reduce_sum(ctx, B)
     s1, _ = dev.reduce_sum(ctx, B, V)
     s0, _ = dev.reduce_sum(ctx, B, NV)
@@ -74,6 +80,7 @@ def test_c3_f64_256Mi_rows_two_masks_bit_exact(env):
     x[idx[::3]] = float("nan")
     x[idx[1::3]] = float("inf")
     y[idx[2::7]] = -0.0
+    torch.cuda.synchronize()
     mx = torch.randint(0, 256, (n // 8,), dtype=torch.uint8, device="cuda", generator=g) | \
         torch.randint(0, 256, (n // 8,), dtype=torch.uint8, device="cuda", generator=g)
     my = torch.randint(0, 256, (n // 8,), dtype=torch.uint8, device="cuda", generator=g) | \

@@ -89,6 +89,7 @@ def main():
         assert all(int(x) == int(t) for x in g), "fused exchange: ranks disagree"
         # asynchronous form, 200 epochs back to back without host synchronisation
         outd = torch.zeros(4, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
         ctx.synchronize()
         for _ in range(200):
             fx.reduce_stats_async(B, V, False, outd.data_ptr())
