@@ -21,4 +21,10 @@ echo "== ncu full: ew f64 masked add"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ew_binary -s 3 -c 2 -f -o $OUT/prof_ew \
     python bench.py --steps 3 --warmup 3 --rows 67108864 --no-e2e --no-cpu --no-supertable > $OUT/ncu_ew.log 2>&1
 tail -2 $OUT/ncu_ew.log
+
+echo "== ncu full: batched kernels (C5 SuperTable)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:batch_kernel -s 8 -c 4 -f -o $OUT/prof_batch \
+    python bench.py --steps 3 --warmup 3 --rows 67108864 --no-e2e --no-cpu > $OUT/ncu_batch.log 2>&1
+tail -2 $OUT/ncu_batch.log
+
 ls -la $OUT
