@@ -1,0 +1,141 @@
+//! Safe layer over libminarrow_b200.so: a device-resident buffer type alongside `Vec64`, a device validity-bitmask
+//! type, Arrow-layout-preserving upload/download, and the reference's leaf functions with identical signatures.
+//!
+//! NOT COMPILED IN THIS REPO (no Rust toolchain in the build image) — see INTEGRATION.md.  Every call maps 1:1 onto an
+//! entry point of include/minarrow_b200.h whose behaviour is pinned by the GPU parity tests.
+pub mod ffi;
+
+use core::ffi::{c_int, c_void};
+use core::marker::PhantomData;
+use std::ffi::CStr;
+
+use minarrow::enums::error::KernelError;
+use minarrow::enums::operators::ArithmeticOperator;
+use minarrow::{Bitmask, FloatArray, IntegerArray, Vec64};
+
+/// Element types the device path carries (IntegerArray<T> / FloatArray<T>).
+pub trait B200Dtype: Copy + 'static { const CODE: c_int; }
+impl B200Dtype for i32 { const CODE: c_int = ffi::MNR_I32; }
+impl B200Dtype for u32 { const CODE: c_int = ffi::MNR_U32; }
+impl B200Dtype for i64 { const CODE: c_int = ffi::MNR_I64; }
+impl B200Dtype for u64 { const CODE: c_int = ffi::MNR_U64; }
+impl B200Dtype for f32 { const CODE: c_int = ffi::MNR_F32; }
+impl B200Dtype for f64 { const CODE: c_int = ffi::MNR_F64; }
+
+fn last_error() -> String {
+    unsafe { CStr::from_ptr(ffi::mnr_last_error()) }.to_string_lossy().into_owned()
+}
+
+/// Status codes -1..-10 are the KernelError variants in declaration order (src/enums/error.rs:157-187).
+fn check(rc: c_int) -> Result<(), KernelError> {
+    match rc {
+        0 => Ok(()),
+        -2 => Err(KernelError::LengthMismatch(last_error())),
+        -5 => Err(KernelError::UnsupportedType(last_error())),
+        -9 => Err(KernelError::OutOfBounds(last_error())),
+        -10 => panic!("{}", last_error()),     // the dense integer kernels' divide-by-zero panic (std.rs:54-55)
+        _ => Err(KernelError::InvalidArguments(last_error())),
+    }
+}
+
+/// One device + stream.  One context per host thread at a time (header "Conventions").
+pub struct Context { h: *mut ffi::mnr_ctx }
+unsafe impl Send for Context {}
+impl Context {
+    pub fn new(device: i32) -> Result<Self, KernelError> {
+        let mut h = core::ptr::null_mut();
+        check(unsafe { ffi::mnr_ctx_create(device as c_int, &mut h) })?;
+        Ok(Self { h })
+    }
+}
+impl Drop for Context { fn drop(&mut self) { unsafe { ffi::mnr_ctx_destroy(self.h) } } }
+
+/// Device-resident values buffer: the `Vec64<T>` / `Buffer<T>` analogue in HBM (src/structs/buffer.rs:126-139).
+pub struct DeviceBuffer<'c, T: B200Dtype> { ctx: &'c Context, h: *mut ffi::mnr_buf, _t: PhantomData<T> }
+/// Device-resident bit-packed mask: the `Bitmask` analogue (src/structs/bitmask.rs:66-71).
+pub struct DeviceBitmask<'c> { ctx: &'c Context, h: *mut ffi::mnr_bits }
+
+impl<'c, T: B200Dtype> DeviceBuffer<'c, T> {
+    /// Arrow-layout-preserving upload: the bytes of `data` one for one.
+    pub fn upload(ctx: &'c Context, data: &[T]) -> Result<Self, KernelError> {
+        let mut h = core::ptr::null_mut();
+        check(unsafe { ffi::mnr_buf_upload(ctx.h, T::CODE, data.as_ptr() as *const c_void, data.len(), &mut h) })?;
+        Ok(Self { ctx, h, _t: PhantomData })
+    }
+    pub fn len(&self) -> usize { unsafe { ffi::mnr_buf_len(self.h) } }
+    /// Download into a 64-byte aligned `Vec64<T>` (taken by `Buffer::from` without a copy, buffer.rs:168-219).
+    pub fn download(&self) -> Result<Vec64<T>, KernelError> {
+        let n = self.len();
+        let mut out = Vec64::<T>::with_capacity(n);
+        unsafe { out.set_len(n) };
+        check(unsafe { ffi::mnr_buf_download(self.ctx.h, self.h, out.as_mut_ptr() as *mut c_void) })?;
+        Ok(out)
+    }
+    /// Fused null-aware `self op rhs` with both validity masks merged inside the kernel (one HBM pass).
+    pub fn binary(&self, op: ArithmeticOperator, rhs: &Self, lhs_mask: Option<&DeviceBitmask<'c>>,
+                  rhs_mask: Option<&DeviceBitmask<'c>>, or_union: bool)
+                  -> Result<(Self, Option<DeviceBitmask<'c>>), KernelError> {
+        let (mut ob, mut om) = (core::ptr::null_mut(), core::ptr::null_mut());
+        check(unsafe {
+            ffi::mnr_ew_binary(self.ctx.h, op as c_int, self.h, rhs.h,
+                               lhs_mask.map_or(core::ptr::null(), |m| m.h as *const _),
+                               rhs_mask.map_or(core::ptr::null(), |m| m.h as *const _),
+                               if or_union { ffi::MNR_MASK_OR } else { ffi::MNR_MASK_AND }, &mut ob, &mut om)
+        })?;
+        let mask = if om.is_null() { None } else { Some(DeviceBitmask { ctx: self.ctx, h: om }) };
+        Ok((Self { ctx: self.ctx, h: ob, _t: PhantomData }, mask))
+    }
+    /// Null-aware {sum, min, max, count} in one pass.
+    pub fn stats(&self, validity: Option<&DeviceBitmask<'c>>) -> Result<ffi::mnr_agg, KernelError> {
+        let mut agg = core::mem::MaybeUninit::<ffi::mnr_agg>::uninit();
+        check(unsafe { ffi::mnr_reduce_stats(self.ctx.h, self.h, validity.map_or(core::ptr::null(), |m| m.h as *const _), agg.as_mut_ptr()) })?;
+        Ok(unsafe { agg.assume_init() })
+    }
+}
+impl<'c, T: B200Dtype> Drop for DeviceBuffer<'c, T> { fn drop(&mut self) { unsafe { ffi::mnr_buf_free(self.h) } } }
+
+impl<'c> DeviceBitmask<'c> {
+    pub fn upload(ctx: &'c Context, mask: &Bitmask) -> Result<Self, KernelError> {
+        let mut h = core::ptr::null_mut();
+        check(unsafe { ffi::mnr_bits_upload(ctx.h, mask.bits.as_ptr(), mask.len(), &mut h) })?;
+        Ok(Self { ctx, h })
+    }
+    pub fn len(&self) -> usize { unsafe { ffi::mnr_bits_len(self.h) } }
+    pub fn count_ones(&self) -> Result<u64, KernelError> {
+        let mut ones = 0u64;
+        check(unsafe { ffi::mnr_bits_popcount(self.ctx.h, self.h, 0, self.len(), &mut ones) })?;
+        Ok(ones)
+    }
+}
+impl<'c> Drop for DeviceBitmask<'c> { fn drop(&mut self) { unsafe { ffi::mnr_bits_free(self.h) } } }
+
+/// Drop-in for `minarrow::kernels::arithmetic::dispatch::apply_int_i64` (dispatch.rs:74-131): same signature, same
+/// result (`Some(mask)` iff a mask was passed; masked zero divisors become nulls; dense zero divisors panic).
+pub fn apply_int_i64(ctx: &Context, lhs: &[i64], rhs: &[i64], op: ArithmeticOperator, mask: Option<&Bitmask>)
+                     -> Result<IntegerArray<i64>, KernelError> {
+    let len = lhs.len();
+    let mut out = Vec64::<i64>::with_capacity(len);
+    unsafe { out.set_len(len) };
+    let mut out_mask = mask.map(|_| Bitmask::new_set_all(len, false));
+    check(unsafe {
+        ffi::mnr_apply_int_i64(ctx.h, lhs.as_ptr(), len, rhs.as_ptr(), rhs.len(), op as c_int,
+                               mask.map_or(core::ptr::null(), |m| m.bits.as_ptr()), out.as_mut_ptr(),
+                               out_mask.as_mut().map_or(core::ptr::null_mut(), |m| m.bits.as_mut_ptr()))
+    })?;
+    Ok(IntegerArray { data: out.into(), null_mask: out_mask })
+}
+
+/// Drop-in for `apply_float_f64` (dispatch.rs:147-204).
+pub fn apply_float_f64(ctx: &Context, lhs: &[f64], rhs: &[f64], op: ArithmeticOperator, mask: Option<&Bitmask>)
+                       -> Result<FloatArray<f64>, KernelError> {
+    let len = lhs.len();
+    let mut out = Vec64::<f64>::with_capacity(len);
+    unsafe { out.set_len(len) };
+    let mut out_mask = mask.map(|_| Bitmask::new_set_all(len, false));
+    check(unsafe {
+        ffi::mnr_apply_float_f64(ctx.h, lhs.as_ptr(), len, rhs.as_ptr(), rhs.len(), op as c_int,
+                                 mask.map_or(core::ptr::null(), |m| m.bits.as_ptr()), out.as_mut_ptr(),
+                                 out_mask.as_mut().map_or(core::ptr::null_mut(), |m| m.bits.as_mut_ptr()))
+    })?;
+    Ok(FloatArray { data: out.into(), null_mask: out_mask })
+}
