@@ -475,9 +475,21 @@ def run_b200(args):
 
     fused = world > 1 and args.exchange == "fused"
     fx = None
+    fused_note = None
     if fused:
+        # The mailboxes need CUDA IPC between the ranks' processes.  Every rank must take the same path, so the outcome
+        # is agreed with one all-reduce; if any rank cannot map its peers the run says so and uses the NCCL exchange.
         from minarrow_b200.sharded import FusedExchange
-        fx = FusedExchange(ctx)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            fx = FusedExchange(ctx)
+        except Exception as e:  # noqa: BLE001
+            fused_note = repr(e)[:200]
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            fused, fx = False, None
+            fused_note = fused_note or "a peer rank could not map the mailboxes"
     total = torch.zeros(4, dtype=torch.int64, device=dev)             # fused path: the combined aggregate on every rank
 
     def reduce_step():
@@ -640,7 +652,8 @@ def run_b200(args):
             "config": {"workload": "configs[1]: 1B-row IntegerArray<i64> null-aware sum/avg, 10% nulls, "
                                    "SuperArray shards over GPUs + NCCL all-gather of 32-byte partials",
                        "exchange": ("fused kernel: reduce + P2P mailbox all-gather over NVLink + rank-order combine" if fused
-                                    else "NCCL all-gather of 32-byte partials" if world > 1 else "none (1 GPU)"),
+                                    else ("NCCL all-gather of 32-byte partials" + (f" (fused exchange unavailable: {fused_note})" if fused_note else ""))
+                                    if world > 1 else "none (1 GPU)"),
                        "rows_per_gpu": rows, "total_rows": total_rows, "bytes_per_row": BYTES_PER_ROW,
                        "l2": "inputs (8.1 GB per GPU) far larger than the 126 MB L2; no flush needed",
                        "values": "i64 uniform in [-2^31, 2^31), seeded per rank", "p_valid": P_VALID},

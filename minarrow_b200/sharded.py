@@ -166,20 +166,37 @@ class FusedExchange:
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         else:
             self.world, self.rank = 1, 0
-        h = C.c_void_p()
-        check(ctx.lib.mnr_xchg_create(ctx.h, self.world, self.rank, C.byref(h)))
-        self.h = h
+        self.h = None
+        err = None
+        mine = (C.c_uint8 * 64)()
+        try:
+            h = C.c_void_p()
+            check(ctx.lib.mnr_xchg_create(ctx.h, self.world, self.rank, C.byref(h)))
+            self.h = h
+            if self.world > 1:
+                check(ctx.lib.mnr_xchg_local_handle(self.h, mine))
+        except KernelError as e:
+            err = e
         if self.world > 1:
-            mine = (C.c_uint8 * 64)()
-            check(ctx.lib.mnr_xchg_local_handle(self.h, mine))
+            # Every rank walks the same collectives whether or not its own setup worked, then all agree on the outcome.
             dev_ = torch.device("cuda", ctx.device)
             local = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev_)
             allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev_)
             dist.all_gather_into_tensor(allh, local, group=group)
-            raw = bytes(allh.cpu().numpy().tobytes())
-            buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
-            check(ctx.lib.mnr_xchg_connect(self.h, buf))
-            dist.barrier(group=group)      # every rank has mapped every mailbox before the first kernel uses them
+            if err is None:
+                try:
+                    raw = bytes(allh.cpu().numpy().tobytes())
+                    buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+                    check(ctx.lib.mnr_xchg_connect(self.h, buf))
+                except KernelError as e:
+                    err = e
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev_)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also the barrier: all mailboxes are mapped
+            if int(ok) == 0:
+                self.close()
+                raise err or KernelError("Cuda", "a peer rank could not set up its exchange mailbox (CUDA IPC)")
+        elif err is not None:
+            raise err
 
     def reduce_stats_async(self, buf, validity, with_minmax: bool, out_device_ptr: int) -> None:
         """Global aggregate of the sharded column -> 32 bytes at `out_device_ptr` on this rank (no sync, no NCCL)."""
