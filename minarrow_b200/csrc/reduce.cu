@@ -10,7 +10,7 @@ namespace mnr {
 // Grid = min(tiles, 148 SMs x resident blocks): a function of (len, dtype, alignment tier) only — never an
 // occupancy query — so a float sum is bit-reproducible run to run and device to device.
 constexpr int kRBlock = 256;
-template <typename T> struct RMinB { static constexpr int value = sizeof(T) >= 4 ? 4 : 2; };   // narrow types carry 8-32 slots
+template <typename T> struct RMinB { static constexpr int value = 4; };
 template <typename VecT, bool MINMAX> struct RU { static constexpr int value = (sizeof(VecT) == 32) ? 2 : 4; };
 
 int reduce_tier(const void* data, bool minmax);
