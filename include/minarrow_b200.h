@@ -341,6 +341,26 @@ int mnr_arrow_export(mnr_ctx* ctx, const mnr_buf* values, const mnr_bits* validi
 int mnr_arrow_export_bool(mnr_ctx* ctx, const mnr_bits* data_bits, const mnr_bits* validity,
                           struct ArrowArray* out_array, struct ArrowSchema* out_schema);
 
+/* Arrow C Stream Interface (src/ffi/arrow_c_ffi.rs:153-168 ArrowArrayStream; the PyCapsule route a chunked producer uses,
+ * :160-168) -> SuperArray chunks on this device.  The stream is drained to its end; chunk i is uploaded (exactly like
+ * mnr_arrow_import, offsets honoured) iff chunk_lo <= i < chunk_hi — the caller passes the contiguous block of chunks
+ * that `chunk i -> rank floor(i*G/n)` assigns to this rank (minarrow_b200/sharded.py), the other chunks are released
+ * unread.  values[k] / validity[k] (k < *n_imported <= capacity) receive the uploaded chunks in stream order;
+ * validity[k] is NULL for a chunk without nulls.  *n_seen = chunks in the stream.  Every consumed ArrowArray is
+ * released here; the stream itself stays with the caller (release after the call).  Numeric formats only. */
+#ifndef ARROW_C_STREAM_INTERFACE
+#define ARROW_C_STREAM_INTERFACE
+struct ArrowArrayStream {
+    int (*get_schema)(struct ArrowArrayStream*, struct ArrowSchema* out);
+    int (*get_next)(struct ArrowArrayStream*, struct ArrowArray* out);
+    const char* (*get_last_error)(struct ArrowArrayStream*);
+    void (*release)(struct ArrowArrayStream*);
+    void* private_data;
+};
+#endif
+int mnr_arrow_stream_import(mnr_ctx* ctx, struct ArrowArrayStream* stream, size_t chunk_lo, size_t chunk_hi, size_t capacity,
+                            mnr_buf** values, mnr_bits** validity, size_t* n_imported, size_t* n_seen);
+
 #ifdef __cplusplus
 }
 #endif

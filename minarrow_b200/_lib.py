@@ -110,6 +110,7 @@ SIGNATURES = {
     "mnr_arrow_import": (c_int, [c_ctx, c_vp, c_vp, PP, PP, PP]),
     "mnr_arrow_export": (c_int, [c_ctx, c_buf, c_bits, c_vp, c_vp]),
     "mnr_arrow_export_bool": (c_int, [c_ctx, c_bits, c_bits, c_vp, c_vp]),
+    "mnr_arrow_stream_import": (c_int, [c_ctx, c_vp, c_sz, c_sz, c_sz, c_vp, c_vp, C.POINTER(c_sz), C.POINTER(c_sz)]),
     "mnr_host_register": (c_int, [c_vp, c_sz]),
     "mnr_host_unregister": (c_int, [c_vp]),
     "mnr_host_alloc": (c_int, [c_sz, PP]),

@@ -57,3 +57,32 @@ def to_arrow_bool(ctx: Context, data_bits: DeviceBitmask, validity: Optional[Dev
     a, s = ArrowArray(), ArrowSchema()
     check(ctx.lib.mnr_arrow_export_bool(ctx.h, data_bits.h, None if validity is None else validity.h, C.byref(a), C.byref(s)))
     return pa.Array._import_from_c(C.addressof(a), C.addressof(s))
+
+
+def shard_range(n_chunks: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) of the chunks `chunk i -> rank floor(i*world/n_chunks)` gives to `rank` (sharded.py uses the same map)."""
+    lo = -(-rank * n_chunks // world)
+    hi = -(-(rank + 1) * n_chunks // world)
+    return lo, hi
+
+
+def from_arrow_stream(ctx: Context, chunked, rank: int = 0, world: int = 1):
+    """Drain an Arrow C stream (anything with `__arrow_c_stream__`: pyarrow.ChunkedArray, a polars Series, the reference's
+    own PyCapsule export, src/ffi/arrow_c_ffi.rs:153-168) and upload this rank's contiguous block of chunks.
+    Returns ([DeviceBuffer], [DeviceBitmask | None], chunks_in_stream)."""
+    n = chunked.num_chunks if hasattr(chunked, "num_chunks") else None
+    if n is None:
+        raise TypeError("from_arrow_stream needs the chunk count (num_chunks) to place the shard boundaries")
+    lo, hi = shard_range(n, rank, world)
+    cap = max(hi - lo, 0)
+    capsule = chunked.__arrow_c_stream__()
+    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    stream = C.pythonapi.PyCapsule_GetPointer(capsule, b"arrow_array_stream")
+    vals, masks = (C.c_void_p * max(cap, 1))(), (C.c_void_p * max(cap, 1))()
+    got, seen = C.c_size_t(), C.c_size_t()
+    check(ctx.lib.mnr_arrow_stream_import(ctx.h, C.c_void_p(stream), lo, hi, cap, vals, masks, C.byref(got), C.byref(seen)))
+    del capsule   # the capsule's destructor releases the (now drained) stream
+    bufs = [DeviceBuffer(ctx, C.c_void_p(vals[k])) for k in range(got.value)]
+    vms = [DeviceBitmask(ctx, C.c_void_p(masks[k])) if masks[k] else None for k in range(got.value)]
+    return bufs, vms, int(seen.value)

@@ -284,10 +284,35 @@ static uint64_t scalar_to_bits(mnr_dtype dt, const void* scalar) {
     return b;
 }
 
+// Integer Div / Rem / FloorDiv whose divisor is the broadcast scalar (rhs == NULL) and non-zero: hand the kernel the
+// scalar's multiplicative inverse (divmagic.h) so no row executes a divide.  A zero scalar keeps the generic kernel,
+// which nulls every row (masked) or raises the divide-by-zero flag (dense).
+static void prepare_scalar_division(EwArgs& a) {
+    a.sdiv = 0;
+    if (is_float_dtype(a.dtype) || a.rhs != nullptr || a.lhs == nullptr) return;
+    if (a.op != MNR_DIV && a.op != MNR_REM && a.op != MNR_FLOORDIV) return;
+    const size_t sz = dtype_size(a.dtype);
+    const bool is_signed = a.dtype == MNR_I8 || a.dtype == MNR_I16 || a.dtype == MNR_I32 || a.dtype == MNR_I64;
+    uint64_t u = a.scalar_bits;
+    if (sz < 8) u &= (1ull << (8 * sz)) - 1ull;
+    if (u == 0) return;
+    const int nbits = sz == 8 ? 64 : 32;   // 8/16-bit columns are widened to 32 bits in the kernel
+    DivMagic k;
+    if (is_signed) {
+        const int64_t d = sz == 8 ? (int64_t)u : sz == 4 ? (int64_t)(int32_t)u : sz == 2 ? (int64_t)(int16_t)u : (int64_t)(int8_t)u;
+        k = div_magic_signed(d, nbits);
+    } else {
+        k = div_magic_unsigned(u, nbits);
+    }
+    a.sdiv = 1;
+    a.magic_m = k.m; a.magic_s1 = k.s1; a.magic_s2 = k.s2;
+}
+
 // Launch + (dense integer Div/Rem/FloorDiv only) the reference's divide-by-zero panic as an error code.
 static int run_ew(mnr_ctx* c, EwArgs& a, cudaStream_t s, bool promote, mnr_dtype lt, mnr_dtype rt) {
     if (a.n == 0) return MNR_OK;
-    const bool dense_int_div = !a.lmask && !a.rmask && !is_float_dtype(a.dtype) &&
+    if (!promote) prepare_scalar_division(a);
+    const bool dense_int_div = !a.lmask && !a.rmask && !is_float_dtype(a.dtype) && !a.sdiv &&
                                (a.op == MNR_DIV || a.op == MNR_REM || a.op == MNR_FLOORDIV);
     a.div0_flag = c->ticket[0] + 8;
     if (dense_int_div) CU(cudaMemsetAsync(a.div0_flag, 0, 4, s));
@@ -459,29 +484,31 @@ static int run_ew_batch(mnr_ctx* c, std::vector<EwArgs>& items) {
     bool any_dense_int_div = false;
     for (auto& a : items) {
         a.div0_flag = flag;
-        if (!a.lmask && !a.rmask && !is_float_dtype(a.dtype) && (a.op == MNR_DIV || a.op == MNR_REM || a.op == MNR_FLOORDIV))
+        prepare_scalar_division(a);
+        if (!a.lmask && !a.rmask && !is_float_dtype(a.dtype) && !a.sdiv && (a.op == MNR_DIV || a.op == MNR_REM || a.op == MNR_FLOORDIV))
             any_dense_int_div = true;
     }
     if (any_dense_int_div) CU(cudaMemsetAsync(flag, 0, 4, c->stream));
-    struct Key { int dtype, tier, masked; };
+    struct Key { int dtype, tier, masked, sdiv; };
     std::vector<Key> keys;
     std::vector<std::vector<EwDev>> groups;
     std::vector<uint64_t> max_n;
     for (const auto& a : items) {
         if (a.n == 0) continue;
-        const int tier = ew_batch_tier(a.dtype, a.op, a.lhs, a.rhs, a.out);
+        const int tier = ew_batch_tier(a.dtype, a.op, a.sdiv != 0, a.lhs, a.rhs, a.out);
         if (tier == 0) {
             CU(launch_ew_binary(a, c->stream));
             c->launches++;
             continue;
         }
-        const Key k{(int)a.dtype, tier, (a.lmask || a.rmask) ? 1 : 0};
+        const Key k{(int)a.dtype, tier, (a.lmask || a.rmask) ? 1 : 0, a.sdiv};
         size_t g = 0;
-        for (; g < keys.size(); ++g) if (keys[g].dtype == k.dtype && keys[g].tier == k.tier && keys[g].masked == k.masked) break;
+        for (; g < keys.size(); ++g) if (keys[g].dtype == k.dtype && keys[g].tier == k.tier && keys[g].masked == k.masked && keys[g].sdiv == k.sdiv) break;
         if (g == keys.size()) { keys.push_back(k); groups.emplace_back(); max_n.push_back(0); }
         EwDev d;
         d.lhs = a.lhs; d.rhs = a.rhs; d.scalar_bits = a.scalar_bits; d.lmask = a.lmask; d.rmask = a.rmask; d.mask_or = a.mask_or;
         d.out = a.out; d.out_mask = a.out_mask; d.n = a.n; d.div0_flag = a.div0_flag; d.op = a.op;
+        d.sdiv = a.sdiv; d.magic.m = a.magic_m; d.magic.s1 = a.magic_s1; d.magic.s2 = a.magic_s2;
         groups[g].push_back(d);
         max_n[g] = std::max<uint64_t>(max_n[g], a.n);
     }
@@ -493,7 +520,7 @@ static int run_ew_batch(mnr_ctx* c, std::vector<EwArgs>& items) {
             char* dst = static_cast<char*>(c->ew_segs) + (c->ew_flip ? c->ew_segs_bytes / 2 : 0);
             c->ew_flip ^= 1;
             CU(cudaMemcpyAsync(dst, groups[g].data() + off, cnt * sizeof(EwDev), cudaMemcpyHostToDevice, c->stream));
-            CU(launch_ew_batch((mnr_dtype)keys[g].dtype, items[0].op, keys[g].tier, keys[g].masked != 0,
+            CU(launch_ew_batch((mnr_dtype)keys[g].dtype, items[0].op, keys[g].tier, keys[g].masked != 0, keys[g].sdiv != 0,
                                reinterpret_cast<const EwDev*>(dst), (uint32_t)cnt, max_n[g], c->stream));
             c->launches++;
         }
@@ -914,7 +941,7 @@ int mnr_reduce_stats_batch_async(mnr_ctx* c, size_t n, const mnr_buf* const* buf
     }
     CU(cudaSetDevice(c->device));
     // Group the segments by kernel instantiation; order inside a group is the caller's order.
-    struct Key { int dtype, tier, masked; };
+    struct Key { int dtype, tier, masked, sdiv; };
     std::vector<Key> keys;
     std::vector<std::vector<ReduceSeg>> groups;
     for (size_t i = 0; i < n; ++i) {
@@ -922,7 +949,7 @@ int mnr_reduce_stats_batch_async(mnr_ctx* c, size_t n, const mnr_buf* const* buf
         const mnr_bits* v = validities ? validities[i] : nullptr;
         const Key k{(int)b->dtype, reduce_tier(b->ptr, minmax), v ? 1 : 0};
         size_t g = 0;
-        for (; g < keys.size(); ++g) if (keys[g].dtype == k.dtype && keys[g].tier == k.tier && keys[g].masked == k.masked) break;
+        for (; g < keys.size(); ++g) if (keys[g].dtype == k.dtype && keys[g].tier == k.tier && keys[g].masked == k.masked && keys[g].sdiv == k.sdiv) break;
         if (g == keys.size()) { keys.push_back(k); groups.emplace_back(); }
         ReduceSeg s;
         s.data = b->ptr; s.mask = v ? v->ptr : nullptr; s.n = b->len;

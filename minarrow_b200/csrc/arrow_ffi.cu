@@ -172,6 +172,50 @@ int mnr_arrow_export(mnr_ctx* c, const mnr_buf* values, const mnr_bits* validity
     return export_common(c, fmt, values->len, values->ptr, values->len * dtype_size(values->dtype), validity, out_array, out_schema);
 }
 
+int mnr_arrow_stream_import(mnr_ctx* c, struct ArrowArrayStream* st, size_t chunk_lo, size_t chunk_hi, size_t capacity,
+                            mnr_buf** values, mnr_bits** validity, size_t* n_imported, size_t* n_seen) {
+    if (!c || !st || !n_imported) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow stream import: NULL argument");
+    if (!st->get_schema || !st->get_next) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow stream import: released or empty stream");
+    if (capacity && (!values || !validity)) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow stream import: NULL output arrays");
+    *n_imported = 0;
+    if (n_seen) *n_seen = 0;
+    struct ArrowSchema schema;
+    memset(&schema, 0, sizeof schema);
+    if (st->get_schema(st, &schema) != 0) {
+        const char* e = st->get_last_error ? st->get_last_error(st) : nullptr;
+        AFAIL(MNR_ERR_INVALID_ARGUMENTS, e ? e : "arrow stream import: get_schema failed");
+    }
+    int rc = MNR_OK;
+    size_t seen = 0, got = 0;
+    for (;;) {
+        struct ArrowArray arr;
+        memset(&arr, 0, sizeof arr);
+        if (st->get_next(st, &arr) != 0) {
+            const char* e = st->get_last_error ? st->get_last_error(st) : nullptr;
+            rc = mnr::fail_public(MNR_ERR_INVALID_ARGUMENTS, e ? e : "arrow stream import: get_next failed");
+            break;
+        }
+        if (!arr.release) break;   // end of stream
+        if (rc == MNR_OK && seen >= chunk_lo && seen < chunk_hi) {
+            if (got >= capacity) rc = mnr::fail_public(MNR_ERR_INVALID_ARGUMENTS, "arrow stream import: more chunks in range than capacity");
+            else {
+                rc = mnr_arrow_import(c, &arr, &schema, &values[got], nullptr, &validity[got]);
+                if (rc == MNR_OK) ++got;
+            }
+        }
+        arr.release(&arr);
+        ++seen;   // keep draining after an error so the producer is left in a defined state
+    }
+    if (schema.release) schema.release(&schema);
+    if (rc != MNR_OK) {
+        for (size_t k = 0; k < got; ++k) { mnr_buf_free(values[k]); mnr_bits_free(validity[k]); values[k] = nullptr; validity[k] = nullptr; }
+        return rc;
+    }
+    *n_imported = got;
+    if (n_seen) *n_seen = seen;
+    return MNR_OK;
+}
+
 int mnr_arrow_export_bool(mnr_ctx* c, const mnr_bits* data_bits, const mnr_bits* validity, struct ArrowArray* out_array,
                           struct ArrowSchema* out_schema) {
     if (!c || !data_bits || !out_array) AFAIL(MNR_ERR_INVALID_ARGUMENTS, "arrow export: NULL argument");

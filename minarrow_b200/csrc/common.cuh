@@ -92,11 +92,20 @@ __device__ __forceinline__ uint32_t load_valid_bits(const uint8_t* __restrict__ 
         return (b >> (uint32_t)(row0 & 7)) & ((1u << NBITS) - 1u);
     } else if constexpr (NBITS == 16) {
         const uint8_t* p = mask + (row0 >> 3);
+        if ((reinterpret_cast<uintptr_t>(p) & 1u) == 0) return ldg_u16(p);   // warp-uniform: row0 is a multiple of 16
         return ldg_u8(p) | (ldg_u8(p + 1) << 8);
     } else {
         const uint8_t* p = mask + (row0 >> 3);
+        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) return ldg_u32(p);
         return ldg_u8(p) | (ldg_u8(p + 1) << 8) | (ldg_u8(p + 2) << 16) | (ldg_u8(p + 3) << 24);
     }
+}
+
+// The low 4 (1-byte elements) or 2 (2-byte elements) validity bits of `bits` -> a 32-bit word with 0xFF / 0xFFFF in
+// the lanes of valid elements (SIMD-in-register paths for 8/16-bit columns).  Higher bits of `bits` are ignored.
+template <int ESZ> __device__ __forceinline__ uint32_t expand_valid_word(uint32_t bits) {
+    if constexpr (ESZ == 1) return (((bits & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
+    else return (((bits & 3u) * 0x00008001u) & 0x00010001u) * 0xFFFFu;
 }
 
 __device__ __forceinline__ bool row_valid(const uint8_t* __restrict__ mask, uint64_t row) {

@@ -21,11 +21,13 @@ struct CfgCheap { static constexpr int BLOCK = 128, U = 4, MINB = 1; static cons
 struct CfgHeavy { static constexpr int BLOCK = 256, U = 2, MINB = 4; static constexpr bool RESIDENT = true; using Wide = V16; };
 template <int CLS> struct CfgOf { using type = CfgHeavy; };
 template <> struct CfgOf<CLS_CHEAP> { using type = CfgCheap; };
+template <> struct CfgOf<CLS_SDIV> { using type = CfgCheap; };   // a multiply-high per row: memory-bound like add
 
 static EwDev to_dev(const EwArgs& a) {
     EwDev d;
     d.lhs = a.lhs; d.rhs = a.rhs; d.scalar_bits = a.scalar_bits; d.lmask = a.lmask; d.rmask = a.rmask;
     d.mask_or = a.mask_or; d.out = a.out; d.out_mask = a.out_mask; d.n = a.n; d.div0_flag = a.div0_flag; d.op = a.op;
+    d.sdiv = a.sdiv; d.magic.m = a.magic_m; d.magic.s1 = a.magic_s1; d.magic.s2 = a.magic_s2;
     return d;
 }
 
@@ -71,7 +73,10 @@ static cudaError_t go_batch_tier(int tier, bool masked, const EwDev* segs, uint3
 }
 
 template <typename T>
-static cudaError_t go_batch_t(int op, int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
+static cudaError_t go_batch_t(int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
+    if constexpr (!Traits<T>::is_float) {
+        if (sdiv) return go_batch_tier<T, CLS_SDIV>(tier, masked, segs, nseg, max_n, s);
+    }
     switch (op_class(Traits<T>::is_float, op)) {
         case CLS_CHEAP: return go_batch_tier<T, CLS_CHEAP>(tier, masked, segs, nseg, max_n, s);
         case CLS_DIV: return go_batch_tier<T, CLS_DIV>(tier, masked, segs, nseg, max_n, s);
@@ -99,6 +104,9 @@ static cudaError_t go_align(const EwArgs& a, cudaStream_t s) {
 
 template <typename T>
 static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
+    if constexpr (!Traits<T>::is_float) {
+        if (a.sdiv) return go_align<T, T, T, CLS_SDIV>(a, s);
+    }
     switch (op_class(Traits<T>::is_float, a.op)) {
         case CLS_CHEAP: return go_align<T, T, T, CLS_CHEAP>(a, s);
         case CLS_DIV: return go_align<T, T, T, CLS_DIV>(a, s);
@@ -112,9 +120,9 @@ static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
 
 #define MNR_EW_ENTRY(NAME, T)                                                                                         \
     cudaError_t NAME(const EwArgs& a, cudaStream_t s) { return go_t<T>(a, s); }                                       \
-    cudaError_t NAME##_batch(int op, int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n,         \
-                             cudaStream_t s) {                                                                        \
-        return go_batch_t<T>(op, tier, masked, segs, nseg, max_n, s);                                                 \
+    cudaError_t NAME##_batch(int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg,              \
+                             uint64_t max_n, cudaStream_t s) {                                                        \
+        return go_batch_t<T>(op, tier, masked, sdiv, segs, nseg, max_n, s);                                           \
     }
 
 #if MNR_EW_DTYPE == 6
@@ -141,34 +149,34 @@ MNR_EW_ENTRY(launch_ew_f64, double)
 
 #define MNR_EW_DECL(NAME)                                 \
     cudaError_t NAME(const EwArgs&, cudaStream_t);         \
-    cudaError_t NAME##_batch(int, int, bool, const EwDev*, uint32_t, uint64_t, cudaStream_t);
+    cudaError_t NAME##_batch(int, int, bool, bool, const EwDev*, uint32_t, uint64_t, cudaStream_t);
 MNR_EW_DECL(launch_ew_i8) MNR_EW_DECL(launch_ew_u8) MNR_EW_DECL(launch_ew_i16) MNR_EW_DECL(launch_ew_u16)
 MNR_EW_DECL(launch_ew_i32) MNR_EW_DECL(launch_ew_u32) MNR_EW_DECL(launch_ew_i64) MNR_EW_DECL(launch_ew_u64)
 MNR_EW_DECL(launch_ew_f32) MNR_EW_DECL(launch_ew_f64)
 
 // 2: every pointer allows the op class's wide vector; 1: 128-bit; 0: element loads (not batched).
-int ew_batch_tier(mnr_dtype dt, int op, const void* lhs, const void* rhs, const void* out) {
+int ew_batch_tier(mnr_dtype dt, int op, bool sdiv, const void* lhs, const void* rhs, const void* out) {
     const bool is_float = dt == MNR_F32 || dt == MNR_F64;
-    const unsigned wide = op_class(is_float, op) == CLS_CHEAP ? 32u : 16u;
+    const unsigned wide = (sdiv || op_class(is_float, op) == CLS_CHEAP) ? 32u : 16u;
     auto ok = [](const void* p, unsigned al) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (al - 1)) == 0; };
     if (wide > 16 && ok(lhs, wide) && ok(rhs, wide) && ok(out, wide)) return 2;
     if (ok(lhs, 16) && ok(rhs, 16) && ok(out, 16)) return wide == 16 ? 2 : 1;
     return 0;
 }
 
-cudaError_t launch_ew_batch(mnr_dtype dt, int op, int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n,
-                            cudaStream_t s) {
+cudaError_t launch_ew_batch(mnr_dtype dt, int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg,
+                            uint64_t max_n, cudaStream_t s) {
     switch (dt) {
-        case MNR_I8: return launch_ew_i8_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_U8: return launch_ew_u8_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_I16: return launch_ew_i16_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_U16: return launch_ew_u16_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_I32: return launch_ew_i32_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_U32: return launch_ew_u32_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_I64: return launch_ew_i64_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_U64: return launch_ew_u64_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_F32: return launch_ew_f32_batch(op, tier, masked, segs, nseg, max_n, s);
-        case MNR_F64: return launch_ew_f64_batch(op, tier, masked, segs, nseg, max_n, s);
+        case MNR_I8: return launch_ew_i8_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_U8: return launch_ew_u8_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_I16: return launch_ew_i16_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_U16: return launch_ew_u16_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_I32: return launch_ew_i32_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_U32: return launch_ew_u32_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_I64: return launch_ew_i64_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_U64: return launch_ew_u64_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_F32: return launch_ew_f32_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_F64: return launch_ew_f64_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
     }
     return cudaErrorInvalidValue;
 }

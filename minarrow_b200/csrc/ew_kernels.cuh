@@ -14,11 +14,14 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "divmagic.h"
 #include "internal.h"
 
 namespace mnr {
 
-enum { CLS_CHEAP = 0, CLS_DIV = 1, CLS_POW = 2, CLS_REM = 3 };
+// CLS_SDIV: integer Div / Rem / FloorDiv by a non-zero column-wide scalar, evaluated with the host-computed
+// multiplicative inverse (divmagic.h) — chosen by the launcher, never by op_class().
+enum { CLS_CHEAP = 0, CLS_DIV = 1, CLS_POW = 2, CLS_REM = 3, CLS_SDIV = 4 };
 
 __host__ __device__ constexpr int op_class(bool is_float, int op) {
     return (op == MNR_ADD || op == MNR_SUB || op == MNR_MUL) ? CLS_CHEAP
@@ -33,19 +36,37 @@ __host__ __device__ constexpr int op_class(bool is_float, int op) {
 // Power: exponent = rhs.to_u32().unwrap_or(0) (std.rs:67), wrapping repeated multiply (simd.rs:94-100)
 // evaluated by squaring — same residue mod 2^bits.
 template <typename T, int CLS>
-__device__ __forceinline__ T int_elem(int op, T l, T r, bool& ok) {
+__device__ __forceinline__ T int_elem(int op, T l, T r, bool& ok, const DivMagic& dm) {
     using UT = typename std::make_unsigned<T>::type;
     ok = true;
     if constexpr (CLS == CLS_CHEAP) {
         const UT a = (UT)l, b = (UT)r;
         return (T)(UT)(op == MNR_ADD ? a + b : op == MNR_SUB ? a - b : a * b);
-    } else if constexpr (CLS == CLS_DIV) {
-        if (r == 0) { ok = false; return 0; }
-        if constexpr (std::is_signed<T>::value) {
-            if (l == (T)((UT)1 << (sizeof(T) * 8 - 1)) && r == (T)-1) return op == MNR_REM ? (T)0 : l;
+    } else if constexpr (CLS == CLS_DIV || CLS == CLS_SDIV) {
+        T q;
+        if constexpr (CLS == CLS_SDIV) {
+            // r is the same non-zero scalar in every row: one high multiply instead of a divide.  8/16-bit columns are
+            // widened to 32 bits; the wrapped quotient of MIN / -1 comes out of the same arithmetic.
+            using W = typename std::conditional<sizeof(T) == 8, T,
+                                                typename std::conditional<std::is_signed<T>::value, int32_t, uint32_t>::type>::type;
+            q = (T)div_by_magic<W>((W)l, (W)r, dm);
+        } else {
+            if (r == 0) { ok = false; return 0; }
+            if constexpr (std::is_signed<T>::value && sizeof(T) == 8) {
+                // The 64-bit signed divide routine has no short path for small negative operands; the unsigned one does
+                // (both high words zero -> 32-bit divide).  |l| / |r| with the signs restored is the same truncating
+                // quotient, and 2^63 / 1 wraps back to MIN for MIN / -1.
+                const uint64_t al = l < 0 ? 0ull - (uint64_t)l : (uint64_t)l, ar = r < 0 ? 0ull - (uint64_t)r : (uint64_t)r;
+                const uint64_t uq = al / ar;
+                q = (T)(((l ^ r) < 0) ? 0ull - uq : uq);
+            } else {
+                if constexpr (std::is_signed<T>::value) {
+                    if (l == (T)((UT)1 << (sizeof(T) * 8 - 1)) && r == (T)-1) return op == MNR_REM ? (T)0 : l;
+                }
+                q = (T)(l / r);
+            }
         }
-        const T q = (T)(l / r);
-        const T m = (T)(l - (T)((UT)q * (UT)r));
+        const T m = (T)((UT)l - (UT)((UT)q * (UT)r));
         if (op == MNR_DIV) return q;
         if (op == MNR_REM) return m;
         if constexpr (std::is_signed<T>::value) {
@@ -82,10 +103,38 @@ __device__ __forceinline__ T float_elem(int op, T a, T b) {
     }
 }
 
+// 8/16-bit Add / Sub / Mul on a whole 32-bit word (4 or 2 elements): wrapping arithmetic has the same bits for signed
+// and unsigned lanes.  Per element the generic path pays a byte extract, the operation, a select and a byte insert; a
+// 1-byte column must move ~2e12 rows/s to stay on the HBM roofline, which leaves room for ~3 instructions per row.
+template <int ESZ, int OP> __device__ __forceinline__ uint32_t packed_cheap_word(uint32_t a, uint32_t b) {
+    if constexpr (ESZ == 1) {
+        if constexpr (OP == MNR_ADD) return __vadd4(a, b);
+        if constexpr (OP == MNR_SUB) return __vsub4(a, b);
+        // the low byte of a product depends on the low bytes of the factors only: shift, multiply, keep byte 0
+        const uint32_t p0 = a * b, p1 = (a >> 8) * (b >> 8), p2 = (a >> 16) * (b >> 16), p3 = (a >> 24) * (b >> 24);
+        return __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
+    } else {
+        if constexpr (OP == MNR_ADD) return __vadd2(a, b);
+        if constexpr (OP == MNR_SUB) return __vsub2(a, b);
+        return __byte_perm(a * b, (a >> 16) * (b >> 16), 0x5410);
+    }
+}
+// One vector (NW words) with the operator fixed at compile time; `bits` = validity of the vector's elements.
+template <int ESZ, int OP, bool MASKED, int NW>
+__device__ __forceinline__ void packed_cheap_vec(const uint32_t* a, const uint32_t* b, uint32_t sword, uint32_t bits, uint32_t* o) {
+    constexpr int EPW = 4 / ESZ;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        uint32_t r = packed_cheap_word<ESZ, OP>(a ? a[j] : sword, b ? b[j] : sword);
+        if constexpr (MASKED) r &= expand_valid_word<ESZ>(bits >> (j * EPW));
+        o[j] = r;
+    }
+}
+
 template <typename T, int CLS>
-__device__ __forceinline__ T elem(int op, T l, T r, bool& ok) {
+__device__ __forceinline__ T elem(int op, T l, T r, bool& ok, const DivMagic& dm) {
     if constexpr (Traits<T>::is_float) { ok = true; return float_elem<T, CLS>(op, l, r); }
-    else return int_elem<T, CLS>(op, l, r, ok);
+    else return int_elem<T, CLS>(op, l, r, ok, dm);
 }
 
 // ---- validity helpers ------------------------------------------------------------------------------------
@@ -143,6 +192,8 @@ struct EwDev {
     uint64_t n;
     unsigned int* div0_flag;
     int op;
+    int sdiv;            // 1: the scalar is a non-zero integer divisor and `magic` is its inverse (CLS_SDIV launches only)
+    DivMagic magic;
 };
 
 template <typename T> __device__ __forceinline__ T scalar_from_bits(uint64_t b) {
@@ -187,6 +238,11 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
     const uint64_t gwarp = (uint64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const T sval = scalar_from_bits<T>(a.scalar_bits);
+    // SIMD-in-register path: 8/16-bit integers, cheap operators, same stored type on both sides, vector loads
+    constexpr bool PACKED = CLS == CLS_CHEAP && !Traits<T>::is_float && sizeof(T) <= 2 && std::is_same<TL, T>::value &&
+                            std::is_same<TR, T>::value && sizeof(VecT) >= 16;
+    const uint32_t sword = sizeof(T) == 1 ? (uint32_t)(uint8_t)a.scalar_bits * 0x01010101u : (uint32_t)(uint16_t)a.scalar_bits * 0x00010001u;
+    const DivMagic dm = a.magic;
     bool div0 = false;
 
     for (uint64_t t = gwarp; t < ntiles; t += warps) {
@@ -206,12 +262,28 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
         for (int u = 0; u < U; ++u) {
             VecU<T, VecT> O;
             uint32_t ob = 0;
+            if constexpr (PACKED) {
+                // 8/16-bit add / sub / mul: 32 bits at a time; these operators never null a row, so the output validity
+                // is the merged input validity and the values of invalid rows are cleared with the expanded mask.
+                constexpr int NW = sizeof(VecT) / 4;
+                union { VecT v; uint32_t w[NW]; } PL, PR, PO;
+                if (lp) memcpy(&PL.v, &L[u].v, sizeof(VecT));
+                if (rp) memcpy(&PR.v, &R[u].v, sizeof(VecT));
+                const uint32_t* pa = lp ? PL.w : nullptr;
+                const uint32_t* pb = rp ? PR.w : nullptr;
+                const uint32_t vb = MASKED ? mb[u] : 0u;
+                if (op == MNR_ADD) packed_cheap_vec<sizeof(T), MNR_ADD, MASKED, NW>(pa, pb, sword, vb, PO.w);
+                else if (op == MNR_SUB) packed_cheap_vec<sizeof(T), MNR_SUB, MASKED, NW>(pa, pb, sword, vb, PO.w);
+                else packed_cheap_vec<sizeof(T), MNR_MUL, MASKED, NW>(pa, pb, sword, vb, PO.w);
+                O.v = PO.v;
+                if constexpr (MASKED) ob = mb[u];
+            } else
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
                 const T l = lp ? (T)L[u].e[k] : sval;
                 const T r = rp ? (T)R[u].e[k] : sval;
                 bool ok;
-                const T val = elem<T, CLS>(op, l, r, ok);
+                const T val = elem<T, CLS>(op, l, r, ok, dm);
                 if constexpr (MASKED) {
                     const bool valid = ((mb[u] >> k) & 1u) && ok;
                     O.e[k] = valid ? val : (T)0;
@@ -259,7 +331,7 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
                 const T l = lp ? (T)L.e[k] : sval;
                 const T r = rp ? (T)R.e[k] : sval;
                 bool ok;
-                const T val = elem<T, CLS>(op, l, r, ok);
+                const T val = elem<T, CLS>(op, l, r, ok, dm);
                 if constexpr (MASKED) {
                     const bool valid = ((m >> k) & 1u) && ok && k < nrows;
                     O.e[k] = valid ? val : (T)0;

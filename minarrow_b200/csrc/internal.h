@@ -44,15 +44,20 @@ struct EwArgs {
     uint8_t* out_mask;
     uint64_t n;
     unsigned int* div0_flag;
+    // integer Div/Rem/FloorDiv by a non-zero scalar divisor: host-computed multiplicative inverse (divmagic.h);
+    // filled in by prepare_scalar_division() in api.cu, sdiv = 0 otherwise.
+    int sdiv;
+    uint64_t magic_m;
+    uint32_t magic_s1, magic_s2;
 };
 cudaError_t launch_ew_binary(const EwArgs& a, cudaStream_t s);
 // I32 operand promoted on load against an F32/F64 operand (routing/arithmetic.rs:244-269).
 cudaError_t launch_ew_promote(const EwArgs& a, mnr_dtype lhs_dtype, mnr_dtype rhs_dtype, cudaStream_t s);
 // Batched element-wise launch: `segs` = device array of EwDev descriptors of one (dtype, op class, masked, tier) class.
 struct EwDev;
-int ew_batch_tier(mnr_dtype dt, int op, const void* lhs, const void* rhs, const void* out);
-cudaError_t launch_ew_batch(mnr_dtype dt, int op, int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n,
-                            cudaStream_t s);
+int ew_batch_tier(mnr_dtype dt, int op, bool sdiv, const void* lhs, const void* rhs, const void* out);
+cudaError_t launch_ew_batch(mnr_dtype dt, int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg,
+                            uint64_t max_n, cudaStream_t s);
 cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void* c, const uint8_t* mask, void* out,
                           uint8_t* out_mask, uint64_t n, cudaStream_t s);
 

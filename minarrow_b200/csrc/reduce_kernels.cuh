@@ -204,10 +204,7 @@ template <typename T> struct NarrowState {
     // One 32-bit word = EPW elements; `bits` = their validity in the low EPW bits (ignored when !MASKED).
     template <bool MASKED, bool MINMAX> __device__ __forceinline__ void add_word(uint32_t w, uint32_t bits, uint32_t& acc32) {
         uint32_t m = 0xFFFFFFFFu;
-        if constexpr (MASKED) {
-            if constexpr (sizeof(T) == 1) m = (((bits & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
-            else m = (((bits & 3u) * 0x00008001u) & 0x00010001u) * 0xFFFFu;
-        }
+        if constexpr (MASKED) m = expand_valid_word<sizeof(T)>(bits);
         const uint32_t wz = w & m;   // invalid lanes -> 0
         if constexpr (sizeof(T) == 1) {
             if constexpr (kSigned) acc32 = (uint32_t)__dp4a((int)wz, 0x01010101, (int)acc32);

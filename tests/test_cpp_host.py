@@ -33,3 +33,16 @@ def test_reference_tests_transcribed_to_cpp_pass_on_the_gpu(gpu_ctx):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " 0 failed" in r.stdout and "kernel launches" in r.stdout, r.stdout[-500:]
+
+
+def test_division_by_invariant_scalar_arithmetic():
+    """minarrow_b200/csrc/divmagic.h (the multiply-high replacement for `column / scalar`) against the CPU's own divide:
+    edge divisors x edge dividends, 20 M random pairs per width, the 16-bit domain exhaustively.  Host-only, ~3 s."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_divmagic.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_divmagic")
+    deps = [src, os.path.join(ROOT, "minarrow_b200", "csrc", "divmagic.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", src, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.count(" 0 failed") == 5, r.stdout

@@ -98,3 +98,40 @@ def test_device_arithmetic_matches_pyarrow_compute(mnr, gpu_ctx, typ):
         assert st["sum"] == pc.sum(sa).as_py()
     else:
         assert abs(st["sum"] - pc.sum(sa).as_py()) <= 1e-9 * abs(pc.sum(pc.abs(sa)).as_py())
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_stream_import_shards_chunks_in_order(mnr, gpu_ctx, world):
+    """Arrow C stream (pyarrow.ChunkedArray.__arrow_c_stream__, the PyCapsule route of src/ffi/arrow_c_ffi.rs:153-168) ->
+    SuperArray chunks: every rank drains the stream and uploads its contiguous block; the blocks tile the column in
+    order, sliced chunks keep their element / bit offsets, per-rank sums add up to pyarrow's."""
+    rng = np.random.default_rng(43)
+    whole, d, mask = _make(rng, pa.int64(), 50_000)
+    cuts = [0, 7, 4_103, 4_103, 20_000, 33_333, 50_000]          # one empty chunk, odd offsets
+    chunks = [whole.slice(a, b - a) for a, b in zip(cuts[:-1], cuts[1:])]
+    ca = pa.chunked_array(chunks)
+    total, count, seen_rows = 0, 0, 0
+    for rank in range(world):
+        bufs, vms, seen = mnr.arrow.from_arrow_stream(gpu_ctx, ca, rank, world)
+        assert seen == len(chunks)
+        lo, hi = mnr.arrow.shard_range(len(chunks), rank, world)
+        assert len(bufs) == hi - lo
+        for k, (b, v) in enumerate(zip(bufs, vms)):
+            src = chunks[lo + k]
+            assert len(b) == len(src)
+            back = mnr.arrow.to_arrow(gpu_ctx, b, v)
+            assert back.equals(src) or (len(src) == 0 and len(back) == 0)
+            if len(b):
+                st = mnr.device_ops.reduce_stats(gpu_ctx, b, v)
+                total += st["sum"]; count += st["count"]
+            seen_rows += len(b)
+    assert seen_rows == 50_000
+    wrap = lambda x: (x + 2 ** 63) % 2 ** 64 - 2 ** 63   # noqa: E731
+    assert wrap(total) == wrap(int(np.sum(d[~mask].astype(object)))) and count == int((~mask).sum())
+
+
+def test_stream_import_rejects_non_numeric(mnr, gpu_ctx):
+    ca = pa.chunked_array([pa.array(["a", "b"]), pa.array(["c"])])
+    with pytest.raises(mnr.KernelError) as ei:
+        mnr.arrow.from_arrow_stream(gpu_ctx, ca)
+    assert ei.value.kind == "UnsupportedType"
