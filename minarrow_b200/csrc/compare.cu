@@ -8,6 +8,22 @@ namespace mnr {
 
 constexpr int kCBlock = 256, kCU = 4;
 
+// 8/16-bit elements, 32 bits at a time: (w & mask) ^ target is zero exactly in the equal lanes; the classic
+// zero-lane test ((x & 0x7f..) + 0x7f.. | x has the lane's top bit set iff the lane is non-zero) turns that into one bit
+// per lane, and a multiply gathers the 4 byte flags into a nibble.  ~2 instructions per row instead of ~5.
+template <int ESZ> __device__ __forceinline__ uint32_t eq_bits_word(uint32_t w, uint32_t fm, uint32_t tg) {
+    const uint32_t x = (w & fm) ^ tg;
+    if constexpr (ESZ == 1) {
+        const uint32_t nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+        const uint32_t eq = (nz ^ 0x80808080u) >> 7;          // bit 0 of byte k = lane k equal
+        return ((eq * 0x00204081u) >> 21) & 15u;              // bits 0, 8, 16, 24 -> bits 21..24 of the product
+    } else {
+        const uint32_t nz = (((x & 0x7fff7fffu) + 0x7fff7fffu) | x) & 0x80008000u;
+        const uint32_t eq = (nz ^ 0x80008000u) >> 15;         // bits 0 and 16
+        return (eq | (eq >> 15)) & 3u;
+    }
+}
+
 template <typename T, typename VecT>
 __global__ void __launch_bounds__(kCBlock)
 eq_mask_kernel(const T* __restrict__ data, uint64_t n, T field_mask, T target, uint8_t* __restrict__ out) {
@@ -27,8 +43,18 @@ eq_mask_kernel(const T* __restrict__ data, uint64_t n, T field_mask, T target, u
 #pragma unroll
         for (int u = 0; u < kCU; ++u) {
             uint32_t bits = 0;
+            if constexpr (sizeof(T) <= 2 && sizeof(VecT) >= 16) {
+                constexpr int NW = sizeof(VecT) / 4, EPW = 4 / sizeof(T);
+                constexpr uint32_t REP = sizeof(T) == 1 ? 0x01010101u : 0x00010001u;
+                union { VecT v; uint32_t w[NW]; } p;
+                p.v = x[u].v;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) bits |= (uint32_t)((T)(x[u].e[k] & field_mask) == target) << k;
+                for (int j = 0; j < NW; ++j)
+                    bits |= eq_bits_word<sizeof(T)>(p.w[j], (uint32_t)field_mask * REP, (uint32_t)target * REP) << (j * EPW);
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) bits |= (uint32_t)((T)(x[u].e[k] & field_mask) == target) << k;
+            }
             store_valid_bits<VEC>(out, (v0 + 32ull * u) * VEC, n, bits);
         }
     }

@@ -17,7 +17,7 @@ int g_ew_grid_cap = 0;   // >0: cap every element-wise grid at this many blocks 
 extern int g_ew_grid_cap;
 #endif
 
-struct CfgCheap { static constexpr int BLOCK = 128, U = 4, MINB = 1; static constexpr bool RESIDENT = false; using Wide = V32; };
+struct CfgCheap { static constexpr int BLOCK = 128, U = 4, MINB = 4; static constexpr bool RESIDENT = false; using Wide = V32; };
 struct CfgHeavy { static constexpr int BLOCK = 256, U = 2, MINB = 4; static constexpr bool RESIDENT = true; using Wide = V16; };
 template <int CLS> struct CfgOf { using type = CfgHeavy; };
 template <> struct CfgOf<CLS_CHEAP> { using type = CfgCheap; };

@@ -87,10 +87,19 @@ def main():
         entry("reduce sum+min+max+count masked", name, n * (sz + 0.125), lambda: ops.reduce_stats_async(ctx, X, MX, True, part.data_ptr()))
         entry("reduce sum dense", name, n * sz, lambda: ops.reduce_stats_async(ctx, X, None, False, part.data_ptr()))
         entry("reduce sum+min+max dense", name, n * sz, lambda: ops.reduce_stats_async(ctx, X, None, True, part.data_ptr()))
-        for opn, op in (("add", A.Add), ("mul", A.Multiply), ("div", A.Divide), ("rem", A.Remainder), ("floordiv", A.FloorDiv),
-                        ("pow", A.Power)):
+        for opn, op in (("add", A.Add), ("mul", A.Multiply), ("div", A.Divide), ("rem", A.Remainder), ("floordiv", A.FloorDiv)):
             entry(f"ew {opn} two masks", name, n * (3 * sz + 0.375),
                   lambda op=op: ops.ew_binary_into(ctx, op, X, Y, MX, MY, mnr.MaskMode.And, O, OM))
+        # Power: exponents 0..7 (the reference's own tests use 2 and 3, arithmetic/mod.rs:507-537); integer pow is a
+        # square-and-multiply loop whose trip count is log2(exponent)
+        if np.dtype(name).kind == "f":
+            te = torch.randint(0, 8, (n,), dtype=torch.int32, device=dev, generator=g).to(tdt[name])
+        else:
+            te = torch.randint(0, 8, (n,), dtype={1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[sz], device=dev, generator=g)
+        E = mnr.DeviceBuffer.wrap(ctx, np.dtype(name), te.data_ptr(), n, te)
+        entry("ew pow two masks (exponents 0..7)", name, n * (3 * sz + 0.375),
+              lambda: ops.ew_binary_into(ctx, A.Power, X, E, MX, MY, mnr.MaskMode.And, O, OM))
+        del E, te
         entry("ew add dense", name, n * 3 * sz, lambda: ops.ew_binary_into(ctx, A.Add, X, Y, None, None, mnr.MaskMode.And, O, None))
         entry("ew scalar add masked", name, n * (2 * sz + 0.25), lambda: ops.ew_scalar_into(ctx, A.Add, X, 3, False, MX, O, OM))
         entry("ew scalar div masked", name, n * (2 * sz + 0.25), lambda: ops.ew_scalar_into(ctx, A.Divide, X, 3, False, MX, O, OM))
@@ -123,7 +132,9 @@ def main():
     L = mnr.LogicalOperator
     for opn, op in (("and", L.And), ("or", L.Or), ("xor", L.Xor)):
         entry(f"bits {opn}", "bit", nb * 3 / 8, lambda op=op: ops.bits_binop_into(ctx, op, Ab, 0, Bb, 0, nb, Rb))
-    entry("bits and (bit offsets 3/5)", "bit", (nb - 64) * 3 / 8, lambda: ops.bits_binop_into(ctx, L.And, Ab, 3, Bb, 5, nb - 64, Rb))
+    tr2 = torch.empty((nb - 64) // 8, dtype=torch.uint8, device=dev)
+    Rb2 = mnr.DeviceBitmask.wrap(ctx, tr2.data_ptr(), nb - 64, tr2)
+    entry("bits and (windows at bytes 1/2)", "bit", (nb - 64) * 3 / 8, lambda: ops.bits_binop_into(ctx, L.And, Ab, 8, Bb, 16, nb - 64, Rb2))
     entry("bits not", "bit", nb * 2 / 8, lambda: ops.bits_not_into(ctx, Ab, 0, nb, Rb))
     entry("bits popcount (sync API)", "bit", nb / 8, lambda: ops.bits_popcount(ctx, Ab, 0, nb))
     entry("bits all_eq (sync API)", "bit", nb * 2 / 8, lambda: ops.bits_all_eq(ctx, Ab, 0, Ab, 0, nb))
