@@ -109,3 +109,15 @@ def test_exchange_and_combine_gloo_world2():
         assert p.exitcode == 0
     for rank, ok, same, shape in res:
         assert ok and same and shape == (2, 4), (rank, ok, same, shape)
+
+
+def test_stream_shard_ranges_match_the_chunk_map():
+    """arrow.shard_range (which chunks of an Arrow C stream a rank uploads) is the inverse of sharded.shard_chunks."""
+    from minarrow_b200.arrow import shard_range
+    from minarrow_b200.sharded import shard_chunks
+    for n in range(0, 40):
+        for w in range(1, 9):
+            rs = shard_chunks(n, w)
+            for r in range(w):
+                lo, hi = shard_range(n, r, w)
+                assert (len(rs[r]) == 0 and lo == hi) or (rs[r].start, rs[r].stop) == (lo, hi), (n, w, r)

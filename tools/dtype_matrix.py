@@ -120,6 +120,19 @@ def main():
                 om.free()
             entry("ew add i32 (cast on load) + T", name, n * (4 + 2 * sz + 0.375), prom)
             del ti, I
+        # consolidate (device concat): 64 chunks with validity; aligned chunk lengths, then ragged ones (rows % 8 != 0, so
+        # every chunk after the first lands on an odd element and an odd bit offset)
+        if name in ("int8", "int32", "int64", "float64"):
+            for label, rows in (("aligned", (n // 64) - (n // 64) % 64), ("ragged", (n // 64) - (n // 64) % 64 - 3)):
+                cb = [X.slice(k * (n // 64), rows) for k in range(64)]
+                cm = [ops.bits_slice(ctx, MX, k * (n // 64) - (k * (n // 64)) % 64, rows) for k in range(64)]
+
+                def cat():
+                    ob, om = ops.concat(ctx, cb, cm)
+                    ob.free()
+                    om.free()
+                entry(f"concat 64 chunks + validity ({label})", name, 64 * rows * 2 * (sz + 0.125), cat)
+                del cb, cm
         del X, Y, O, MX, MY, OM, tx, ty, to, tmx, tmy, tom
         torch.cuda.empty_cache()
 
