@@ -334,7 +334,31 @@ def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows, supertable=True):
     assert torch.equal(r[: 1 << 24], a[: 1 << 24] & b[: 1 << 24])
     entry("bitmask_not_4Gbit", nb * 2 / 8, lambda: devops.bits_not_into(ctx, Ab, 0, nb, Rb))
     entry("bitmask_popcount_4Gbit", nb / 8, lambda: devops.bits_popcount(ctx, Ab, 0, nb), iters=10)
-    del Ab, Bb, Rb, a, b, r
+    # BitmaskVT windows that do not start on a vector boundary (byte offsets 1 and 2): aligned loads + funnel shift
+    r2 = torch.empty((nb - 64) // 8, dtype=torch.uint8, device=dev)
+    Rb2 = mnr.DeviceBitmask.wrap(ctx, r2.data_ptr(), nb - 64, r2)
+    entry("bitmask_and_4Gbit_unaligned_windows", (nb - 64) * 3 / 8,
+          lambda: devops.bits_binop_into(ctx, mnr.LogicalOperator.And, Ab, 8, Bb, 16, nb - 64, Rb2))
+    assert torch.equal(r2[: 1 << 24], a[1: (1 << 24) + 1] & b[2: (1 << 24) + 2])
+    del Ab, Bb, Rb, Rb2, a, b, r, r2
+    torch.cuda.empty_cache()
+
+    # integer column / broadcast scalar (Array o Scalar route): multiply-high by the host-computed inverse, no divide
+    n = 1 << 28
+    xi = torch.randint(-2 ** 40, 2 ** 40, (n,), dtype=torch.int64, device=dev, generator=g)
+    mi = torch.randint(0, 256, (n // 8,), dtype=torch.uint8, device=dev, generator=g) | \
+        torch.randint(0, 256, (n // 8,), dtype=torch.uint8, device=dev, generator=g)
+    oi = torch.empty_like(xi)
+    omi = torch.empty_like(mi)
+    XI = mnr.DeviceBuffer.wrap(ctx, np.int64, xi.data_ptr(), n, xi)
+    OI = mnr.DeviceBuffer.wrap(ctx, np.int64, oi.data_ptr(), n, oi)
+    MI = mnr.DeviceBitmask.wrap(ctx, mi.data_ptr(), n, mi)
+    OMI = mnr.DeviceBitmask.wrap(ctx, omi.data_ptr(), n, omi)
+    entry("i64_masked_div_by_scalar_86400", n * 16.25, lambda: devops.ew_scalar_into(ctx, A.Divide, XI, 86400, False, MI, OI, OMI))
+    vb = ((mi[: 1 << 17].to(torch.int32).view(-1, 1) >> torch.arange(8, device=dev, dtype=torch.int32)) & 1).bool().view(-1)
+    exp = torch.where(vb, torch.div(xi[: 1 << 20], 86400, rounding_mode="trunc"), torch.zeros((), dtype=torch.int64, device=dev))
+    assert torch.equal(exp, oi[: 1 << 20]), "i64 / scalar mismatch vs torch"
+    del XI, OI, MI, OMI, xi, mi, oi, omi
     torch.cuda.empty_cache()
 
     # configs[0]: IntegerArray<i64> sum of 1 000 elements, averaged over 1 000 runs (hotloop_benchmark_simd shape).
