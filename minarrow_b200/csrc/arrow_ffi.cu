@@ -65,12 +65,15 @@ int upload_bits_window(mnr_ctx* c, const uint8_t* host, int64_t bit_offset, int6
     const size_t first = (size_t)bit_offset >> 3, shift = (size_t)bit_offset & 7;
     const size_t nbytes = (shift + (size_t)len + 7) >> 3;
     if (shift == 0) {
-        if (cudaMemcpyAsync((*out)->ptr, host + first, (size_t)(len + 7) >> 3, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
-            AFAIL(MNR_ERR_CUDA, "arrow import: validity upload failed");
-        // clear the slack bits of the last byte (Bitmask::mask_trailing_bits)
-        if (launch_bits_op(5, (*out)->ptr, 0, (uint64_t)len, nullptr, 0, 0, (uint64_t)len, (*out)->ptr, c->stream) != cudaSuccess)
-            AFAIL(MNR_ERR_CUDA, "arrow import: trailing-bit clear failed");
-        c->launches++;
+        // byte-aligned window: plain copy; the slack bits of the last byte (Bitmask::mask_trailing_bits, bitmask.rs:83-90) are
+        // cleared on the host copy of that one byte — a foreign producer may leave anything there
+        const size_t nb = (size_t)(len + 7) >> 3;
+        uint8_t last = host[first + nb - 1];
+        if (len & 7) last &= (uint8_t)((1u << (len & 7)) - 1u);
+        bool ok = true;
+        if (nb > 1) ok &= cudaMemcpyAsync((*out)->ptr, host + first, nb - 1, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+        ok &= cudaMemcpyAsync((*out)->ptr + nb - 1, &last, 1, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+        if (!ok) AFAIL(MNR_ERR_CUDA, "arrow import: validity upload failed");
     } else {
         void* tmp = nullptr;
         if (cudaMallocAsync(&tmp, nbytes + 16, c->stream) != cudaSuccess) AFAIL(MNR_ERR_OUT_OF_MEMORY, "arrow import: staging allocation failed");

@@ -151,7 +151,7 @@ __device__ __forceinline__ void popcount_finish(unsigned long long acc, unsigned
 // Output vectors [v_lo, v_hi) through the shifted body, every other output byte through the byte path.
 // POPC: count the bits of (a op b) instead of storing them (op = B_COPY for one operand, B_XOR for all_eq).
 template <bool POPC>
-__global__ void __launch_bounds__(kBBlock)
+__global__ void __launch_bounds__(kBBlock, 4)   // <= 64 registers: 4 blocks/SM (ncu r01s: 72 registers, 3 blocks, 34 % warps active, 70 % DRAM)
 bits_shift_kernel(int op, const uint8_t* __restrict__ a, uint64_t a_pos, uint64_t a_nbytes, ShiftSrc sa,
                   const uint8_t* __restrict__ b, uint64_t b_pos, uint64_t b_nbytes, ShiftSrc sb, uint64_t len,
                   uint8_t* __restrict__ out, uint64_t v_lo, uint64_t v_hi, unsigned long long* __restrict__ partials,

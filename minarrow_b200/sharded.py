@@ -52,6 +52,39 @@ def shard_rows(n_rows: int, world: int, align: int = 64) -> List[Tuple[int, int]
     return out
 
 
+def rebalance_plan(rows: Sequence[int], align: int = 64) -> Tuple[List[List[Tuple[int, int, int]]], List[Tuple[int, int]]]:
+    """Who sends which rows to whom when the shards of one column (rank order = row order, `rows[r]` rows on rank r) are
+    re-cut into the even contiguous windows of `shard_rows` — the multi-GPU form of SuperArray::rechunk
+    (src/structs/chunked/super_array.rs:674-787), which the reference needs whenever one operand's chunking has to match
+    the other's (`create_aligned_chunks_from_array`, src/utils.rs:417-481).
+
+    Returns (sends, targets): sends[r] = [(dst, lo, hi), ...] local row windows of rank r in ascending dst (= ascending
+    row) order, covering [0, rows[r]) exactly once; targets[d] = (global_start, n_rows) of rank d afterwards."""
+    world = len(rows)
+    if world < 1 or any(r < 0 for r in rows):
+        raise KernelError("InvalidArguments", "rows must list one non-negative count per rank")
+    targets = shard_rows(sum(rows), world, align)
+    sends: List[List[Tuple[int, int, int]]] = []
+    start = 0
+    for r in range(world):
+        mine = []
+        for d, (t0, tn) in enumerate(targets):
+            lo, hi = max(start, t0), min(start + rows[r], t0 + tn)
+            if hi > lo:
+                mine.append((d, lo - start, hi - start))
+        sends.append(mine)
+        start += rows[r]
+    return sends, targets
+
+
+class _CudaView:
+    """`__cuda_array_interface__` over library-owned device memory so torch can alias it (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int, keep):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        self.keep = keep
+
+
 def agg_to_words(agg: "_lib.Agg") -> np.ndarray:
     """The 32-byte `mnr_agg` as 4 x int64 (the wire format of the exchange)."""
     return np.frombuffer(bytes(agg), dtype=np.int64).copy()
@@ -151,6 +184,95 @@ class ShardedColumn:
         if not keep:
             raise KernelError("InvalidArguments", "empty SuperArray")
         return combine_partials(self.dtype, keep)
+
+
+    def rebalance(self, group=None, align: int = 64) -> "ShardedColumn":
+        """Re-cut the column into even contiguous shards (one chunk per rank, cut on `align`-row boundaries), moving rows
+        between GPUs.  Local side: one device consolidate (`mnr_concat`), validity windows cut at their exact bit
+        offsets (`mnr_bits_slice`), received pieces stitched with the bit-granular gather of `mnr_concat`.  Exchange:
+        ONE all-to-all of value bytes and one of validity bytes (NCCL over NVLink on the box; the only place on this path
+        where link bandwidth, not latency, matters).  Row order, values and validity bits are preserved exactly."""
+        import torch
+        import torch.distributed as dist
+        from . import device_ops as dev
+        from .core import DeviceBitmask, DeviceBuffer
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dev_ = torch.device("cuda", self.ctx.device)
+        es = self.dtype.itemsize
+        # 1. one contiguous local shard
+        if self.chunks:
+            vals = self.validities if any(v is not None for v in self.validities) else None
+            whole, wmask = dev.concat(self.ctx, self.chunks, vals)
+        else:
+            whole, wmask = DeviceBuffer.alloc(self.ctx, self.dtype, 0), None
+        n_local = len(whole)
+        # 2. every rank learns every rank's row count and whether any shard carries validity
+        meta = torch.tensor([n_local, 0 if wmask is None else 1], dtype=torch.int64, device=dev_)
+        allm = torch.empty(world * 2, dtype=torch.int64, device=dev_)
+        if world > 1:
+            dist.all_gather_into_tensor(allm, meta, group=group)
+        else:
+            allm.copy_(meta)
+        allm = allm.cpu().numpy().reshape(world, 2)
+        rows = [int(x) for x in allm[:, 0]]
+        any_mask = bool(allm[:, 1].any())
+        sends, targets = rebalance_plan(rows, align)
+        my_sends = sends[rank]
+        recv_rows = [0] * world                      # rows this rank receives from each source, in source (= row) order
+        for src in range(world):
+            for d, lo, hi in sends[src]:
+                if d == rank:
+                    recv_rows[src] += hi - lo
+        send_rows = [0] * world
+        for d, lo, hi in my_sends:
+            send_rows[d] = hi - lo
+        # 3. values: the consolidated shard already is the send buffer (windows in ascending destination order)
+        self.ctx.synchronize()
+        send_v = torch.as_tensor(_CudaView(whole.device_ptr, n_local * es, whole), device=dev_) if n_local else \
+            torch.empty(0, dtype=torch.uint8, device=dev_)
+        recv_v = torch.empty(sum(recv_rows) * es, dtype=torch.uint8, device=dev_)
+        if world > 1:
+            dist.all_to_all_single(recv_v, send_v, [r * es for r in recv_rows], [r * es for r in send_rows], group=group)
+        else:
+            recv_v.copy_(send_v)
+        # 4. validity: each window re-based to bit 0 (exact bit offset), byte-padded per destination
+        recv_m = None
+        if any_mask:
+            nb = lambda r: (r + 7) // 8   # noqa: E731
+            send_m = torch.zeros(sum(nb(r) for r in send_rows), dtype=torch.uint8, device=dev_)
+            pos, pieces = 0, []
+            for d, lo, hi in my_sends:
+                n = hi - lo
+                piece = dev.bits_slice(self.ctx, wmask, lo, n) if wmask is not None else DeviceBitmask.new_set_all(self.ctx, n, True)
+                pieces.append((pos, nb(n), piece))
+                pos += nb(n)
+            self.ctx.synchronize()
+            for pos, k, piece in pieces:
+                send_m[pos:pos + k].copy_(torch.as_tensor(_CudaView(piece.device_ptr, k, piece), device=dev_))
+            recv_m = torch.empty(sum(nb(r) for r in recv_rows), dtype=torch.uint8, device=dev_)
+            if world > 1:
+                dist.all_to_all_single(recv_m, send_m, [nb(r) for r in recv_rows], [nb(r) for r in send_rows], group=group)
+            else:
+                recv_m.copy_(send_m)
+        torch.cuda.synchronize(dev_)
+        # 5. stitch: values are already contiguous in row order; validity pieces are byte-padded per source -> bit gather
+        bufs, vms, voff, moff = [], [], 0, 0
+        for src in range(world):
+            r = recv_rows[src]
+            if r == 0:
+                continue
+            bufs.append(DeviceBuffer.wrap(self.ctx, self.dtype, recv_v.data_ptr() + voff, r, recv_v))
+            if recv_m is not None:
+                vms.append(DeviceBitmask.wrap(self.ctx, recv_m.data_ptr() + moff, r, recv_m))
+                moff += (r + 7) // 8
+            voff += r * es
+        if not bufs:
+            return ShardedColumn(self.ctx, self.dtype, [], [])
+        out, om = dev.concat(self.ctx, bufs, vms if recv_m is not None else None)
+        self.ctx.synchronize()
+        assert len(out) == targets[rank][1]
+        return ShardedColumn(self.ctx, self.dtype, [out], [om])
 
 
 class FusedExchange:

@@ -16,6 +16,10 @@
 #include <cstring>
 #include <functional>
 #include <numeric>
+#include <algorithm>
+#include <climits>
+#include <utility>
+#include <vector>
 
 #include "minarrow_b200.hpp"
 
@@ -98,6 +102,142 @@ template <class T, class F> static void float_kernel_suite(F apply, T eps) {
     CHECK(apply(e, e, Op::Add, nullptr).is_empty());
 }
 
+// ---- paths beyond the reference's own vectors, sized to reach the vector / shifted / packed bodies -------------------
+// (run under compute-sanitizer by tools/gpu_sanitize.sh: memcheck, racecheck, initcheck, synccheck).  Expectations are
+// computed here on the host, bit by bit / row by row.
+static uint64_t lcg_state = 12345;
+static uint32_t lcg() { lcg_state = lcg_state * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(lcg_state >> 33); }
+static bool host_bit(const std::vector<uint8_t>& m, size_t i) { return (m[i >> 3] >> (i & 7)) & 1; }
+#define OK(call) CHECK((call) == MNR_OK)
+
+static void device_path_suite(Context& ctx) {
+    mnr_ctx* c = ctx.get();
+    const size_t NB = 100003;   // bits
+    std::vector<uint8_t> ha((NB + 7) / 8), hb((NB + 7) / 8);
+    for (auto& x : ha) x = (uint8_t)lcg();
+    for (auto& x : hb) x = (uint8_t)lcg();
+    ha.back() &= (uint8_t)((1u << (NB & 7)) - 1); hb.back() &= (uint8_t)((1u << (NB & 7)) - 1);
+    mnr_bits *A = nullptr, *B = nullptr;
+    OK(mnr_bits_upload(c, ha.data(), NB, &A));
+    OK(mnr_bits_upload(c, hb.data(), NB, &B));
+    {   // and_masks over windows at byte offsets (BitmaskVT offsets are floored to bytes, bitmask/mod.rs:124-128): shifted body
+        for (auto [lo, ro] : {std::pair<size_t, size_t>{8, 16}, {24, 0}, {136, 40}, {5, 77}}) {
+            const size_t len = NB - 200;
+            mnr_bits* R = nullptr;
+            OK(mnr_bits_binop(c, MNR_AND, A, lo, B, ro, len, &R));
+            std::vector<uint8_t> got((len + 7) / 8);
+            OK(mnr_bits_download(c, R, got.data()));
+            bool same_bits = true;
+            const size_t lb = lo / 8 * 8, rb = ro / 8 * 8;
+            for (size_t i = 0; i < len; ++i) same_bits &= host_bit(got, i) == (host_bit(ha, lb + i) && host_bit(hb, rb + i));
+            for (size_t i = len; i < got.size() * 8; ++i) same_bits &= !host_bit(got, i);   // slack bits zero
+            CHECK(same_bits);
+            mnr_bits_free(R);
+        }
+    }
+    {   // Bitmask::slice_clone at arbitrary bit offsets + popcount of offset windows
+        for (size_t off : {size_t(1), size_t(13), size_t(64), size_t(127), size_t(1001)}) {
+            const size_t len = NB - 2000;
+            mnr_bits* S = nullptr;
+            OK(mnr_bits_slice(c, A, off, len, &S));
+            std::vector<uint8_t> got((len + 7) / 8);
+            OK(mnr_bits_download(c, S, got.data()));
+            bool same_bits = true;
+            size_t ones = 0;
+            for (size_t i = 0; i < len; ++i) { same_bits &= host_bit(got, i) == host_bit(ha, off + i); ones += host_bit(ha, off + i); }
+            CHECK(same_bits);
+            uint64_t pc = 0;
+            OK(mnr_bits_popcount(c, S, 0, len, &pc));
+            CHECK(pc == ones);
+            const size_t w = off / 64 * 64;   // popcount_mask floors the offset to a 64-bit word (simd.rs:596-645)
+            size_t ones_w = 0;
+            for (size_t i = 0; i < len; ++i) ones_w += host_bit(ha, w + i);
+            OK(mnr_bits_popcount(c, A, off, len, &pc));
+            CHECK(pc == ones_w);
+            mnr_bits_free(S);
+        }
+    }
+    {   // consolidate: ragged chunks (odd element and bit offsets), 1- and 4-byte elements, one chunk without validity
+        const size_t lens[] = {4099, 0, 333, 70001, 7, 12345};
+        std::vector<int8_t> h8; std::vector<int32_t> h32; std::vector<uint8_t> hv;
+        std::vector<mnr_buf*> b8, b32; std::vector<mnr_bits*> vs;
+        size_t k = 0;
+        for (size_t n : lens) {
+            std::vector<int8_t> d8(n); std::vector<int32_t> d32(n); std::vector<uint8_t> v((n + 7) / 8, 0);
+            for (size_t i = 0; i < n; ++i) { d8[i] = (int8_t)lcg(); d32[i] = (int32_t)lcg(); const bool ok = k == 2 || (lcg() % 5) != 0; if (ok) v[i >> 3] |= uint8_t(1u << (i & 7)); hv.push_back(ok); }
+            h8.insert(h8.end(), d8.begin(), d8.end()); h32.insert(h32.end(), d32.begin(), d32.end());
+            mnr_buf *x8 = nullptr, *x32 = nullptr; mnr_bits* m = nullptr;
+            OK(mnr_buf_upload(c, MNR_I8, d8.data(), n, &x8)); OK(mnr_buf_upload(c, MNR_I32, d32.data(), n, &x32));
+            if (k != 2) OK(mnr_bits_upload(c, v.data(), n, &m));
+            b8.push_back(x8); b32.push_back(x32); vs.push_back(m);
+            ++k;
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            mnr_buf* out = nullptr; mnr_bits* om = nullptr;
+            OK(mnr_concat(c, b8.size(), pass ? b32.data() : b8.data(), vs.data(), &out, &om));
+            const size_t total = h8.size();
+            CHECK(out && mnr_buf_len(out) == total && om && mnr_bits_len(om) == total);
+            if (pass) { std::vector<int32_t> g(total); OK(mnr_buf_download(c, out, g.data())); CHECK(g == h32); }
+            else { std::vector<int8_t> g(total); OK(mnr_buf_download(c, out, g.data())); CHECK(g == h8); }
+            std::vector<uint8_t> gm((total + 7) / 8);
+            OK(mnr_bits_download(c, om, gm.data()));
+            bool same_bits = true;
+            for (size_t i = 0; i < total; ++i) same_bits &= host_bit(gm, i) == (hv[i] != 0);
+            CHECK(same_bits);
+            mnr_buf_free(out); mnr_bits_free(om);
+        }
+        for (auto* x : b8) mnr_buf_free(x);
+        for (auto* x : b32) mnr_buf_free(x);
+        for (auto* x : vs) mnr_bits_free(x);
+    }
+    {   // column / scalar through the multiplicative inverse, 8-bit packed add, 8-bit masked sum/min/max
+        const size_t n = 70001;
+        std::vector<int64_t> h(n); std::vector<int8_t> p(n), q(n); std::vector<uint8_t> v((n + 7) / 8, 0);
+        for (size_t i = 0; i < n; ++i) {
+            h[i] = (int64_t)(((uint64_t)lcg() << 32) | lcg()); p[i] = (int8_t)lcg(); q[i] = (int8_t)lcg();
+            if (lcg() % 4) v[i >> 3] |= uint8_t(1u << (i & 7));
+        }
+        h[0] = INT64_MIN; h[1] = INT64_MAX; h[2] = -1; h[3] = 0;
+        mnr_buf *H = nullptr, *P = nullptr, *Q = nullptr; mnr_bits* V = nullptr;
+        OK(mnr_buf_upload(c, MNR_I64, h.data(), n, &H)); OK(mnr_buf_upload(c, MNR_I8, p.data(), n, &P));
+        OK(mnr_buf_upload(c, MNR_I8, q.data(), n, &Q)); OK(mnr_bits_upload(c, v.data(), n, &V));
+        for (int64_t d : {int64_t(7), int64_t(-86400), int64_t(1) << 40, int64_t(-1)}) {
+            mnr_buf* o = nullptr; mnr_bits* om = nullptr;
+            OK(mnr_ew_scalar(c, MNR_FLOORDIV, H, &d, 0, V, &o, &om));
+            std::vector<int64_t> g(n);
+            OK(mnr_buf_download(c, o, g.data()));
+            bool same_vals = true;
+            for (size_t i = 0; i < n; ++i) {
+                int64_t e = 0;
+                if (host_bit(v, i)) {
+                    if (h[i] == INT64_MIN && d == -1) e = INT64_MIN;
+                    else { const int64_t qq = h[i] / d, m = h[i] % d; e = (m != 0 && ((h[i] ^ d) < 0)) ? qq - 1 : qq; }
+                }
+                same_vals &= g[i] == e;
+            }
+            CHECK(same_vals);
+            mnr_buf_free(o); mnr_bits_free(om);
+        }
+        {
+            mnr_buf* o = nullptr; mnr_bits* om = nullptr;
+            OK(mnr_ew_binary(c, MNR_ADD, P, Q, V, nullptr, MNR_MASK_AND, &o, &om));
+            std::vector<int8_t> g(n);
+            OK(mnr_buf_download(c, o, g.data()));
+            bool same_vals = true;
+            for (size_t i = 0; i < n; ++i) same_vals &= g[i] == (host_bit(v, i) ? (int8_t)(uint8_t)((uint8_t)p[i] + (uint8_t)q[i]) : 0);
+            CHECK(same_vals);
+            mnr_buf_free(o); mnr_bits_free(om);
+            mnr_agg a;
+            OK(mnr_reduce_stats(c, P, V, &a));
+            int64_t sum = 0, mn = INT8_MAX, mx = INT8_MIN; uint64_t cnt = 0;
+            for (size_t i = 0; i < n; ++i) if (host_bit(v, i)) { sum += p[i]; mn = std::min<int64_t>(mn, p[i]); mx = std::max<int64_t>(mx, p[i]); ++cnt; }
+            CHECK(a.sum.i64 == sum && a.min.i64 == mn && a.max.i64 == mx && a.count == cnt);
+        }
+        mnr_buf_free(H); mnr_buf_free(P); mnr_buf_free(Q); mnr_bits_free(V);
+    }
+    mnr_bits_free(A); mnr_bits_free(B);
+}
+
 int main(int argc, char** argv) {
     if (argc > 1 && !std::strcmp(argv[1], "--link")) {
         std::printf("abi %d, devices %d\n", mnr_abi_version(), mnr_device_count());
@@ -171,6 +311,7 @@ int main(int argc, char** argv) {
             auto host = sq.download();
             CHECK(host[10] == 100 && host[11] == 0 && sqm && sqm->count_ones() == 500);
         }
+        device_path_suite(ctx);
         std::printf("%d checks, %d failed, %llu kernel launches\n", g_checks, g_failed, (unsigned long long)ctx.launch_count());
     } catch (const std::exception& e) {
         std::printf("EXCEPTION %s\n", e.what());

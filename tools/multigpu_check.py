@@ -57,6 +57,32 @@ def main():
             m = orc.Bits(chunks[i].null_mask.bits, rows)
             ed, em = orc.apply(chunks[i].data, chunks[i].data, orc.MUL, m)
             assert ob.download().tobytes() == ed.tobytes() and np.array_equal(om.download().bits, em.bits), (dt, i)
+    # rebalance (multi-GPU rechunk): deliberately uneven shards -> even 64-row-aligned windows; rows move between GPUs
+    # with one all-to-all of value bytes + one of validity bytes, stitched by the device consolidate
+    for dt in (np.int64, np.int8, np.float32):
+        sizes = [int(x) for x in rng.integers(0, 200_000, world)]
+        sizes[0] = 300_001                                   # rank 0 is overloaded, odd row count -> odd bit offsets
+        n = sum(sizes)
+        whole = rng.integers(-100, 100, n).astype(dt)
+        valid = rng.random(n) < 0.85
+        st = int(np.sum(sizes[:rank]))
+        cuts = [0, sizes[rank] // 3, sizes[rank] // 3, sizes[rank]]           # three local chunks, one empty
+        chunks_l, vals_l = [], []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            chunks_l.append(mnr.DeviceBuffer.upload(ctx, whole[st + a:st + b]))
+            vals_l.append(mnr.DeviceBitmask.upload(ctx, mnr.Bitmask.from_bools(valid[st + a:st + b])))
+        col = sh.ShardedColumn(ctx, dt, chunks_l, vals_l)
+        before = col.stats(True)
+        bal = col.rebalance()
+        t0, tn = sh.shard_rows(n, world)[rank]
+        assert len(bal.chunks) == (1 if tn else 0)
+        if tn:
+            assert len(bal.chunks[0]) == tn
+            assert bal.chunks[0].download().tobytes() == whole[t0:t0 + tn].tobytes(), (dt, rank)
+            assert np.array_equal(bal.validities[0].download().bits, np.packbits(valid[t0:t0 + tn], bitorder="little")), (dt, rank)
+        after = bal.stats(True)
+        assert (after["count"], after["min"], after["max"]) == (before["count"], before["min"], before["max"])
+        assert after["sum"] == before["sum"] or np.dtype(dt).kind == "f"
     # fused reduction + exchange kernel (P2P mailboxes): every rank reduces its window of one big column and must end
     # with the oracle's aggregate of the WHOLE column, bit-identical on all ranks, over many back-to-back epochs.
     fx = sh.FusedExchange(ctx)
