@@ -334,6 +334,9 @@ def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows, supertable=True):
     assert torch.equal(r[: 1 << 24], a[: 1 << 24] & b[: 1 << 24])
     entry("bitmask_not_4Gbit", nb * 2 / 8, lambda: devops.bits_not_into(ctx, Ab, 0, nb, Rb))
     entry("bitmask_popcount_4Gbit", nb / 8, lambda: devops.bits_popcount(ctx, Ab, 0, nb), iters=10)
+    cnt_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    entry("bitmask_popcount_4Gbit_async", nb / 8, lambda: devops.bits_popcount_async(ctx, Ab, 0, nb, cnt_dev.data_ptr()))
+    assert int(cnt_dev.item()) == devops.bits_popcount(ctx, Ab, 0, nb)
     # BitmaskVT windows that do not start on a vector boundary (byte offsets 1 and 2): aligned loads + funnel shift
     r2 = torch.empty((nb - 64) // 8, dtype=torch.uint8, device=dev)
     Rb2 = mnr.DeviceBitmask.wrap(ctx, r2.data_ptr(), nb - 64, r2)

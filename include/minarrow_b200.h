@@ -198,6 +198,9 @@ int mnr_bits_not_into(mnr_ctx* ctx, const mnr_bits* src, size_t offset, size_t l
  * Bitmask::count_ones / null_count (bitmask.rs:393-417): offset 0, len = mask len; null_count = len - ones.
  * Synchronises. */
 int mnr_bits_popcount(mnr_ctx* ctx, const mnr_bits* mask, size_t offset, size_t len, uint64_t* ones);
+/* Asynchronous form for device-resident pipelines: the count is written to DEVICE memory `out_device` (one uint64,
+ * 8-byte aligned) on the context stream; no synchronisation (null_count feeding a later kernel never visits the host). */
+int mnr_bits_popcount_async(mnr_ctx* ctx, const mnr_bits* mask, size_t offset, size_t len, void* out_device);
 /* all_true_mask / all_false_mask (dispatch.rs:273-295). Synchronise. */
 int mnr_bits_all_true(mnr_ctx* ctx, const mnr_bits* mask, int* out);
 int mnr_bits_all_false(mnr_ctx* ctx, const mnr_bits* mask, int* out);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "mnr_bits_not": (c_int, [c_ctx, c_bits, c_sz, c_sz, PP]),
     "mnr_bits_not_into": (c_int, [c_ctx, c_bits, c_sz, c_sz, c_bits]),
     "mnr_bits_popcount": (c_int, [c_ctx, c_bits, c_sz, c_sz, C.POINTER(C.c_uint64)]),
+    "mnr_bits_popcount_async": (c_int, [c_ctx, c_bits, c_sz, c_sz, c_vp]),
     "mnr_bits_all_true": (c_int, [c_ctx, c_bits, C.POINTER(c_int)]),
     "mnr_bits_all_false": (c_int, [c_ctx, c_bits, C.POINTER(c_int)]),
     "mnr_bits_merge": (c_int, [c_ctx, c_bits, c_bits, c_sz, c_int, PP]),

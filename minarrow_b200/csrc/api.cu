@@ -690,6 +690,20 @@ int mnr_bits_popcount(mnr_ctx* c, const mnr_bits* m, size_t off, size_t len, uin
     return popcount_sync(c, m, p, nullptr, 0, len, ones);
 }
 
+int mnr_bits_popcount_async(mnr_ctx* c, const mnr_bits* m, size_t off, size_t len, void* out_device) {
+    REQUIRE(c && m && out_device, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE((reinterpret_cast<uintptr_t>(out_device) & 7u) == 0, MNR_ERR_INVALID_ARGUMENTS, "out_device must be 8-byte aligned");
+    const uint64_t p = (uint64_t)(off / 64) * 64;
+    int rc = check_window(m, p, len, "popcount_mask");
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if (len == 0) { CU(cudaMemsetAsync(out_device, 0, 8, c->stream)); return MNR_OK; }
+    CU(launch_bits_popcount(m->ptr, p, m->len, nullptr, 0, 0, len, reinterpret_cast<unsigned long long*>(c->partials[3]),
+                            c->ticket[3] + 4, static_cast<unsigned long long*>(out_device), nullptr, c->stream));
+    c->launches++;
+    return MNR_OK;
+}
+
 int mnr_bits_all_true(mnr_ctx* c, const mnr_bits* m, int* out) {
     REQUIRE(c && m && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
     uint64_t ones = 0;

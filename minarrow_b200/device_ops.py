@@ -102,6 +102,11 @@ def bits_popcount(ctx: Context, m: DeviceBitmask, off: int, length: int) -> int:
     return int(ones.value)
 
 
+def bits_popcount_async(ctx: Context, m: DeviceBitmask, off: int, length: int, out_device_ptr: int) -> None:
+    """Set-bit count of the window -> one uint64 in device memory on the context stream (no sync)."""
+    check(ctx.lib.mnr_bits_popcount_async(ctx.h, m.h, off, length, C.c_void_p(out_device_ptr)))
+
+
 def bits_all_true(ctx: Context, m: DeviceBitmask) -> bool:
     r = C.c_int()
     check(ctx.lib.mnr_bits_all_true(ctx.h, m.h, C.byref(r)))

@@ -41,6 +41,7 @@ extern "C" {
                           rhs_offset: usize, len: usize, out: *mut *mut mnr_bits) -> c_int;
     pub fn mnr_bits_not(ctx: *mut mnr_ctx, src: *const mnr_bits, offset: usize, len: usize, out: *mut *mut mnr_bits) -> c_int;
     pub fn mnr_bits_popcount(ctx: *mut mnr_ctx, mask: *const mnr_bits, offset: usize, len: usize, ones: *mut u64) -> c_int;
+    pub fn mnr_bits_popcount_async(ctx: *mut mnr_ctx, mask: *const mnr_bits, offset: usize, len: usize, out_device: *mut c_void) -> c_int;
     pub fn mnr_reduce_stats(ctx: *mut mnr_ctx, buf: *const mnr_buf, validity: *const mnr_bits, out: *mut mnr_agg) -> c_int;
     pub fn mnr_reduce_stats_batch(ctx: *mut mnr_ctx, n: usize, bufs: *const *const mnr_buf, validities: *const *const mnr_bits,
                                   with_minmax: c_int, out: *mut mnr_agg) -> c_int;

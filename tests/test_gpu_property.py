@@ -120,3 +120,6 @@ def test_bitmask_random_windows(gpu_ctx, nbits, ao, bo, op, seed):
     assert np.array_equal(dev.bits_slice(gpu_ctx, X, ao, nbits).download().bits, np.packbits(x[ao:ao + nbits], bitorder="little"))
     w = (ao // 64) * 64
     assert dev.bits_popcount(gpu_ctx, X, w, nbits) == orc.popcount_mask((ox, w, nbits))
+    cnt = mnr.DeviceBuffer.alloc(gpu_ctx, np.uint64, 1)                   # asynchronous form: count stays on the device
+    dev.bits_popcount_async(gpu_ctx, X, w, nbits, cnt.device_ptr)
+    assert int(cnt.download()[0]) == orc.popcount_mask((ox, w, nbits))
