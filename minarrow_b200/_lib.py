@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libminarrow_b200.so")
+LIB_PATH = os.environ.get("MINARROW_B200_LIB") or os.path.join(_HERE, "libminarrow_b200.so")   # override: tuning builds
 
 c_ctx = C.c_void_p
 c_buf = C.c_void_p

@@ -13,15 +13,21 @@ namespace mnr {
 
 #if MNR_EW_DTYPE == 100
 int g_ew_grid_cap = 0;   // >0: cap every element-wise grid at this many blocks (tuning knob, mnr_ctx_set_option)
+int g_ew_max_tier = 2;   // 1: never use the 256-bit tier (tuning knob)
 #else
 extern int g_ew_grid_cap;
+extern int g_ew_max_tier;
 #endif
 
-struct CfgCheap { static constexpr int BLOCK = 128, U = 4, MINB = 4; static constexpr bool RESIDENT = false; using Wide = V32; };
+// MINB = 4 caps the kernel at 128 registers (4 blocks/SM).  1-byte columns carry the packed SIMD-in-register path (~150
+// registers uncapped) and gain from the cap; 4/8-byte kernels fit 128 registers on their own, the cap only matters for
+// their batched variants (C5 scalar broadcast 6.30 -> 6.77 TB/s, r01j -> r01s); 2-byte columns LOSE with it (r01v:
+// two-mask add 7.07 TB/s uncapped, 5.0 capped), so they stay uncapped.
+template <int ESZ> struct CfgCheap { static constexpr int BLOCK = 128, U = 4, MINB = ESZ == 2 ? 1 : 4; static constexpr bool RESIDENT = false; using Wide = V32; };
 struct CfgHeavy { static constexpr int BLOCK = 256, U = 2, MINB = 4; static constexpr bool RESIDENT = true; using Wide = V16; };
-template <int CLS> struct CfgOf { using type = CfgHeavy; };
-template <> struct CfgOf<CLS_CHEAP> { using type = CfgCheap; };
-template <> struct CfgOf<CLS_SDIV> { using type = CfgCheap; };   // a multiply-high per row: memory-bound like add
+template <int CLS, int ESZ> struct CfgOf { using type = CfgHeavy; };
+template <int ESZ> struct CfgOf<CLS_CHEAP, ESZ> { using type = CfgCheap<ESZ>; };
+template <int ESZ> struct CfgOf<CLS_SDIV, ESZ> { using type = CfgCheap<ESZ>; };   // a multiply-high per row: memory-bound like add
 
 static EwDev to_dev(const EwArgs& a) {
     EwDev d;
@@ -45,7 +51,7 @@ static unsigned ew_grid(uint64_t n, int vec) {
 
 template <typename T, typename TL, typename TR, typename VecT, int CLS>
 static cudaError_t go(const EwArgs& a, cudaStream_t s) {
-    using Cfg = typename CfgOf<CLS>::type;
+    using Cfg = typename CfgOf<CLS, (int)sizeof(T)>::type;
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     const bool masked = a.lmask || a.rmask;
     const unsigned grid = ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(a.n, VEC);
@@ -56,7 +62,7 @@ static cudaError_t go(const EwArgs& a, cudaStream_t s) {
 
 template <typename T, typename VecT, int CLS>
 static cudaError_t go_batch(bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
-    using Cfg = typename CfgOf<CLS>::type;
+    using Cfg = typename CfgOf<CLS, (int)sizeof(T)>::type;
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     const dim3 grid(ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(max_n, VEC), nseg, 1);
     if (masked) ew_binary_batch_kernel<T, T, T, VecT, CLS, true, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(segs);
@@ -67,7 +73,7 @@ static cudaError_t go_batch(bool masked, const EwDev* segs, uint32_t nseg, uint6
 // tier 2 = the class's wide vector (256-bit for cheap ops), tier 1 = 128-bit.  Unaligned items are launched one by one.
 template <typename T, int CLS>
 static cudaError_t go_batch_tier(int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
-    using Wide = typename CfgOf<CLS>::type::Wide;
+    using Wide = typename CfgOf<CLS, (int)sizeof(T)>::type::Wide;
     if (tier == 2) return go_batch<T, Wide, CLS>(masked, segs, nseg, max_n, s);
     return go_batch<T, V16, CLS>(masked, segs, nseg, max_n, s);
 }
@@ -92,10 +98,10 @@ static cudaError_t go_batch_t(int op, int tier, bool masked, bool sdiv, const Ew
 // widest vector every operand pointer allows, else 128-bit, else element-wise loads.
 template <typename T, typename TL, typename TR, int CLS>
 static cudaError_t go_align(const EwArgs& a, cudaStream_t s) {
-    using Wide = typename CfgOf<CLS>::type::Wide;
+    using Wide = typename CfgOf<CLS, (int)sizeof(T)>::type::Wide;
     auto ok = [](const void* p, size_t align) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % align) == 0; };
     constexpr int VW = sizeof(Wide) / sizeof(T);
-    if (sizeof(Wide) > 16 && ok(a.lhs, sizeof(TL) * VW) && ok(a.rhs, sizeof(TR) * VW) && ok(a.out, sizeof(Wide)))
+    if (sizeof(Wide) > 16 && g_ew_max_tier >= 2 && ok(a.lhs, sizeof(TL) * VW) && ok(a.rhs, sizeof(TR) * VW) && ok(a.out, sizeof(Wide)))
         return go<T, TL, TR, Wide, CLS>(a, s);
     constexpr int V = 16 / sizeof(T);
     if (ok(a.lhs, sizeof(TL) * V) && ok(a.rhs, sizeof(TR) * V) && ok(a.out, 16)) return go<T, TL, TR, V16, CLS>(a, s);

@@ -120,13 +120,21 @@ template <int ESZ, int OP> __device__ __forceinline__ uint32_t packed_cheap_word
     }
 }
 // One vector (NW words) with the operator fixed at compile time; `bits` = validity of the vector's elements.
+// (a / b are register arrays: the scalar side is chosen per VALUE with has_a / has_b — choosing between POINTERS would force
+// the arrays into local memory, ncu r01w: 64 LDL per tile and 60 % DRAM utilisation.)
 template <int ESZ, int OP, bool MASKED, int NW>
-__device__ __forceinline__ void packed_cheap_vec(const uint32_t* a, const uint32_t* b, uint32_t sword, uint32_t bits, uint32_t* o) {
+__device__ __forceinline__ void packed_cheap_vec(const uint32_t (&a)[NW], bool has_a, const uint32_t (&b)[NW], bool has_b, uint32_t sword,
+                                                 uint32_t bits, uint32_t (&o)[NW]) {
     constexpr int EPW = 4 / ESZ;
+    uint32_t even = 0, odd = 0;   // 1-byte elements: nibble planes of the validity word, one PRMT per word picks nibble j
+    if constexpr (MASKED && ESZ == 1) { even = bits & 0x0F0F0F0Fu; odd = (bits >> 4) & 0x0F0F0F0Fu; }
 #pragma unroll
     for (int j = 0; j < NW; ++j) {
-        uint32_t r = packed_cheap_word<ESZ, OP>(a ? a[j] : sword, b ? b[j] : sword);
-        if constexpr (MASKED) r &= expand_valid_word<ESZ>(bits >> (j * EPW));
+        uint32_t r = packed_cheap_word<ESZ, OP>(has_a ? a[j] : sword, has_b ? b[j] : sword);
+        if constexpr (MASKED) {
+            if constexpr (ESZ == 1) r &= ((__byte_perm((j & 1) ? odd : even, 0u, 0x4440u | (uint32_t)(j >> 1)) * 0x00204081u) & 0x01010101u) * 0xFFu;
+            else r &= expand_valid_word<ESZ>(bits >> (j * EPW));
+        }
         o[j] = r;
     }
 }
@@ -205,6 +213,13 @@ template <typename T> __device__ __forceinline__ T scalar_from_bits(uint64_t b) 
 template <int VEC, bool GUARD>
 __device__ __forceinline__ uint32_t merged_bits(const EwDev& a, uint64_t row0) {
     uint32_t m;
+    if constexpr (VEC == 32 && !GUARD) {
+        // 1-byte elements, two masks: one loop-invariant test of both base pointers instead of an alignment test per load
+        if (a.lmask && a.rmask && ((reinterpret_cast<uintptr_t>(a.lmask) | reinterpret_cast<uintptr_t>(a.rmask)) & 3u) == 0) {
+            const uint32_t x = ldg_u32(a.lmask + (row0 >> 3)), y = ldg_u32(a.rmask + (row0 >> 3));
+            return a.mask_or ? (x | y) : (x & y);
+        }
+    }
     if (a.lmask && a.rmask) {
         const uint32_t x = GUARD ? load_valid_bits_guard<VEC>(a.lmask, row0, a.n) : load_valid_bits<VEC>(a.lmask, row0);
         const uint32_t y = GUARD ? load_valid_bits_guard<VEC>(a.rmask, row0, a.n) : load_valid_bits<VEC>(a.rmask, row0);
@@ -269,14 +284,13 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
                 // is the merged input validity and the values of invalid rows are cleared with the expanded mask.
                 constexpr int NW = sizeof(VecT) / 4;
                 union { VecT v; uint32_t w[NW]; } PL, PR, PO;
-                if (lp) memcpy(&PL.v, &L[u].v, sizeof(VecT));
-                if (rp) memcpy(&PR.v, &R[u].v, sizeof(VecT));
-                const uint32_t* pa = lp ? PL.w : nullptr;
-                const uint32_t* pb = rp ? PR.w : nullptr;
+                memcpy(&PL.v, &L[u].v, sizeof(VecT));
+                memcpy(&PR.v, &R[u].v, sizeof(VecT));
+                const bool ha = lp != nullptr, hb = rp != nullptr;
                 const uint32_t vb = MASKED ? mb[u] : 0u;
-                if (op == MNR_ADD) packed_cheap_vec<sizeof(T), MNR_ADD, MASKED, NW>(pa, pb, sword, vb, PO.w);
-                else if (op == MNR_SUB) packed_cheap_vec<sizeof(T), MNR_SUB, MASKED, NW>(pa, pb, sword, vb, PO.w);
-                else packed_cheap_vec<sizeof(T), MNR_MUL, MASKED, NW>(pa, pb, sword, vb, PO.w);
+                if (op == MNR_ADD) packed_cheap_vec<sizeof(T), MNR_ADD, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
+                else if (op == MNR_SUB) packed_cheap_vec<sizeof(T), MNR_SUB, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
+                else packed_cheap_vec<sizeof(T), MNR_MUL, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
                 O.v = PO.v;
                 if constexpr (MASKED) ob = mb[u];
             } else

@@ -203,6 +203,21 @@ template <typename T> struct NarrowState {
 
     // One 32-bit word = EPW elements; `bits` = their validity in the low EPW bits (ignored when !MASKED).
     template <bool MASKED, bool MINMAX> __device__ __forceinline__ void add_word(uint32_t w, uint32_t bits, uint32_t& acc32) {
+        if constexpr (sizeof(T) == 1 && MASKED) {
+            // `bits` is a clean nibble here (accum_vec_packed extracts it with one PRMT).  The sum needs no select at all:
+            // the dot product against the 0/1 byte pattern skips invalid lanes; the 0xFF mask is only built for min/max.
+            const uint32_t s01 = (bits * 0x00204081u) & 0x01010101u;
+            if constexpr (kSigned) acc32 = (uint32_t)__dp4a((int)w, (int)s01, (int)acc32);
+            else acc32 = __dp4a(w, s01, acc32);
+            if constexpr (MINMAX) {
+                const uint32_t m = s01 * 0xFFu;
+                const uint32_t wmn = kSigned ? ((w & m) | (0x7f7f7f7fu & ~m)) : (w | ~m);
+                const uint32_t wmx = kSigned ? ((w & m) | (0x80808080u & ~m)) : (w & m);
+                mn2 = min3(mn2, widen_lo(wmn), widen_hi(wmn));
+                mx2 = max3(mx2, widen_lo(wmx), widen_hi(wmx));
+            }
+            return;
+        }
         uint32_t m = 0xFFFFFFFFu;
         if constexpr (MASKED) m = expand_valid_word<sizeof(T)>(bits);
         const uint32_t wz = w & m;   // invalid lanes -> 0
@@ -253,8 +268,17 @@ __device__ __forceinline__ void accum_vec_packed(const VecT& v, uint32_t bits, N
     union { VecT v; uint32_t w[NW]; } u;
     u.v = v;
     uint32_t acc32 = 0;
+    if constexpr (sizeof(T) == 1 && MASKED) {
+        // nibble j of `bits` = byte j/2 of the even- or odd-nibble plane: two ops per vector + one PRMT per word
+        // (a shift + mask per word would be two ALU ops; this path is ALU-bound)
+        const uint32_t even = bits & 0x0F0F0F0Fu, odd = (bits >> 4) & 0x0F0F0F0Fu;
 #pragma unroll
-    for (int j = 0; j < NW; ++j) ns.template add_word<MASKED, MINMAX>(u.w[j], MASKED ? (bits >> (j * EPW)) : 0u, acc32);
+        for (int j = 0; j < NW; ++j)
+            ns.template add_word<MASKED, MINMAX>(u.w[j], __byte_perm((j & 1) ? odd : even, 0u, 0x4440u | (uint32_t)(j >> 1)), acc32);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) ns.template add_word<MASKED, MINMAX>(u.w[j], MASKED ? (bits >> (j * EPW)) : 0u, acc32);
+    }
     ns.fold(acc32);
     if constexpr (MASKED) cnt += (uint64_t)__popc(bits);
 }

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--gib", type=float, default=1.0)
     ap.add_argument("--out", default="")
     ap.add_argument("--only", default="")
+    ap.add_argument("--dtypes", default="", help="comma-separated numpy dtype names (default: all ten)")
     args = ap.parse_args()
 
     import numpy as np
@@ -72,6 +73,8 @@ def main():
 
     part = torch.zeros(4, dtype=torch.int64, device=dev)
     for name in ("int8", "uint8", "int16", "uint16", "int32", "uint32", "int64", "uint64", "float32", "float64"):
+        if args.dtypes and name not in args.dtypes.split(","):
+            continue
         sz = np.dtype(name).itemsize
         n = int(args.gib * (1 << 30)) // sz
         n -= n % 64
