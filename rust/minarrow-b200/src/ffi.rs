@@ -47,6 +47,15 @@ extern "C" {
                                   with_minmax: c_int, out: *mut mnr_agg) -> c_int;
     pub fn mnr_agg_mean(dtype: c_int, agg: *const mnr_agg) -> f64;
 
+    // SuperArray chunks: consolidate / rechunk on the device, and shards fed straight from the reference's own Arrow C
+    // stream export (`stream` = *mut minarrow::ffi::arrow_c_ffi::ArrowArrayStream, src/ffi/arrow_c_ffi.rs:153-168)
+    pub fn mnr_concat(ctx: *mut mnr_ctx, n: usize, bufs: *const *const mnr_buf, validities: *const *const mnr_bits,
+                      out: *mut *mut mnr_buf, out_validity: *mut *mut mnr_bits) -> c_int;
+    pub fn mnr_bits_slice(ctx: *mut mnr_ctx, src: *const mnr_bits, offset: usize, len: usize, out: *mut *mut mnr_bits) -> c_int;
+    pub fn mnr_arrow_stream_import(ctx: *mut mnr_ctx, stream: *mut c_void, chunk_lo: usize, chunk_hi: usize, capacity: usize,
+                                   values: *mut *mut mnr_buf, validity: *mut *mut mnr_bits, n_imported: *mut usize,
+                                   n_seen: *mut usize) -> c_int;
+
     // host-slice drop-ins: the reference leaf signatures (src/kernels/arithmetic/dispatch.rs:74-79,147-152)
     pub fn mnr_apply_int_i32(ctx: *mut mnr_ctx, lhs: *const i32, lhs_len: usize, rhs: *const i32, rhs_len: usize, op: c_int,
                              mask: *const u8, out: *mut i32, out_mask: *mut u8) -> c_int;
