@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "divmagic.h"
+#include "fastmod.h"
 #include "internal.h"
 
 namespace mnr {
@@ -31,6 +32,28 @@ __host__ __device__ constexpr int op_class(bool is_float, int op) {
 }
 
 // ---- one element ---------------------------------------------------------------------------------------
+// Truncating quotient of two 8/16-bit integers (r != 0) through the f32 pipe.  The compiler's `/` on the promoted ints
+// is the generic 32-bit routine (~30 instructions: two conversions, a reciprocal, two correction steps); operands below
+// 2^16 need none of the corrections:  uq = trunc((|l| + 0.5) * rcp(|r|)).  With t' = (|l| + 0.5) / |r|, both
+// t' - floor(|l| / |r|) and floor(|l| / |r|) + 1 - t' are >= 0.5 / |r|, while the computed product is off by less than
+// t' * 2^-21 <= 2^-5 / |r| (MUFU.RCP: 1 ulp, one rounding in the multiply) — the truncation can not cross an integer.
+// int -> float and float -> int go through the 2^23 exponent trick (LOP3 + FADD, FADD.RZ + LOP3): only the reciprocal
+// uses the quarter-rate conversion/transcendental pipe.  MIN / -1 comes out as 2^(bits-1), which wraps to MIN in the
+// caller's cast (the same wrapped quotient as the wide types).  Exhaustive check: tests/test_gpu_narrow_division.py.
+template <bool SIGNED> __device__ __forceinline__ int narrow_quot(int l, int r) {
+    const uint32_t al = SIGNED ? (uint32_t)abs(l) : (uint32_t)l, ar = SIGNED ? (uint32_t)abs(r) : (uint32_t)r;
+    const float fa = __fsub_rn(__uint_as_float(0x4B000000u | al), 8388607.5f);   // |l| + 0.5, exact
+    const float fb = __fsub_rn(__uint_as_float(0x4B000000u | ar), 8388608.0f);   // |r|, exact
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fb));
+    const uint32_t uq = __float_as_uint(__fadd_rz(__fmul_rn(fa, rc), 8388608.0f)) & 0x007FFFFFu;
+    if constexpr (SIGNED) {
+        const uint32_t s = (uint32_t)((l ^ r) >> 31);
+        return (int)((uq ^ s) - s);
+    }
+    return (int)uq;
+}
+
 // Integers: Add/Sub/Mul wrap; Div/Rem truncate, FloorDiv per std.rs:68-77; MIN / -1 = MIN and
 // MIN % -1 = 0 (core::simd's guard; DESIGN.md assumption); zero divisor => ok = false, value 0.
 // Power: exponent = rhs.to_u32().unwrap_or(0) (std.rs:67), wrapping repeated multiply (simd.rs:94-100)
@@ -42,6 +65,16 @@ __device__ __forceinline__ T int_elem(int op, T l, T r, bool& ok, const DivMagic
     if constexpr (CLS == CLS_CHEAP) {
         const UT a = (UT)l, b = (UT)r;
         return (T)(UT)(op == MNR_ADD ? a + b : op == MNR_SUB ? a - b : a * b);
+    } else if constexpr ((CLS == CLS_DIV || CLS == CLS_SDIV) && sizeof(T) <= 2) {
+        // 8/16-bit columns: branch-free (a zero divisor flows through as rcp = Inf -> quotient bits 0 and is nulled by `ok`),
+        // in 32-bit registers, narrowed once at the end.  A broadcast divisor (CLS_SDIV: non-zero by construction) takes the
+        // same route — its reciprocal is loop-invariant, which leaves five full-rate instructions per quotient.
+        ok = CLS == CLS_SDIV || r != 0;
+        const int q = narrow_quot<std::is_signed<T>::value>((int)l, (int)r);
+        const int m = (int)l - q * (int)r;
+        int res = op == MNR_DIV ? q : m;
+        if (op == MNR_FLOORDIV) res = (std::is_signed<T>::value && m != 0 && (((int)l ^ (int)r) < 0)) ? q - 1 : q;
+        return ok ? (T)res : (T)0;
     } else if constexpr (CLS == CLS_DIV || CLS == CLS_SDIV) {
         T q;
         if constexpr (CLS == CLS_SDIV) {
@@ -97,7 +130,7 @@ __device__ __forceinline__ T float_elem(int op, T a, T b) {
         const T q = a / b;
         return op == MNR_DIV ? q : floor(q);
     } else if constexpr (CLS == CLS_REM) {
-        return fmod(a, b);
+        return fast_fmod<T>(a, b);   // exact like fmod; the libm loop only for NaN / Inf / zero divisors / huge quotients
     } else {
         return exp(b * log(a));
     }

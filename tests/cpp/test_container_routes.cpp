@@ -1,0 +1,198 @@
+// The reference's router / container-route tests, transcribed into C++ against include/minarrow_b200_containers.hpp
+// (same function names, argument order and expectations) and run on the GPU through the C ABI.
+//
+//   src/kernels/broadcast/super_array.rs:480-524  array + scalar, scalar + array, array + array
+//   src/kernels/broadcast/super_array.rs:526-594  SuperArray add, chunk length mismatch
+//   src/kernels/broadcast/super_array.rs:596-672,721-763  route_super_array_broadcast multiply / divide / subtract
+//   src/kernels/broadcast/table.rs:432-566        table + table, column count mismatch, multiply, table op array / scalar
+//   src/kernels/broadcast/super_table.rs:684-887  SuperTable add / subtract / chunk count mismatch / three batches
+//   src/kernels/routing/arithmetic.rs:244-269,342-373  i32 (op) f64 / f32 promotion; :403 unsupported pairs
+//   examples/arithmetic.rs:19-58                  [10,20,30] (op) [2,4,6]
+// plus what the reference leaves to the caller and this layer fuses: per-chunk validity union, windows, null-aware
+// aggregates over chunks.
+//
+// Usage: test_container_routes            run on cuda:0 (exit code = number of failed checks)
+//        test_container_routes --link     only prove that the binary links and the library loads (no GPU needed)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "minarrow_b200_containers.hpp"
+
+using namespace minarrow_b200;
+using Op = ArithmeticOperator;
+
+static int g_failed = 0, g_checks = 0;
+#define CHECK(cond)                                                                     \
+    do {                                                                                \
+        ++g_checks;                                                                     \
+        if (!(cond)) { ++g_failed; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); } \
+    } while (0)
+
+template <class T> static bool is(const Array& a, std::initializer_list<T> exp) {
+    const auto* v = a.values<T>();
+    return v && v->size() == exp.size() && std::equal(v->begin(), v->end(), exp.begin());
+}
+template <class F> static std::string error_kind(F f, std::string* msg = nullptr) {
+    try { f(); } catch (const KernelError& e) { if (msg) *msg = e.what(); return e.kind; }
+    return "";
+}
+static Array i32(std::initializer_list<int32_t> v, const Bitmask* m = nullptr) { return Array::from_slice<int32_t>(v, m); }
+static Table create_test_table(const char* name, std::initializer_list<int32_t> c1, std::initializer_list<int32_t> c2) {   // table.rs:415-429
+    return Table(name, {i32(c1), i32(c2)});
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && !std::strcmp(argv[1], "--link")) {
+        std::printf("abi %d, %d CUDA device(s)\n", mnr_abi_version(), mnr_device_count());
+        return 0;
+    }
+    try {
+        Context& ctx = Context::thread_default();
+        {   // super_array.rs:480-524
+            CHECK(is<int32_t>(broadcast_array_add(ArrayV(i32({1, 2, 3}), 0, 3), ArrayV(i32({5}), 0, 1)), {6, 7, 8}));
+            CHECK(is<int32_t>(broadcast_array_add(ArrayV(i32({5}), 0, 1), ArrayV(i32({1, 2, 3}), 0, 3)), {6, 7, 8}));
+            CHECK(is<int32_t>(broadcast_array_add(ArrayV(i32({1, 2, 3}), 0, 3), ArrayV(i32({4, 5, 6}), 0, 3)), {5, 7, 9}));
+        }
+        {   // examples/arithmetic.rs:19-58
+            Array a = i32({10, 20, 30}), b = i32({2, 4, 6});
+            CHECK(is<int32_t>(resolve_binary_arithmetic(Op::Add, a, b), {12, 24, 36}));
+            CHECK(is<int32_t>(resolve_binary_arithmetic(Op::Subtract, a, b), {8, 16, 24}));
+            CHECK(is<int32_t>(resolve_binary_arithmetic(Op::Multiply, a, b), {20, 80, 180}));
+            CHECK(is<int32_t>(resolve_binary_arithmetic(Op::Divide, a, b), {5, 5, 5}));
+            CHECK(is<int32_t>(resolve_binary_arithmetic(Op::Remainder, a, i32({3, 7, 4})), {1, 6, 2}));
+            // operand order with a length-1 side; windows
+            CHECK(is<int32_t>(resolve_binary_arithmetic(Op::Subtract, i32({100}), a), {90, 80, 70}));
+            CHECK(is<int32_t>(resolve_binary_arithmetic(Op::Divide, a, i32({10})), {1, 2, 3}));
+            Array w = i32({0, 1, 2, 3, 4, 5, 6, 7});
+            CHECK(is<int32_t>(resolve_binary_arithmetic(Op::Multiply, ArrayV(w, 2, 3), ArrayV(w, 5, 3)), {10, 18, 28}));
+            // the leaf API's single mask: null rows are zeroed, integer / 0 under a mask is a null, without one the reference panics
+            Bitmask m = Bitmask::from_bools({true, false, true});
+            Array r = resolve_binary_arithmetic(Op::Divide, a, i32({2, 4, 0}), &m);
+            CHECK(is<int32_t>(r, {5, 0, 0}) && r.null_mask() && r.null_mask()->get(0) && !r.null_mask()->get(1) && !r.null_mask()->get(2));
+            CHECK(error_kind([&] { resolve_binary_arithmetic(Op::Divide, a, i32({2, 4, 0})); }) == "DivideByZero");
+            CHECK(error_kind([&] { resolve_binary_arithmetic(Op::Add, a, i32({1, 2})); }) == "LengthMismatch");
+        }
+        {   // routing/arithmetic.rs:342-373 promotion; :403 unsupported pairs
+            Array f = Array::from_slice<double>({0.5, 1.5, 2.5}), g = Array::from_slice<float>({0.5f, 1.5f, 2.5f});
+            CHECK(is<double>(resolve_binary_arithmetic(Op::Add, i32({1, 2, 3}), f), {1.5, 3.5, 5.5}));
+            CHECK(is<double>(resolve_binary_arithmetic(Op::Subtract, f, i32({1, 2, 3})), {-0.5, -0.5, -0.5}));
+            CHECK(is<float>(resolve_binary_arithmetic(Op::Multiply, i32({2, 2, 2}), g), {1.0f, 3.0f, 5.0f}));
+            CHECK(is<double>(resolve_binary_arithmetic(Op::Multiply, i32({1, 2, 3}), Array::from_slice<double>({2.0})), {2.0, 4.0, 6.0}));
+            CHECK(is<double>(resolve_binary_arithmetic(Op::Subtract, i32({10}), f), {9.5, 8.5, 7.5}));
+            CHECK(error_kind([&] { resolve_binary_arithmetic(Op::Add, Array::from_slice<int64_t>({1, 2, 3}), f); }) == "UnsupportedType");
+            CHECK(error_kind([&] { resolve_binary_arithmetic(Op::Add, Array::from_slice<int64_t>({1, 2, 3}), i32({1, 2, 3})); }) == "UnsupportedType");
+            CHECK(is<uint64_t>(resolve_binary_arithmetic(Op::Subtract, Array::from_slice<uint64_t>({0}), Array::from_slice<uint64_t>({1})), {UINT64_MAX}));   // wraps
+        }
+        {   // super_array.rs:526-594
+            SuperArray s1 = SuperArray::from_chunks({i32({1, 2, 3}), i32({4, 5, 6})});
+            SuperArray s2 = SuperArray::from_chunks({i32({10, 10, 10}), i32({20, 20, 20})});
+            SuperArray r = broadcast_super_array_add(s1, s2);
+            CHECK(r.chunks().size() == 2 && is<int32_t>(r.chunks()[0], {11, 12, 13}) && is<int32_t>(r.chunks()[1], {24, 25, 26}));
+            std::string msg;
+            const std::string kind = error_kind([&] { broadcast_super_array_add(SuperArray::from_chunks({i32({1, 2, 3})}), SuperArray::from_chunks({i32({10, 10})})); }, &msg);
+            CHECK(kind == "ShapeError" && msg.find("Super Array broadcasting error") != std::string::npos);
+        }
+        {   // super_array.rs:596-672, 721-763
+            SuperArray a = SuperArray::from_chunks({i32({2, 3, 4}), i32({5, 6, 7})}), b = SuperArray::from_chunks({i32({10, 10, 10}), i32({2, 2, 2})});
+            SuperArray r = route_super_array_broadcast(Op::Multiply, a, b);
+            CHECK(is<int32_t>(r.chunks()[0], {20, 30, 40}) && is<int32_t>(r.chunks()[1], {10, 12, 14}));
+            r = route_super_array_broadcast(Op::Divide, SuperArray::from_chunks({i32({100, 200, 300})}), SuperArray::from_chunks({i32({10, 20, 30})}));
+            CHECK(is<int32_t>(r.chunks()[0], {10, 10, 10}));
+            r = route_super_array_broadcast(Op::Subtract, SuperArray::from_chunks({i32({10, 20, 30}), i32({100, 200, 300})}),
+                                            SuperArray::from_chunks({i32({1, 2, 3}), i32({10, 20, 30})}));
+            CHECK(is<int32_t>(r.chunks()[0], {9, 18, 27}) && is<int32_t>(r.chunks()[1], {90, 180, 270}));
+        }
+        {   // per-chunk validity (super_array.rs:214-230): union of both masks, the one that exists, or the override
+            Bitmask ml = Bitmask::from_bools({true, false, false}), mr = Bitmask::from_bools({false, false, true});
+            SuperArray a = SuperArray::from_chunks({i32({1, 2, 3}, &ml), i32({4, 5, 6}, &ml), i32({7, 8, 9})});
+            SuperArray b = SuperArray::from_chunks({i32({10, 20, 30}, &mr), i32({40, 50, 60}), i32({70, 80, 90})});
+            SuperArray r = route_super_array_broadcast(Op::Add, a, b);
+            CHECK(is<int32_t>(r.chunks()[0], {11, 0, 33}) && r.chunks()[0].null_mask() && r.chunks()[0].null_mask()->to_bools() == std::vector<bool>({true, false, true}));
+            CHECK(is<int32_t>(r.chunks()[1], {44, 0, 0}) && r.chunks()[1].null_mask()->to_bools() == std::vector<bool>({true, false, false}));
+            CHECK(is<int32_t>(r.chunks()[2], {77, 88, 99}) && !r.chunks()[2].null_mask());
+            Bitmask ov = Bitmask::from_bools({false, true, true});
+            r = route_super_array_broadcast(Op::Add, a, b, &ov);
+            CHECK(is<int32_t>(r.chunks()[0], {0, 22, 33}) && is<int32_t>(r.chunks()[2], {0, 88, 99}) && r.chunks()[2].null_mask()->null_count() == 1);
+            // chunks of different dtypes in one SuperArray pair: one launch per dtype class
+            SuperArray c = SuperArray::from_chunks({i32({1, 2}), Array::from_slice<double>({0.5, 0.25})});
+            SuperArray d = SuperArray::from_chunks({i32({3, 4}), Array::from_slice<double>({2.0, 4.0})});
+            r = route_super_array_broadcast(Op::Multiply, c, d);
+            CHECK(is<int32_t>(r.chunks()[0], {3, 8}) && is<double>(r.chunks()[1], {1.0, 1.0}));
+        }
+        {   // chunked null-aware aggregates (benchmark_parallel_simd.rs:81-97 shape): 37 ragged chunks of 0..N
+            // odd chunks carry a mask (row valid iff its value is not a multiple of 3), even chunks are dense
+            std::vector<Array> chunks;
+            int64_t next = 0, expect_sum = 0, expect_count = 0;
+            for (int c = 0; c < 37; ++c) {
+                IntegerArray<int64_t> a;
+                a.data.resize(1000 + 37 * (size_t)c);
+                Bitmask m = Bitmask::new_set_all(a.data.size(), false);
+                for (size_t i = 0; i < a.data.size(); ++i, ++next) {
+                    a.data[i] = next;
+                    const bool valid = !(c & 1) || next % 3 != 0;
+                    if (next % 3 != 0) m.bits[i >> 3] |= uint8_t(1u << (i & 7));
+                    if (valid) { expect_sum += next; ++expect_count; }
+                }
+                if (c & 1) a.null_mask = m;
+                chunks.push_back(Array(std::move(a)));
+            }
+            SuperArray s = SuperArray::from_chunks(std::move(chunks));
+            mnr_agg a = super_array_stats(s);
+            CHECK(a.sum.i64 == expect_sum && (int64_t)a.count == expect_count && a.min.i64 == 0 && a.max.i64 == next - 1);
+        }
+        {   // table.rs:432-566
+            Table t1 = create_test_table("table1", {1, 2, 3}, {10, 20, 30}), t2 = create_test_table("table2", {4, 5, 6}, {40, 50, 60});
+            Table r = broadcast_table_add(t1, t2);
+            CHECK(r.n_cols() == 2 && r.n_rows() == 3 && r.name == "table1");
+            CHECK(r.col_ix(0) && is<int32_t>(*r.col_ix(0), {5, 7, 9}) && is<int32_t>(*r.col_ix(1), {50, 70, 90}));
+            std::string msg;
+            CHECK(error_kind([&] { broadcast_table_add(Table("table1", {i32({1, 2, 3})}), t2); }, &msg) == "ShapeError" && msg.find("column count mismatch") != std::string::npos);
+            CHECK(error_kind([&] { broadcast_table_add(create_test_table("table1", {1, 2}, {10, 20}), t2); }) == "LengthMismatch");   // "row count mismatch" panic
+            r = broadcast_table_with_operator(Op::Multiply, create_test_table("table1", {2, 3, 4}, {5, 6, 7}), create_test_table("table2", {10, 10, 10}, {2, 2, 2}));
+            CHECK(is<int32_t>(r.cols[0], {20, 30, 40}) && is<int32_t>(r.cols[1], {10, 12, 14}));
+            Table t = create_test_table("table1", {10, 20, 30}, {100, 200, 300});
+            r = broadcast_table_to_array(Op::Add, t, i32({1, 2, 3}));
+            CHECK(is<int32_t>(r.cols[0], {11, 22, 33}) && is<int32_t>(r.cols[1], {101, 202, 303}));
+            r = broadcast_table_to_scalar<int32_t>(Op::Multiply, t, 5);
+            CHECK(is<int32_t>(r.cols[0], {50, 100, 150}) && is<int32_t>(r.cols[1], {500, 1000, 1500}));
+            r = broadcast_scalar_to_table<int32_t>(Op::Subtract, 1000, t);
+            CHECK(is<int32_t>(r.cols[0], {990, 980, 970}) && is<int32_t>(r.cols[1], {900, 800, 700}));
+            CHECK(error_kind([&] { broadcast_table_to_scalar<double>(Op::Multiply, Table("t", {Array::from_slice<int64_t>({1, 2})}), 2.5); }) == "UnsupportedType");
+        }
+        {   // super_table.rs:684-887
+            SuperTable l = SuperTable::from_batches({create_test_table("batch1", {1, 2, 3}, {10, 20, 30}), create_test_table("batch2", {4, 5, 6}, {40, 50, 60})});
+            SuperTable r = SuperTable::from_batches({create_test_table("batch1", {1, 1, 1}, {5, 5, 5}), create_test_table("batch2", {2, 2, 2}, {10, 10, 10})});
+            SuperTable o = broadcast_super_table_with_operator(Op::Add, l, r);
+            CHECK(o.n_batches() == 2 && o.n_rows() == 6 && o.n_cols() == 2);
+            CHECK(is<int32_t>(o.batches[0]->cols[0], {2, 3, 4}) && is<int32_t>(o.batches[1]->cols[0], {6, 7, 8}) && is<int32_t>(o.batches[1]->cols[1], {50, 60, 70}));
+            o = broadcast_super_table_with_operator(Op::Subtract, SuperTable::from_batches({create_test_table("batch1", {10, 20, 30}, {100, 200, 300})}),
+                                                    SuperTable::from_batches({create_test_table("batch1", {1, 2, 3}, {10, 20, 30})}));
+            CHECK(o.n_batches() == 1 && is<int32_t>(o.batches[0]->cols[0], {9, 18, 27}) && is<int32_t>(o.batches[0]->cols[1], {90, 180, 270}));
+            o = broadcast_super_table_with_operator(Op::Multiply, SuperTable::from_batches({create_test_table("b", {2, 3, 4}, {5, 6, 7})}),
+                                                    SuperTable::from_batches({create_test_table("b", {10, 10, 10}, {2, 2, 2})}));
+            CHECK(is<int32_t>(o.batches[0]->cols[0], {20, 30, 40}) && is<int32_t>(o.batches[0]->cols[1], {10, 12, 14}));
+            o = broadcast_super_table_with_operator(Op::Divide, SuperTable::from_batches({create_test_table("b", {100, 200, 300}, {1000, 2000, 3000})}),
+                                                    SuperTable::from_batches({create_test_table("b", {10, 20, 30}, {100, 200, 300})}));
+            CHECK(is<int32_t>(o.batches[0]->cols[0], {10, 10, 10}) && is<int32_t>(o.batches[0]->cols[1], {10, 10, 10}));
+            std::string msg;
+            CHECK(error_kind([&] { broadcast_super_table_with_operator(Op::Add, SuperTable::from_batches({create_test_table("batch1", {1, 2, 3}, {10, 20, 30})}), r); }, &msg) == "ShapeError" &&
+                  msg.find("chunk count mismatch") != std::string::npos);
+            SuperTable l3 = SuperTable::from_batches({create_test_table("batch1", {1, 2, 3}, {10, 20, 30}), create_test_table("batch2", {4, 5, 6}, {40, 50, 60}),
+                                                      create_test_table("batch3", {7, 8, 9}, {70, 80, 90})});
+            SuperTable r3 = SuperTable::from_batches({create_test_table("batch1", {1, 1, 1}, {1, 1, 1}), create_test_table("batch2", {2, 2, 2}, {2, 2, 2}),
+                                                      create_test_table("batch3", {3, 3, 3}, {3, 3, 3})});
+            o = broadcast_super_table_with_operator(Op::Add, l3, r3);
+            CHECK(o.n_batches() == 3 && o.n_rows() == 9);
+            CHECK(is<int32_t>(o.batches[0]->cols[0], {2, 3, 4}) && is<int32_t>(o.batches[1]->cols[0], {6, 7, 8}) && is<int32_t>(o.batches[2]->cols[0], {10, 11, 12}));
+            o = broadcast_super_table_to_scalar<int32_t>(Op::Add, l3, 100);
+            CHECK(is<int32_t>(o.batches[2]->cols[1], {170, 180, 190}));
+        }
+        std::printf("%d checks, %d failed, %llu kernel launches\n", g_checks, g_failed, (unsigned long long)ctx.launch_count());
+    } catch (const std::exception& e) {
+        std::printf("EXCEPTION %s\n", e.what());
+        return 99;
+    }
+    return g_failed;
+}

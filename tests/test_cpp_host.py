@@ -9,22 +9,46 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "test_reference_kats.cpp")
 EXE = os.path.join(ROOT, "tests", "cpp", "test_reference_kats")
+ROUTES_SRC = os.path.join(ROOT, "tests", "cpp", "test_container_routes.cpp")
+ROUTES_EXE = os.path.join(ROOT, "tests", "cpp", "test_container_routes")
+
+
+def _build(src, exe):
+    lib = os.path.join(ROOT, "minarrow_b200", "libminarrow_b200.so")
+    deps = [src, lib] + [os.path.join(ROOT, "include", h) for h in ("minarrow_b200.hpp", "minarrow_b200_containers.hpp", "minarrow_b200.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        # $ORIGIN-relative rpath: the binary finds the library wherever the repo is copied (the GPU box uses another path)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), src,
+                               "-L" + os.path.join(ROOT, "minarrow_b200"), "-lminarrow_b200",
+                               "-Wl,-rpath,$ORIGIN/../../minarrow_b200", "-o", exe])
+    return exe
 
 
 def build_cpp():
-    lib = os.path.join(ROOT, "minarrow_b200", "libminarrow_b200.so")
-    deps = [SRC, os.path.join(ROOT, "include", "minarrow_b200.hpp"), os.path.join(ROOT, "include", "minarrow_b200.h"), lib]
-    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), SRC,
-                               "-L" + os.path.join(ROOT, "minarrow_b200"), "-lminarrow_b200",
-                               "-Wl,-rpath," + os.path.join(ROOT, "minarrow_b200"), "-o", EXE])
-    return EXE
+    _build(ROUTES_SRC, ROUTES_EXE)
+    return _build(SRC, EXE)
 
 
 def test_cpp_host_layer_compiles_links_and_loads():
     exe = build_cpp()
     r = subprocess.run([exe, "--link"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.startswith("abi 1"), r.stdout + r.stderr
+
+
+def test_cpp_container_routes_compile_link_and_load():
+    build_cpp()
+    r = subprocess.run([ROUTES_EXE, "--link"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.startswith("abi 1"), r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_router_and_container_tests_transcribed_to_cpp_pass_on_the_gpu(gpu_ctx):
+    """resolve_binary_arithmetic, route_super_array_broadcast, Table / SuperTable routes: the reference's own tests
+    (broadcast/super_array.rs:480-763, table.rs:432-566, super_table.rs:684-887) against include/minarrow_b200_containers.hpp."""
+    build_cpp()
+    r = subprocess.run([ROUTES_EXE], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " 0 failed" in r.stdout and "kernel launches" in r.stdout, r.stdout[-500:]
 
 
 @pytest.mark.gpu
@@ -46,3 +70,17 @@ def test_division_by_invariant_scalar_arithmetic():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout[-2000:]
     assert r.stdout.count(" 0 failed") == 5, r.stdout
+
+
+def test_float_remainder_fast_path_is_exact():
+    """minarrow_b200/csrc/fastmod.h (one division + one fma instead of the libm loop for float `%`) against libm's
+    fmod / fmodf bit for bit: specials x specials, every exponent distance, exact multiples and their neighbours,
+    subnormals.  Host-only, ~4 s; the device build of the same header is checked in tests/test_gpu_narrow_division.py."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_fastmod.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_fastmod")
+    deps = [src, os.path.join(ROOT, "minarrow_b200", "csrc", "fastmod.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", src, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.count(", 0 failed") == 2, r.stdout
