@@ -18,7 +18,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gib", type=float, default=1.0)
     ap.add_argument("--out", default="")
-    ap.add_argument("--only", default="")
+    ap.add_argument("--only", default="", help="comma-separated substrings of kernel labels to run")
     ap.add_argument("--dtypes", default="", help="comma-separated numpy dtype names (default: all ten)")
     args = ap.parse_args()
 
@@ -63,7 +63,7 @@ def main():
         return t, mnr.DeviceBitmask.wrap(ctx, t.data_ptr(), n, t)
 
     def entry(kernel, dtype, nbytes, fn):
-        if args.only and args.only not in kernel:
+        if args.only and not any(k in kernel for k in args.only.split(",")):
             return
         med, best = event_time_ms(torch, fn, 15)
         gbs = nbytes / med / 1e6
