@@ -37,21 +37,26 @@ __host__ __device__ constexpr int op_class(bool is_float, int op) {
 // 2^16 need none of the corrections:  uq = trunc((|l| + 0.5) * rcp(|r|)).  With t' = (|l| + 0.5) / |r|, both
 // t' - floor(|l| / |r|) and floor(|l| / |r|) + 1 - t' are >= 0.5 / |r|, while the computed product is off by less than
 // t' * 2^-21 <= 2^-5 / |r| (MUFU.RCP: 1 ulp, one rounding in the multiply) — the truncation can not cross an integer.
-// int -> float and float -> int go through the 2^23 exponent trick (LOP3 + FADD, FADD.RZ + LOP3): only the reciprocal
-// uses the quarter-rate conversion/transcendental pipe.  MIN / -1 comes out as 2^(bits-1), which wraps to MIN in the
-// caller's cast (the same wrapped quotient as the wide types).  Exhaustive check: tests/test_gpu_narrow_division.py.
+// int -> float goes through the 2^23 exponent trick (one integer op + FADD); unsigned quotients come back the same way
+// (FADD.RZ + LOP3), signed ones through one truncating conversion.  MIN / -1 comes out as 2^(bits-1), which wraps to MIN
+// in the caller's cast (the same wrapped quotient as the wide types).  Checked over the whole operand domain:
+// tests/test_gpu_narrow_division.py (8-bit, and every multiple boundary of 16-bit), tools/exhaustive_div16.py (all 2^32 pairs).
 template <bool SIGNED> __device__ __forceinline__ int narrow_quot(int l, int r) {
-    const uint32_t al = SIGNED ? (uint32_t)abs(l) : (uint32_t)l, ar = SIGNED ? (uint32_t)abs(r) : (uint32_t)r;
-    const float fa = __fsub_rn(__uint_as_float(0x4B000000u | al), 8388607.5f);   // |l| + 0.5, exact
-    const float fb = __fsub_rn(__uint_as_float(0x4B000000u | ar), 8388608.0f);   // |r|, exact
     float rc;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fb));
-    const uint32_t uq = __float_as_uint(__fadd_rz(__fmul_rn(fa, rc), 8388608.0f)) & 0x007FFFFFu;
     if constexpr (SIGNED) {
-        const uint32_t s = (uint32_t)((l ^ r) >> 31);
-        return (int)((uq ^ s) - s);
+        // Signed operands keep their signs through the float pipe: 1.5 * 2^23 + x is exact for |x| < 2^22, the half is
+        // added away from zero (copysign), and the conversion truncates toward zero — no |x|, no sign restore.
+        const float fa = __fsub_rn(__int_as_float(0x4B400000 + l), 12582912.0f);   // l, exact
+        const float fb = __fsub_rn(__int_as_float(0x4B400000 + r), 12582912.0f);   // r, exact
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fb));
+        return __float2int_rz(__fmul_rn(__fadd_rn(fa, copysignf(0.5f, fa)), rc));    // r = 0: +-Inf saturates, nulled by the caller
+    } else {
+        const uint32_t al = (uint32_t)l, ar = (uint32_t)r;
+        const float fa = __fsub_rn(__uint_as_float(0x4B000000u | al), 8388607.5f);   // l + 0.5, exact
+        const float fb = __fsub_rn(__uint_as_float(0x4B000000u | ar), 8388608.0f);   // r, exact
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fb));
+        return (int)(__float_as_uint(__fadd_rz(__fmul_rn(fa, rc), 8388608.0f)) & 0x007FFFFFu);
     }
-    return (int)uq;
 }
 
 // Integers: Add/Sub/Mul wrap; Div/Rem truncate, FloorDiv per std.rs:68-77; MIN / -1 = MIN and
@@ -65,10 +70,12 @@ __device__ __forceinline__ T int_elem(int op, T l, T r, bool& ok, const DivMagic
     if constexpr (CLS == CLS_CHEAP) {
         const UT a = (UT)l, b = (UT)r;
         return (T)(UT)(op == MNR_ADD ? a + b : op == MNR_SUB ? a - b : a * b);
-    } else if constexpr ((CLS == CLS_DIV || CLS == CLS_SDIV) && sizeof(T) <= 2) {
+    } else if constexpr ((CLS == CLS_DIV || (CLS == CLS_SDIV && !std::is_signed<T>::value)) && sizeof(T) <= 2) {
         // 8/16-bit columns: branch-free (a zero divisor flows through as rcp = Inf -> quotient bits 0 and is nulled by `ok`),
-        // in 32-bit registers, narrowed once at the end.  A broadcast divisor (CLS_SDIV: non-zero by construction) takes the
-        // same route — its reciprocal is loop-invariant, which leaves five full-rate instructions per quotient.
+        // in 32-bit registers, narrowed once at the end.  An UNSIGNED broadcast divisor (CLS_SDIV: non-zero by construction)
+        // takes the same route — its reciprocal is loop-invariant, five full-rate instructions per quotient (r01y: u8 1.85 ->
+        // 2.48 TB/s, u16 3.35 -> 3.60).  A signed one keeps the multiplicative inverse below: the |l| / sign-restore steps
+        // cost more than the high multiply they replace (r01y: i16 3.63 -> 2.65 TB/s on this route, reverted).
         ok = CLS == CLS_SDIV || r != 0;
         const int q = narrow_quot<std::is_signed<T>::value>((int)l, (int)r);
         const int m = (int)l - q * (int)r;
