@@ -109,33 +109,93 @@ impl<'c> DeviceBitmask<'c> {
 }
 impl<'c> Drop for DeviceBitmask<'c> { fn drop(&mut self) { unsafe { ffi::mnr_bits_free(self.h) } } }
 
-/// Drop-in for `minarrow::kernels::arithmetic::dispatch::apply_int_i64` (dispatch.rs:74-131): same signature, same
-/// result (`Some(mask)` iff a mask was passed; masked zero divisors become nulls; dense zero divisors panic).
-pub fn apply_int_i64(ctx: &Context, lhs: &[i64], rhs: &[i64], op: ArithmeticOperator, mask: Option<&Bitmask>)
-                     -> Result<IntegerArray<i64>, KernelError> {
-    let len = lhs.len();
-    let mut out = Vec64::<i64>::with_capacity(len);
-    unsafe { out.set_len(len) };
-    let mut out_mask = mask.map(|_| Bitmask::new_set_all(len, false));
-    check(unsafe {
-        ffi::mnr_apply_int_i64(ctx.h, lhs.as_ptr(), len, rhs.as_ptr(), rhs.len(), op as c_int,
-                               mask.map_or(core::ptr::null(), |m| m.bits.as_ptr()), out.as_mut_ptr(),
-                               out_mask.as_mut().map_or(core::ptr::null_mut(), |m| m.bits.as_mut_ptr()))
-    })?;
-    Ok(IntegerArray { data: out.into(), null_mask: out_mask })
+// Drop-ins for the reference's leaf functions (src/kernels/arithmetic/dispatch.rs:74-131,147-204,376-402): same names,
+// same signatures (plus the context), same results — `Some(mask)` iff a mask was passed; masked zero divisors become
+// nulls; dense integer zero divisors panic like the reference's kernels do.
+macro_rules! impl_apply {
+    ($name:ident, $ffi:ident, $t:ty, $arr:ident) => {
+        pub fn $name(ctx: &Context, lhs: &[$t], rhs: &[$t], op: ArithmeticOperator, mask: Option<&Bitmask>)
+                     -> Result<$arr<$t>, KernelError> {
+            let len = lhs.len();
+            let mut out = Vec64::<$t>::with_capacity(len);
+            unsafe { out.set_len(len) };
+            let mut out_mask = mask.map(|_| Bitmask::new_set_all(len, false));
+            check(unsafe {
+                ffi::$ffi(ctx.h, lhs.as_ptr(), len, rhs.as_ptr(), rhs.len(), op as c_int,
+                          mask.map_or(core::ptr::null(), |m| m.bits.as_ptr()), out.as_mut_ptr(),
+                          out_mask.as_mut().map_or(core::ptr::null_mut(), |m| m.bits.as_mut_ptr()))
+            })?;
+            Ok($arr { data: out.into(), null_mask: out_mask })
+        }
+    };
 }
+impl_apply!(apply_int_i32, mnr_apply_int_i32, i32, IntegerArray);
+impl_apply!(apply_int_u32, mnr_apply_int_u32, u32, IntegerArray);
+impl_apply!(apply_int_i64, mnr_apply_int_i64, i64, IntegerArray);
+impl_apply!(apply_int_u64, mnr_apply_int_u64, u64, IntegerArray);
+impl_apply!(apply_float_f32, mnr_apply_float_f32, f32, FloatArray);
+impl_apply!(apply_float_f64, mnr_apply_float_f64, f64, FloatArray);
 
-/// Drop-in for `apply_float_f64` (dispatch.rs:147-204).
-pub fn apply_float_f64(ctx: &Context, lhs: &[f64], rhs: &[f64], op: ArithmeticOperator, mask: Option<&Bitmask>)
-                       -> Result<FloatArray<f64>, KernelError> {
+/// Drop-in for `apply_fma_f64` (dispatch.rs:221-290,411-418): `lhs.mul_add(rhs, acc)` with one rounding.
+pub fn apply_fma_f64(ctx: &Context, lhs: &[f64], rhs: &[f64], acc: &[f64], mask: Option<&Bitmask>)
+                     -> Result<FloatArray<f64>, KernelError> {
     let len = lhs.len();
     let mut out = Vec64::<f64>::with_capacity(len);
     unsafe { out.set_len(len) };
     let mut out_mask = mask.map(|_| Bitmask::new_set_all(len, false));
     check(unsafe {
-        ffi::mnr_apply_float_f64(ctx.h, lhs.as_ptr(), len, rhs.as_ptr(), rhs.len(), op as c_int,
-                                 mask.map_or(core::ptr::null(), |m| m.bits.as_ptr()), out.as_mut_ptr(),
-                                 out_mask.as_mut().map_or(core::ptr::null_mut(), |m| m.bits.as_mut_ptr()))
+        ffi::mnr_apply_fma_host(ctx.h, ffi::MNR_F64, lhs.as_ptr() as *const c_void, len, rhs.as_ptr() as *const c_void, rhs.len(),
+                                acc.as_ptr() as *const c_void, acc.len(), mask.map_or(core::ptr::null(), |m| m.bits.as_ptr()),
+                                out.as_mut_ptr() as *mut c_void, out_mask.as_mut().map_or(core::ptr::null_mut(), |m| m.bits.as_mut_ptr()))
     })?;
     Ok(FloatArray { data: out.into(), null_mask: out_mask })
+}
+
+impl<'c> DeviceBitmask<'c> {
+    /// `and_masks` / `or_masks` / `xor_masks` over two device-resident masks (src/kernels/bitmask/dispatch.rs:96-131).
+    pub fn binop(&self, op: minarrow::enums::operators::LogicalOperator, rhs: &Self) -> Result<Self, KernelError> {
+        let mut h = core::ptr::null_mut();
+        check(unsafe { ffi::mnr_bits_binop(self.ctx.h, op as c_int, self.h, 0, rhs.h, 0, self.len(), &mut h) })?;
+        Ok(Self { ctx: self.ctx, h })
+    }
+    /// `not_mask` (dispatch.rs:133-145): trailing bits of the result stay zero.
+    pub fn not(&self) -> Result<Self, KernelError> {
+        let mut h = core::ptr::null_mut();
+        check(unsafe { ffi::mnr_bits_not(self.ctx.h, self.h, 0, self.len(), &mut h) })?;
+        Ok(Self { ctx: self.ctx, h })
+    }
+    pub fn download(&self) -> Result<Bitmask, KernelError> {
+        let mut m = Bitmask::new_set_all(self.len(), false);
+        check(unsafe { ffi::mnr_bits_download(self.ctx.h, self.h, m.bits.as_mut_ptr()) })?;
+        Ok(m)
+    }
+}
+
+impl<'c, T: B200Dtype> DeviceBuffer<'c, T> {
+    /// `array op scalar` / `scalar op array` without materialising the length-1 operand
+    /// (replaces broadcast_length_1_array + the binary kernel, src/kernels/routing/broadcast.rs:25-112).
+    pub fn scalar(&self, op: ArithmeticOperator, scalar: T, scalar_is_lhs: bool, mask: Option<&DeviceBitmask<'c>>)
+                  -> Result<(Self, Option<DeviceBitmask<'c>>), KernelError> {
+        let (mut ob, mut om) = (core::ptr::null_mut(), core::ptr::null_mut());
+        check(unsafe {
+            ffi::mnr_ew_scalar(self.ctx.h, op as c_int, self.h, &scalar as *const T as *const c_void, scalar_is_lhs as c_int,
+                               mask.map_or(core::ptr::null(), |m| m.h as *const _), &mut ob, &mut om)
+        })?;
+        let mask = if om.is_null() { None } else { Some(DeviceBitmask { ctx: self.ctx, h: om }) };
+        Ok((Self { ctx: self.ctx, h: ob, _t: PhantomData }, mask))
+    }
+}
+
+/// Null-aware {sum, min, max, count} of a SuperArray's chunks resident on one GPU: one batched launch per dtype class,
+/// partials folded in chunk order (the device form of `par_chunks(1 << 20).map(sum).sum()`,
+/// benches/benchmark_parallel_simd.rs:81-97).  Per-GPU results are combined by the caller's all-reduce.
+pub fn chunk_stats<'c, T: B200Dtype>(ctx: &'c Context, chunks: &[(&DeviceBuffer<'c, T>, Option<&DeviceBitmask<'c>>)])
+                                     -> Result<ffi::mnr_agg, KernelError> {
+    let bufs: Vec<*const ffi::mnr_buf> = chunks.iter().map(|(b, _)| b.h as *const _).collect();
+    let masks: Vec<*const ffi::mnr_bits> = chunks.iter().map(|(_, m)| m.map_or(core::ptr::null(), |m| m.h as *const _)).collect();
+    let mut parts = vec![core::mem::MaybeUninit::<ffi::mnr_agg>::uninit(); chunks.len()];
+    check(unsafe { ffi::mnr_reduce_stats_batch(ctx.h, chunks.len(), bufs.as_ptr(), masks.as_ptr(), 1, parts.as_mut_ptr() as *mut ffi::mnr_agg) })?;
+    let mut out = core::mem::MaybeUninit::<ffi::mnr_agg>::uninit();
+    check(unsafe { ffi::mnr_agg_combine(T::CODE, parts.as_ptr() as *const ffi::mnr_agg, chunks.len(), out.as_mut_ptr()) })?;
+    Ok(unsafe { out.assume_init() })
 }

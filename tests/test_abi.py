@@ -31,6 +31,23 @@ def test_library_exports_every_declared_symbol():
     assert exported == set(names), exported ^ set(names)
 
 
+def test_rust_ffi_is_generated_from_the_header():
+    """rust/minarrow-b200/src/ffi.rs (the `extern "C"` block of the binding crate; unbuilt here, no cargo/rustc) is
+    generated from the header: it is up to date, declares every entry point, and agrees with the ctypes table on arity."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_ffi
+    from minarrow_b200 import _lib
+    text = gen_rust_ffi.generate()
+    assert open(gen_rust_ffi.OUT).read() == text, "stale: run python tools/gen_rust_ffi.py"
+    decls = dict(re.findall(r"pub fn (mnr_[a-z0-9_]+)\((.*?)\)(?: -> [^;]+)?;", text))
+    assert set(decls) == set(header_functions())
+    for name, (res, args) in _lib.SIGNATURES.items():
+        n_rust = 0 if not decls[name].strip() else decls[name].count(":")
+        assert n_rust == len(args), (name, decls[name], len(args))
+        assert ("->" in re.search(rf"pub fn {name}\(.*?\)([^;]*);", text).group(1)) == (res is not None), name
+
+
 def test_abi_is_plain_c():
     src = open(HEADER).read()
     code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
