@@ -40,7 +40,7 @@ __host__ __device__ constexpr int op_class(bool is_float, int op) {
 // int -> float goes through the 2^23 exponent trick (one integer op + FADD); unsigned quotients come back the same way
 // (FADD.RZ + LOP3), signed ones through one truncating conversion.  MIN / -1 comes out as 2^(bits-1), which wraps to MIN
 // in the caller's cast (the same wrapped quotient as the wide types).  Checked over the whole operand domain:
-// tests/test_gpu_narrow_division.py (8-bit, and every multiple boundary of 16-bit), tools/exhaustive_div16.py (all 2^32 pairs).
+// tests/test_gpu_narrow_division.py (8-bit, and every multiple boundary of 16-bit), tests/sweep_div16.py (all 2^32 pairs).
 template <bool SIGNED> __device__ __forceinline__ int narrow_quot(int l, int r) {
     float rc;
     if constexpr (SIGNED) {

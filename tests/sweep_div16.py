@@ -1,7 +1,7 @@
 """Whole-domain check of the 16-bit integer division path (narrow_quot, minarrow_b200/csrc/ew_kernels.cuh): all 2^32
 (dividend, divisor) pairs of int16 and of uint16 against the CPU oracle, Div on every block, Rem / FloorDiv on
 alternating blocks.  ~1.5 min on the GPU box; run by tools/gpu_round.sh, output kept under profiles/.
-Usage: python tools/exhaustive_div16.py [blocks-per-dtype (default 64 = everything)]"""
+Usage: python tests/sweep_div16.py [blocks-per-dtype (default 64 = everything)]"""
 import os
 import sys
 import time

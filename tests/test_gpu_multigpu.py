@@ -15,7 +15,7 @@ def test_sharded_superarray_two_gpus():
         pytest.skip("needs >= 2 GPUs")
     n = min(torch.cuda.device_count(), 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", "29571", os.path.join(ROOT, "tools", "multigpu_check.py")]
+           "--master-port", "29571", os.path.join(ROOT, "tests", "multigpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "multigpu_check ok" in r.stdout

@@ -70,7 +70,7 @@ def test_16bit_division_boundaries_and_blocks(gpu_ctx, dt):
     """(i) For EVERY divisor magnitude d and every multiple k*d in range: dividends k*d - 1, k*d, k*d + 1 with all sign
     combinations — the only places a truncated approximate quotient could land on the wrong integer.  (ii) Whole
     divisor blocks (1 024 divisors x all 65 536 dividends) at the ends and the middle of the domain.  The sweep over all
-    2^32 pairs is tools/exhaustive_div16.py (run per GPU round, result under profiles/)."""
+    2^32 pairs is tests/sweep_div16.py (run per GPU round, result under profiles/)."""
     info = np.iinfo(dt)
     top = int(info.max) + (1 if info.min < 0 else 0)       # largest magnitude: 65 535 or 32 768
     ds, ls = [], []
