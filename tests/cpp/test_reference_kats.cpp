@@ -235,6 +235,67 @@ static void device_path_suite(Context& ctx) {
         }
         mnr_buf_free(H); mnr_buf_free(P); mnr_buf_free(Q); mnr_bits_free(V);
     }
+    {   // 8/16-bit division through the f32 pipe and float % without the libm loop, against the machine divide / libm fmod:
+        // the whole 8-bit domain (zero divisors nulled), 16-bit pairs around every multiple of a few divisors, f64 pairs
+        std::vector<int8_t> a8, b8; std::vector<uint16_t> a16, b16; std::vector<int16_t> s16a, s16b;
+        for (int l = -128; l < 128; ++l) for (int r = -128; r < 128; ++r) { a8.push_back((int8_t)l); b8.push_back((int8_t)r); }
+        for (uint32_t d : {1u, 2u, 3u, 7u, 255u, 256u, 257u, 1000u, 32767u, 32768u, 65535u})
+            for (uint32_t k = 0; k * d <= 65535u; k += (65535u / d > 4096 ? 97 : 1))
+                for (int e = -1; e <= 1; ++e) {
+                    const int64_t l = (int64_t)k * d + e;
+                    if (l < 0 || l > 65535) continue;
+                    a16.push_back((uint16_t)l); b16.push_back((uint16_t)d);
+                    if (l <= 32768 && d <= 32768)
+                        for (int sg = 0; sg < 4; ++sg) {
+                            const int64_t sl = (sg & 1) ? -l : l, sd = (sg & 2) ? -(int64_t)d : (int64_t)d;
+                            if (sl > 32767 || sd > 32767) continue;
+                            s16a.push_back((int16_t)sl); s16b.push_back((int16_t)sd);
+                        }
+                }
+        auto run_int = [&](auto tag, mnr_dtype dt, const auto& l, const auto& r) {
+            using T = decltype(tag);
+            const size_t n = l.size();
+            std::vector<uint8_t> ones((n + 7) / 8, 0xFF);
+            mnr_buf *L = nullptr, *R = nullptr; mnr_bits* V = nullptr;
+            OK(mnr_buf_upload(c, dt, l.data(), n, &L)); OK(mnr_buf_upload(c, dt, r.data(), n, &R)); OK(mnr_bits_upload(c, ones.data(), n, &V));
+            for (mnr_op op : {MNR_DIV, MNR_REM, MNR_FLOORDIV}) {
+                mnr_buf* o = nullptr; mnr_bits* om = nullptr;
+                OK(mnr_ew_binary(c, op, L, R, V, nullptr, MNR_MASK_AND, &o, &om));
+                std::vector<T> g(n); std::vector<uint8_t> gm((n + 7) / 8);
+                OK(mnr_buf_download(c, o, g.data())); OK(mnr_bits_download(c, om, gm.data()));
+                bool same_vals = true;
+                for (size_t i = 0; i < n; ++i) {
+                    const int x = l[i], y = r[i];
+                    if (y == 0) { same_vals &= g[i] == 0 && !host_bit(gm, i); continue; }
+                    const int qq = x / y, m = x % y;
+                    const int e = op == MNR_DIV ? qq : op == MNR_REM ? m : ((m != 0 && ((x ^ y) < 0)) ? qq - 1 : qq);
+                    same_vals &= g[i] == (T)e && host_bit(gm, i);
+                }
+                CHECK(same_vals);
+                mnr_buf_free(o); mnr_bits_free(om);
+            }
+            mnr_buf_free(L); mnr_buf_free(R); mnr_bits_free(V);
+        };
+        run_int(int8_t{}, MNR_I8, a8, b8);
+        run_int(uint16_t{}, MNR_U16, a16, b16);
+        run_int(int16_t{}, MNR_I16, s16a, s16b);
+        const size_t n = 50021;
+        std::vector<double> x(n), y(n);
+        for (size_t i = 0; i < n; ++i) {
+            x[i] = std::ldexp((double)(int32_t)lcg() / 65536.0, (int)(lcg() % 80) - 40);
+            y[i] = std::ldexp((double)(int32_t)lcg() / 65536.0 + 0.5, (int)(lcg() % 80) - 40);
+            if (i % 11 == 0) x[i] = y[i] * (double)(lcg() % 100000);             // exact multiples
+            if (i % 13 == 0) x[i] = std::nextafter(y[i] * (double)(lcg() % 1000), 0.0);
+        }
+        x[0] = 0.0; x[1] = -0.0; x[2] = INFINITY; y[3] = 0.0; y[4] = INFINITY; x[5] = NAN; x[6] = 5e-324; y[7] = 5e-324;
+        auto f = apply_float_f64(x, y, Op::Remainder, nullptr);
+        bool same_vals = true;
+        for (size_t i = 0; i < n; ++i) {
+            const double e = std::fmod(x[i], y[i]);
+            same_vals &= std::isnan(e) ? std::isnan(f.data[i]) : (std::memcmp(&e, &f.data[i], 8) == 0);
+        }
+        CHECK(same_vals);
+    }
     mnr_bits_free(A); mnr_bits_free(B);
 }
 

@@ -34,7 +34,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:batc
 tail -2 $OUT/ncu_batch.log
 echo "== ncu full: shifted bit windows + i64 / scalar (multiplicative inverse)"
 timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k regex:"bits_shift_kernel|ew_binary_kernel<long, long, long, V32, 4" -s 4 -c 3 -f -o $OUT/prof_shift_sdiv \
+    -k regex:"bits_shift_kernel|ew_binary_kernel<long, long, long, (mnr::)?V32, 4," -s 4 -c 3 -f -o $OUT/prof_shift_sdiv \
     python bench.py --steps 3 --warmup 3 --rows 67108864 --no-e2e --no-cpu --no-supertable > $OUT/ncu_shift_sdiv.log 2>&1
 tail -2 $OUT/ncu_shift_sdiv.log
 fi
