@@ -14,9 +14,13 @@ namespace mnr {
 #if MNR_EW_DTYPE == 100
 int g_ew_grid_cap = 0;   // >0: cap every element-wise grid at this many blocks (tuning knob, mnr_ctx_set_option)
 int g_ew_max_tier = 2;   // 1: never use the 256-bit tier (tuning knob)
+int g_ew_sdiv64_cfg = 0; // launch geometry of 64-bit column / scalar (tuning knob, see CfgSdiv64)
+int g_ew_fdiv_cfg = 0;   // launch geometry of float Div / FloorDiv (tuning knob, see CfgFdiv2 / CfgFdiv3)
 #else
 extern int g_ew_grid_cap;
 extern int g_ew_max_tier;
+extern int g_ew_sdiv64_cfg;
+extern int g_ew_fdiv_cfg;
 #endif
 
 // MINB = 4 caps the kernel at 128 registers (4 blocks/SM).  1-byte columns carry the packed SIMD-in-register path (~150
@@ -28,6 +32,24 @@ struct CfgHeavy { static constexpr int BLOCK = 256, U = 2, MINB = 4; static cons
 template <int CLS, int ESZ> struct CfgOf { using type = CfgHeavy; };
 template <int ESZ> struct CfgOf<CLS_CHEAP, ESZ> { using type = CfgCheap<ESZ>; };
 template <int ESZ> struct CfgOf<CLS_SDIV, ESZ> { using type = CfgCheap<ESZ>; };   // a multiply-high per row: memory-bound like add
+// 64-bit column / scalar is ~115 instructions per row (a 64 x 64 -> 128-bit signed high multiply out of 32-bit IMADs): with
+// CfgCheap's 128 registers only 16 warps per SM are resident and the issue slots sit at 51 % (ncu r01zz: long-scoreboard
+// + fixed-latency stalls, DRAM 63 %).  Half the loads in flight and <= 85 registers (6 blocks/SM) is worth +9 % on the
+// masked kernels (i64 5.08 -> 5.52 TB/s, FloorDiv 4.49 -> 4.93; tools/sdiv64_exp.py, profiles/r01zz_sdiv64_exp.txt); the
+// dense kernels lose 5 % with it and keep CfgCheap.  Also measured and dropped: 256 thr x 2 x 128-bit at <= 64 registers
+// (resident grid 5.05, covering grid 4.25) and 256 thr x 2 x 256-bit at <= 85 registers (5.30).
+struct CfgSdiv64 { static constexpr int BLOCK = 128, U = 2, MINB = 6; static constexpr bool RESIDENT = false; using Wide = V32; };
+// Float Div / FloorDiv: the division sequence (~10 FMA-pipe instructions + a range check per row) sits between the cheap
+// and the heavy classes, and the best geometry depends on how many streams a row touches (tools/fdiv_exp.py,
+// profiles/r01zz_fdiv_exp.txt, 1 GiB per operand, GB/s; CfgHeavy = 256 thr x 2 x 128-bit, <= 64 regs, resident grid):
+//                          CfgHeavy   CfgFdiv2   CfgFdiv3
+//   f64 scalar, masked       5 469      5 573      6 149      f32: 5 264 / 5 879 / 6 242
+//   f64 scalar, dense        6 109      6 090      6 070      f32: 6 049 / 6 537 / 6 209
+//   f64 two masks            6 555      6 845      5 939      f32: 6 453 / 6 365 / 6 769
+//   f64 dense                6 367      7 038      6 258      f32: 6 371 / 6 965 / 6 150
+// (also measured: CfgCheap's 128 thr x 4 x 256-bit — never the best; CfgHeavy with a covering grid — always the worst.)
+struct CfgFdiv2 { static constexpr int BLOCK = 128, U = 2, MINB = 6; static constexpr bool RESIDENT = false; using Wide = V32; };
+struct CfgFdiv3 { static constexpr int BLOCK = 256, U = 2, MINB = 3; static constexpr bool RESIDENT = true; using Wide = V32; };
 
 static EwDev to_dev(const EwArgs& a) {
     EwDev d;
@@ -49,9 +71,8 @@ static unsigned ew_grid(uint64_t n, int vec) {
     return (unsigned)blocks;
 }
 
-template <typename T, typename TL, typename TR, typename VecT, int CLS>
+template <typename T, typename TL, typename TR, typename VecT, int CLS, typename Cfg = typename CfgOf<CLS, (int)sizeof(T)>::type>
 static cudaError_t go(const EwArgs& a, cudaStream_t s) {
-    using Cfg = typename CfgOf<CLS, (int)sizeof(T)>::type;
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     const bool masked = a.lmask || a.rmask;
     const unsigned grid = ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(a.n, VEC);
@@ -96,26 +117,44 @@ static cudaError_t go_batch_t(int op, int tier, bool masked, bool sdiv, const Ew
 
 // Alignment tiers, like the reference's "64-byte aligned -> SIMD body, else scalar body" (dispatch.rs:86,108-111):
 // widest vector every operand pointer allows, else 128-bit, else element-wise loads.
-template <typename T, typename TL, typename TR, int CLS>
+template <typename T, typename TL, typename TR, int CLS, typename Cfg = typename CfgOf<CLS, (int)sizeof(T)>::type>
 static cudaError_t go_align(const EwArgs& a, cudaStream_t s) {
-    using Wide = typename CfgOf<CLS, (int)sizeof(T)>::type::Wide;
+    using Wide = typename Cfg::Wide;
     auto ok = [](const void* p, size_t align) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % align) == 0; };
     constexpr int VW = sizeof(Wide) / sizeof(T);
     if (sizeof(Wide) > 16 && g_ew_max_tier >= 2 && ok(a.lhs, sizeof(TL) * VW) && ok(a.rhs, sizeof(TR) * VW) && ok(a.out, sizeof(Wide)))
-        return go<T, TL, TR, Wide, CLS>(a, s);
+        return go<T, TL, TR, Wide, CLS, Cfg>(a, s);
     constexpr int V = 16 / sizeof(T);
-    if (ok(a.lhs, sizeof(TL) * V) && ok(a.rhs, sizeof(TR) * V) && ok(a.out, 16)) return go<T, TL, TR, V16, CLS>(a, s);
-    return go<T, TL, TR, T, CLS>(a, s);
+    if (ok(a.lhs, sizeof(TL) * V) && ok(a.rhs, sizeof(TR) * V) && ok(a.out, 16)) return go<T, TL, TR, V16, CLS, Cfg>(a, s);
+    return go<T, TL, TR, T, CLS, Cfg>(a, s);
 }
 
 template <typename T>
 static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
     if constexpr (!Traits<T>::is_float) {
-        if (a.sdiv) return go_align<T, T, T, CLS_SDIV>(a, s);
+        if (a.sdiv) {
+            if constexpr (sizeof(T) == 8) {
+                // 0 = masked -> CfgSdiv64, dense -> CfgCheap; 1 / 2 force one of them (tools/sdiv64_exp.py)
+                const bool masked = a.lmask || a.rmask;
+                if (g_ew_sdiv64_cfg == 2 || (g_ew_sdiv64_cfg == 0 && masked)) return go_align<T, T, T, CLS_SDIV, CfgSdiv64>(a, s);
+            }
+            return go_align<T, T, T, CLS_SDIV>(a, s);
+        }
     }
     switch (op_class(Traits<T>::is_float, a.op)) {
         case CLS_CHEAP: return go_align<T, T, T, CLS_CHEAP>(a, s);
-        case CLS_DIV: return go_align<T, T, T, CLS_DIV>(a, s);
+        case CLS_DIV:
+            if constexpr (Traits<T>::is_float) {
+                // ew_fdiv_cfg: 0 = the table above, 1 = CfgHeavy, 2 / 3 = force CfgFdiv2 / CfgFdiv3
+                int cfg = g_ew_fdiv_cfg;
+                if (cfg == 0) {
+                    const bool masked = a.lmask || a.rmask, scalar = !a.lhs || !a.rhs;
+                    cfg = scalar ? (masked ? 3 : 2) : (masked ? (sizeof(T) == 8 ? 2 : 3) : 2);
+                }
+                if (cfg == 2) return go_align<T, T, T, CLS_DIV, CfgFdiv2>(a, s);
+                if (cfg == 3) return go_align<T, T, T, CLS_DIV, CfgFdiv3>(a, s);
+            }
+            return go_align<T, T, T, CLS_DIV>(a, s);
         case CLS_POW: return go_align<T, T, T, CLS_POW>(a, s);
         case CLS_REM:
             if constexpr (Traits<T>::is_float) return go_align<T, T, T, CLS_REM>(a, s);

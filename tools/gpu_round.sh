@@ -10,7 +10,7 @@ mkdir -p $OUT
 { nvidia-smi; nproc; lscpu | head -20; free -g; } > $OUT/box.txt 2>&1
 echo "== pytest -m gpu"; timeout 600 python -m pytest tests -m gpu -q -x --timeout 300 2>&1 | tail -25 | tee $OUT/pytest_gpu.txt
 echo "== smoke"; timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke.txt
-echo "== whole-domain 16-bit division sweep"; timeout 300 python tests/sweep_div16.py 2>&1 | tail -4 | tee $OUT/exhaustive_div16.txt
+[ -n "$SKIP_SWEEP" ] || { echo "== whole-domain 16-bit division sweep"; timeout 300 python tests/sweep_div16.py 2>&1 | tail -4 | tee $OUT/exhaustive_div16.txt; }
 echo "== bench reference arm"; timeout 300 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | tail -3 | tee $OUT/bench_reference.json
 echo "== bench"; timeout 600 python bench.py 2>&1 | tail -5 | tee $OUT/bench.json
 echo "== (kernel, dtype) matrix: division / remainder rows"
