@@ -18,6 +18,7 @@ extern int g_ew_grid_cap;
 extern int g_ew_max_tier;
 extern int g_ew_sdiv64_cfg;
 extern int g_ew_fdiv_cfg;
+extern int g_ew_heavy_cfg;
 __global__ void clear_trailing_kernel(uint8_t* bits, uint64_t len) {
     if (len & 7) bits[(len - 1) >> 3] &= (uint8_t)((1u << (unsigned)(len & 7)) - 1u);
 }
@@ -157,6 +158,7 @@ int mnr_ctx_set_option(mnr_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "ew_max_tier")) { g_ew_max_tier = (int)value; return MNR_OK; }
     if (!strcmp(key, "ew_sdiv64_cfg")) { g_ew_sdiv64_cfg = (int)value; return MNR_OK; }
     if (!strcmp(key, "ew_fdiv_cfg")) { g_ew_fdiv_cfg = (int)value; return MNR_OK; }
+    if (!strcmp(key, "ew_heavy_cfg")) { g_ew_heavy_cfg = (int)value; return MNR_OK; }
     if (!strcmp(key, "host_chunk_rows")) {
         REQUIRE(value >= 1024 && value % 1024 == 0, MNR_ERR_INVALID_ARGUMENTS, "host_chunk_rows must be a multiple of 1024");
         c->host_chunk_rows = (size_t)value;

@@ -16,11 +16,13 @@ int g_ew_grid_cap = 0;   // >0: cap every element-wise grid at this many blocks 
 int g_ew_max_tier = 2;   // 1: never use the 256-bit tier (tuning knob)
 int g_ew_sdiv64_cfg = 0; // launch geometry of 64-bit column / scalar (tuning knob, see CfgSdiv64)
 int g_ew_fdiv_cfg = 0;   // launch geometry of float Div / FloorDiv (tuning knob, see CfgFdiv2 / CfgFdiv3)
+int g_ew_heavy_cfg = 0;  // launch geometry of integer Div/Rem/FloorDiv, float Rem, Power (tuning knob, 2 / 3 = CfgFdiv2 / CfgFdiv3)
 #else
 extern int g_ew_grid_cap;
 extern int g_ew_max_tier;
 extern int g_ew_sdiv64_cfg;
 extern int g_ew_fdiv_cfg;
+extern int g_ew_heavy_cfg;
 #endif
 
 // MINB = 4 caps the kernel at 128 registers (4 blocks/SM).  1-byte columns carry the packed SIMD-in-register path (~150
@@ -129,6 +131,33 @@ static cudaError_t go_align(const EwArgs& a, cudaStream_t s) {
     return go<T, TL, TR, T, CLS, Cfg>(a, s);
 }
 
+// Integer Div / Rem / FloorDiv of two columns, float Rem, Power.  CfgHeavy was tuned on f64 division in r01c; with the
+// same two alternatives as above the wider types and Power gain 4-18 % (tools/heavy_exp.py, profiles/r01zz_heavy_exp.txt,
+// 1 GiB per operand, GB/s, CfgHeavy / CfgFdiv2 / CfgFdiv3):
+//   u64 div two masks 6 187 / 6 988 / 6 634     i64 div two masks 5 307 / 5 789 / 5 854     i64 div dense 6 202 / 6 740 / 5 756
+//   u32 div two masks 5 544 / 5 847 / 5 556     i32 div two masks 5 039 / 5 050 / 5 214     i32 div dense 5 784 / 6 243 / 5 963
+//   i16 div two masks 4 735 / 4 352 / 4 170     i8 floordiv two masks 2 041 / 2 145 / 1 961
+//   f64 rem two masks 6 141 / 6 701 / 6 387     f32 rem two masks 5 792 / 5 596 / 5 451
+//   pow two masks: i64 5 845 / 6 877 / 6 453, u32 5 538 / 5 803 / 5 555, i16 2 468 / 2 810 / 2 512, f32 5 883 / 6 764 / 6 036,
+//                  f64 3 675 / 4 106 / 3 930
+// ew_heavy_cfg: 0 = the choice below, 1 = CfgHeavy, 2 / 3 = force CfgFdiv2 / CfgFdiv3.
+template <typename T, int CLS>
+static cudaError_t go_heavy(const EwArgs& a, cudaStream_t s) {
+    int cfg = g_ew_heavy_cfg;
+    if (cfg == 0) {
+        const bool masked = a.lmask || a.rmask;
+        if (CLS == CLS_POW) cfg = 2;
+        else if (CLS == CLS_REM) cfg = sizeof(T) == 8 ? 2 : 1;                       // float remainder
+        else if (sizeof(T) == 8) cfg = 2;
+        else if (sizeof(T) == 4) cfg = (masked && Traits<T>::is_signed) ? 3 : 2;
+        else if (sizeof(T) == 2) cfg = 1;
+        else cfg = masked ? 2 : 1;
+    }
+    if (cfg == 2) return go_align<T, T, T, CLS, CfgFdiv2>(a, s);
+    if (cfg == 3) return go_align<T, T, T, CLS, CfgFdiv3>(a, s);
+    return go_align<T, T, T, CLS>(a, s);
+}
+
 template <typename T>
 static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
     if constexpr (!Traits<T>::is_float) {
@@ -154,10 +183,11 @@ static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
                 if (cfg == 2) return go_align<T, T, T, CLS_DIV, CfgFdiv2>(a, s);
                 if (cfg == 3) return go_align<T, T, T, CLS_DIV, CfgFdiv3>(a, s);
             }
-            return go_align<T, T, T, CLS_DIV>(a, s);
-        case CLS_POW: return go_align<T, T, T, CLS_POW>(a, s);
+            if constexpr (Traits<T>::is_float) return go_align<T, T, T, CLS_DIV>(a, s);
+            else return go_heavy<T, CLS_DIV>(a, s);
+        case CLS_POW: return go_heavy<T, CLS_POW>(a, s);
         case CLS_REM:
-            if constexpr (Traits<T>::is_float) return go_align<T, T, T, CLS_REM>(a, s);
+            if constexpr (Traits<T>::is_float) return go_heavy<T, CLS_REM>(a, s);
             break;
     }
     return cudaErrorInvalidValue;
