@@ -38,6 +38,7 @@ typedef struct mnr_ctx mnr_ctx;   /* device + stream + scratch                  
 typedef struct mnr_buf mnr_buf;   /* device-resident values buffer: the Vec64<T>/Buffer<T> analogue      */
 typedef struct mnr_bits mnr_bits; /* device-resident bit-packed mask: the Bitmask analogue               */
 typedef struct mnr_xchg mnr_xchg; /* cross-GPU mailbox set for the fused reduction + exchange kernel      */
+typedef struct mnr_group mnr_group; /* the GPUs of one box driven from one process: one ctx + mailbox per device */
 
 /* Element types of IntegerArray<T> / FloatArray<T> (src/structs/variants/{integer,float}.rs);
  * 8/16-bit integers are the reference's `extended_numeric_types` feature (dispatch.rs:380-387). */
@@ -104,15 +105,25 @@ int mnr_ctx_device(const mnr_ctx* ctx);
 void* mnr_ctx_stream(const mnr_ctx* ctx);
 /* Number of kernels of this library launched through `ctx` so far. */
 uint64_t mnr_ctx_launch_count(const mnr_ctx* ctx);
-/* Kernel variant knobs for tuning sweeps ("reduce_unroll", "reduce_blocks_per_sm", "ew_unroll", ...).
- * Unknown keys return MNR_ERR_INVALID_ARGUMENTS.  Results never depend on these for integer work;
- * float sums change order with the reduce knobs (documented in DESIGN.md). */
+/* Per-context options; contexts are independent (a knob set on one never changes another's launches).
+ *   "ew_grid_cap", "ew_max_tier", "ew_sdiv64_cfg", "ew_fdiv_cfg", "ew_heavy_cfg": launch geometry of the element-wise
+ *       kernels for tuning sweeps — results never depend on them;
+ *   "host_chunk_rows": rows per staging chunk of the host-slice drop-ins (multiple of 1024; default 4 Mi).  A float sum
+ *       through mnr_stats_host folds one partial per staging chunk in chunk order, so its bits depend on this value
+ *       (integer results never do);
+ *   "reduce_overlap" (0/1, default 0): consecutive mnr_reduce_stats_exchange calls on this context may overlap — the
+ *       next reduction streams its column while the previous one finishes its cross-GPU exchange.  Opt-in because the
+ *       caller vouches that the column being reduced is at rest (not written by work still in flight on the stream other
+ *       than this library's own reductions).
+ * Unknown keys return MNR_ERR_INVALID_ARGUMENTS. */
 int mnr_ctx_set_option(mnr_ctx* ctx, const char* key, int64_t value);
 
 /* ---- device-resident buffers: Vec64<T> / Buffer<T> (src/structs/buffer.rs:126-139) -------------------- */
 int mnr_buf_alloc(mnr_ctx* ctx, mnr_dtype dtype, size_t len, mnr_buf** out);
 /* Arrow-layout-preserving upload of `len` elements (Array::data_ptr_and_byte_len, src/enums/array.rs:2563). */
 int mnr_buf_upload(mnr_ctx* ctx, mnr_dtype dtype, const void* host, size_t len, mnr_buf** out);
+/* Same without the final synchronise: `host` (ideally pinned) must stay untouched until mnr_ctx_synchronize. */
+int mnr_buf_upload_async(mnr_ctx* ctx, mnr_dtype dtype, const void* host, size_t len, mnr_buf** out);
 /* Non-owning view of caller-owned device memory. */
 int mnr_buf_wrap(mnr_ctx* ctx, mnr_dtype dtype, void* device_ptr, size_t len, mnr_buf** out);
 /* ArrayV window `(array, offset, len)` (src/structs/views/array_view.rs:79-94): non-owning, parent must outlive it. */
@@ -129,6 +140,7 @@ int mnr_bits_alloc(mnr_ctx* ctx, size_t len_bits, mnr_bits** out);
 int mnr_bits_new_set_all(mnr_ctx* ctx, size_t len_bits, int value, mnr_bits** out);
 /* Upload ceil(len_bits/8) bytes (Array::null_mask_ptr_and_byte_len, src/enums/array.rs:2672); slack bits are cleared. */
 int mnr_bits_upload(mnr_ctx* ctx, const uint8_t* host_bytes, size_t len_bits, mnr_bits** out);
+int mnr_bits_upload_async(mnr_ctx* ctx, const uint8_t* host_bytes, size_t len_bits, mnr_bits** out);
 int mnr_bits_wrap(mnr_ctx* ctx, void* device_ptr, size_t len_bits, mnr_bits** out);
 int mnr_bits_download(mnr_ctx* ctx, const mnr_bits* bits, uint8_t* host_bytes);   /* synchronises */
 size_t mnr_bits_len(const mnr_bits* bits);
@@ -258,21 +270,80 @@ int mnr_reduce_stats_batch(mnr_ctx* ctx, size_t n, const mnr_buf* const* bufs, c
 int mnr_reduce_stats_batch_async(mnr_ctx* ctx, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
                                  int with_minmax, void* out_device);
 /* ---- fused reduction + cross-GPU exchange (SuperArray shards over the GPUs of one box) -----------------------
- * One process per GPU.  Each rank creates a mailbox, publishes its 64-byte CUDA IPC handle (any transport: the
- * harness all-gathers them with torch.distributed), and connects to its peers' mailboxes once.  After that
- * mnr_reduce_stats_exchange is ONE kernel per call: the shard's null-aware aggregate, P2P stores of the 32-byte
+ * Each rank (one per GPU) owns a mailbox in its HBM that every peer can store into.  One process per GPU: publish the
+ * 64-byte CUDA IPC handle (any transport: the Python harness all-gathers them with torch.distributed) and call
+ * mnr_xchg_connect.  One process, many GPUs: mnr_xchg_connect_local (peer access), or simply mnr_group_create below.
+ * After that mnr_reduce_stats_exchange is ONE kernel per call: the shard's null-aware aggregate, P2P stores of the 32-byte
  * partial into every peer's mailbox through NVLink/NVSwitch, a flag wait, and the rank-order combine — every rank
  * ends with the same global aggregate (bit-identical, floats included) in `out_device`.  Collective: every rank of
- * the group must make the same sequence of calls.  world <= 16. */
+ * the group must make the same sequence of exchange calls.  world <= 16.
+ * Failure: if a peer's partial never arrives (~10 s) the kernel sets the exchange's error word and marks the result
+ * unusable (count = UINT64_MAX).  The _sync forms return MNR_ERR_CUDA and clear the word; asynchronous callers poll
+ * mnr_xchg_status.  An epoch is consumed only by a launch that actually happened. */
 #define MNR_IPC_HANDLE_BYTES 64
+#define MNR_XCHG_MAX_AGGS 64   /* aggregates (columns) one exchange can carry */
 int mnr_xchg_create(mnr_ctx* ctx, int world, int rank, mnr_xchg** out);
 int mnr_xchg_local_handle(mnr_xchg* x, uint8_t* handle64);
 int mnr_xchg_connect(mnr_xchg* x, const uint8_t* handles /* world x MNR_IPC_HANDLE_BYTES, rank order */);
+/* Same process: peers[r] = rank r's exchange (peers[own rank] ignored).  Enables peer access between the devices; two
+ * ranks may share one device ("virtual ranks": the whole exchange path runs on a single-GPU box). */
+int mnr_xchg_connect_local(mnr_xchg* x, mnr_xchg* const* peers);
+/* *timed_out = 1 if an exchange on `x` gave up waiting since the last clear; synchronises the context stream. */
+int mnr_xchg_status(mnr_xchg* x, int clear, int* timed_out);
 void mnr_xchg_destroy(mnr_xchg* x);
 int mnr_reduce_stats_exchange(mnr_ctx* ctx, mnr_xchg* x, const mnr_buf* buf, const mnr_bits* validity, int with_minmax,
                               void* out_device);
 int mnr_reduce_stats_exchange_sync(mnr_ctx* ctx, mnr_xchg* x, const mnr_buf* buf, const mnr_bits* validity,
                                    int with_minmax, mnr_agg* out_host);
+/* Sharded SuperArray / SuperTable reduction in one call per rank (benches/benchmark_parallel_simd.rs:81-97 par_chunks ->
+ * chunk sums -> combine, over the chunk lists of broadcast/super_array.rs:180-249 and super_table.rs:38-73): the `n`
+ * LOCAL chunks (chunk i belongs to column col_of_chunk[i] < n_cols, dtype col_dtypes[col]) are reduced by batched
+ * launches; the block that writes the last chunk aggregate folds them per column in chunk order, exchanges the n_cols
+ * per-column partials with every peer in ONE mailbox epoch and folds those in rank order.  out_device receives n_cols x
+ * 32 bytes, identical on every rank.  A rank may hold no chunk at all (n = 0): it still takes part.  x = NULL: local
+ * per-column fold only (single GPU).  n_cols <= MNR_XCHG_MAX_AGGS. */
+int mnr_reduce_stats_batch_exchange(mnr_ctx* ctx, mnr_xchg* x, size_t n, const mnr_buf* const* bufs,
+                                    const mnr_bits* const* validities, int with_minmax, size_t n_cols,
+                                    const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes, void* out_device);
+int mnr_reduce_stats_batch_exchange_sync(mnr_ctx* ctx, mnr_xchg* x, size_t n, const mnr_buf* const* bufs,
+                                         const mnr_bits* const* validities, int with_minmax, size_t n_cols,
+                                         const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes, mnr_agg* out_host);
+
+/* ---- sharding: chunks -> GPUs --------------------------------------------------------------------------
+ * Chunk i of n lives on rank floor(i * world / n): contiguous blocks, so global row order is preserved and results
+ * re-assemble as a SuperArray with the same chunk boundaries.  Pure host arithmetic. */
+int mnr_shard_owner(size_t chunk, size_t n_chunks, int world);   /* rank >= 0, or a negative mnr_status */
+int mnr_shard_chunk_range(size_t n_chunks, int world, int rank, size_t* lo, size_t* hi);   /* chunks [lo, hi) */
+/* One big Array cut into `world` contiguous windows on `align`-row boundaries (64 rows = one validity word). */
+int mnr_shard_row_range(size_t n_rows, int world, int rank, size_t align, size_t* offset, size_t* len);
+
+/* One process driving all GPUs of the box: `world` contexts (own streams) + mailboxes connected through peer access.
+ * devices = NULL means devices 0..world-1; a device may be listed more than once (virtual ranks).  The mnr_group_*
+ * calls route every chunk to the context that owns it (mnr_buf carries its context) and launch per device; the
+ * per-rank handles are ordinary mnr_ctx / mnr_xchg for everything else in this header. */
+int mnr_group_create(int world, const int* devices, mnr_group** out);
+void mnr_group_destroy(mnr_group* g);
+int mnr_group_world(const mnr_group* g);
+mnr_ctx* mnr_group_ctx(mnr_group* g, int rank);
+mnr_xchg* mnr_group_xchg(mnr_group* g, int rank);
+int mnr_group_synchronize(mnr_group* g);
+/* Upload the chunks of a host SuperArray: chunk i -> rank mnr_shard_owner(i, n_chunks, world), all links copying at the
+ * same time (pinned host memory).  host_validity may be NULL or hold NULL entries; out_validity[i] is NULL for those. */
+int mnr_group_upload(mnr_group* g, mnr_dtype dtype, size_t n_chunks, const void* const* host_chunks, const size_t* lens,
+                     const uint8_t* const* host_validity, mnr_buf** out_bufs, mnr_bits** out_validity);
+/* Shard-local element-wise fan-out (no communication): chunk pair i runs on the device that owns it; lhs[i] and rhs[i]
+ * must live on the same rank.  One batched launch per device and (dtype, alignment, masked) class; fresh outputs on the
+ * owning device.  Semantics per chunk = mnr_ew_binary / mnr_ew_scalar. */
+int mnr_group_ew_binary(mnr_group* g, mnr_op op, size_t n, const mnr_buf* const* lhs, const mnr_buf* const* rhs,
+                        const mnr_bits* const* lhs_mask, const mnr_bits* const* rhs_mask, mnr_mask_mode mode, mnr_buf** out,
+                        mnr_bits** out_mask);
+int mnr_group_ew_scalar(mnr_group* g, mnr_op op, size_t n, const mnr_buf* const* arrs, const void* const* scalars,
+                        int scalar_is_lhs, const mnr_bits* const* masks, mnr_buf** out, mnr_bits** out_mask);
+/* Per-column {sum, min, max, count} of a sharded SuperArray / SuperTable: mnr_reduce_stats_batch_exchange on every rank
+ * (the fused NVLink exchange), then rank 0's n_cols aggregates are copied to out_host.  Synchronises the group. */
+int mnr_group_reduce_stats(mnr_group* g, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
+                           int with_minmax, size_t n_cols, const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes,
+                           mnr_agg* out_host);
 /* mean = (double)sum / (double)count on the host from a (combined) aggregate; NaN when count == 0. */
 double mnr_agg_mean(mnr_dtype dtype, const mnr_agg* agg);
 /* Combine per-chunk / per-GPU partials in index order (the documented rank-order float add). */

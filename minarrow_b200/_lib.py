@@ -45,6 +45,7 @@ SIGNATURES = {
     "mnr_ctx_set_option": (c_int, [c_ctx, C.c_char_p, C.c_int64]),
     "mnr_buf_alloc": (c_int, [c_ctx, c_int, c_sz, PP]),
     "mnr_buf_upload": (c_int, [c_ctx, c_int, c_vp, c_sz, PP]),
+    "mnr_buf_upload_async": (c_int, [c_ctx, c_int, c_vp, c_sz, PP]),
     "mnr_buf_wrap": (c_int, [c_ctx, c_int, c_vp, c_sz, PP]),
     "mnr_buf_slice": (c_int, [c_buf, c_sz, c_sz, PP]),
     "mnr_buf_download": (c_int, [c_ctx, c_buf, c_vp]),
@@ -55,6 +56,7 @@ SIGNATURES = {
     "mnr_bits_alloc": (c_int, [c_ctx, c_sz, PP]),
     "mnr_bits_new_set_all": (c_int, [c_ctx, c_sz, c_int, PP]),
     "mnr_bits_upload": (c_int, [c_ctx, c_vp, c_sz, PP]),
+    "mnr_bits_upload_async": (c_int, [c_ctx, c_vp, c_sz, PP]),
     "mnr_bits_wrap": (c_int, [c_ctx, c_vp, c_sz, PP]),
     "mnr_bits_download": (c_int, [c_ctx, c_bits, c_vp]),
     "mnr_bits_len": (c_sz, [c_bits]),
@@ -93,7 +95,27 @@ SIGNATURES = {
     "mnr_xchg_create": (c_int, [c_ctx, c_int, c_int, PP]),
     "mnr_xchg_local_handle": (c_int, [c_vp, c_vp]),
     "mnr_xchg_connect": (c_int, [c_vp, c_vp]),
+    "mnr_xchg_connect_local": (c_int, [c_vp, PP]),
+    "mnr_xchg_status": (c_int, [c_vp, c_int, C.POINTER(c_int)]),
     "mnr_xchg_destroy": (None, [c_vp]),
+    "mnr_reduce_stats_batch_exchange": (c_int, [c_ctx, c_vp, c_sz, PP, PP, c_int, c_sz, C.POINTER(C.c_uint32),
+                                                C.POINTER(c_int), c_vp]),
+    "mnr_reduce_stats_batch_exchange_sync": (c_int, [c_ctx, c_vp, c_sz, PP, PP, c_int, c_sz, C.POINTER(C.c_uint32),
+                                                     C.POINTER(c_int), C.POINTER(Agg)]),
+    "mnr_shard_owner": (c_int, [c_sz, c_sz, c_int]),
+    "mnr_shard_chunk_range": (c_int, [c_sz, c_int, c_int, C.POINTER(c_sz), C.POINTER(c_sz)]),
+    "mnr_shard_row_range": (c_int, [c_sz, c_int, c_int, c_sz, C.POINTER(c_sz), C.POINTER(c_sz)]),
+    "mnr_group_create": (c_int, [c_int, C.POINTER(c_int), PP]),
+    "mnr_group_destroy": (None, [c_vp]),
+    "mnr_group_world": (c_int, [c_vp]),
+    "mnr_group_ctx": (c_vp, [c_vp, c_int]),
+    "mnr_group_xchg": (c_vp, [c_vp, c_int]),
+    "mnr_group_synchronize": (c_int, [c_vp]),
+    "mnr_group_upload": (c_int, [c_vp, c_int, c_sz, PP, C.POINTER(c_sz), PP, PP, PP]),
+    "mnr_group_ew_binary": (c_int, [c_vp, c_int, c_sz, PP, PP, PP, PP, c_int, PP, PP]),
+    "mnr_group_ew_scalar": (c_int, [c_vp, c_int, c_sz, PP, PP, c_int, PP, PP, PP]),
+    "mnr_group_reduce_stats": (c_int, [c_vp, c_sz, PP, PP, c_int, c_sz, C.POINTER(C.c_uint32), C.POINTER(c_int),
+                                       C.POINTER(Agg)]),
     "mnr_reduce_stats_exchange": (c_int, [c_ctx, c_vp, c_buf, c_bits, c_int, c_vp]),
     "mnr_reduce_stats_exchange_sync": (c_int, [c_ctx, c_vp, c_buf, c_bits, c_int, C.POINTER(Agg)]),
     "mnr_agg_mean": (C.c_double, [c_int, C.POINTER(Agg)]),

@@ -95,6 +95,22 @@ class Context:
             check(self.lib.mnr_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h)))
         self.h = h
         self.device = device
+        self._owned = True
+
+    @classmethod
+    def borrow(cls, handle) -> "Context":
+        """Non-owning view of a context that belongs to a `mnr_group` (sharded.Group)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+        self.device = int(self.lib.mnr_ctx_device(self.h))
+        self._owned = False
+        return self
+
+    @property
+    def stream(self) -> int:
+        """Raw cudaStream_t of the context (wrap with torch.cuda.ExternalStream to put torch work on it)."""
+        return int(self.lib.mnr_ctx_stream(self.h) or 0)
 
     def synchronize(self) -> None:
         check(self.lib.mnr_ctx_synchronize(self.h))
@@ -108,7 +124,8 @@ class Context:
 
     def close(self) -> None:
         if getattr(self, "h", None):
-            self.lib.mnr_ctx_destroy(self.h)
+            if getattr(self, "_owned", True):
+                self.lib.mnr_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -188,6 +205,8 @@ class DeviceBitmask:
     def upload(cls, ctx: Context, mask: "Bitmask") -> "DeviceBitmask":
         h = C.c_void_p()
         bits = np.ascontiguousarray(mask.bits, dtype=np.uint8)
+        if bits.size < (mask.len + 7) // 8:   # the reference would panic on the slice; never hand the C ABI a short buffer
+            raise KernelError("OutOfBounds", f"Bitmask of {mask.len} bits is backed by {bits.size} bytes, need {(mask.len + 7) // 8}")
         check(ctx.lib.mnr_bits_upload(ctx.h, _vp(bits), mask.len, C.byref(h)))
         return cls(ctx, h)
 

@@ -14,11 +14,6 @@
 #include "reduce_kernels.cuh"
 
 namespace mnr {
-extern int g_ew_grid_cap;
-extern int g_ew_max_tier;
-extern int g_ew_sdiv64_cfg;
-extern int g_ew_fdiv_cfg;
-extern int g_ew_heavy_cfg;
 __global__ void clear_trailing_kernel(uint8_t* bits, uint64_t len) {
     if (len & 7) bits[(len - 1) >> 3] &= (uint8_t)((1u << (unsigned)(len & 7)) - 1u);
 }
@@ -76,25 +71,31 @@ int mnr_device_count(void) {
 }
 
 // ---- context -------------------------------------------------------------------------------------------------
-static int ctx_init(int device, cudaStream_t stream, bool own, mnr_ctx** out) {
-    REQUIRE(out, MNR_ERR_INVALID_ARGUMENTS, "mnr_ctx_create: out is NULL");
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        cudaGetLastError();
-        return fail(MNR_ERR_NO_DEVICE, "no CUDA device (%s); minarrow_b200 has no CPU fallback",
-                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+static void ctx_release(mnr_ctx* c) {
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 3; ++i) {
+        if (c->slot_stream[i]) { cudaStreamSynchronize(c->slot_stream[i]); cudaStreamDestroy(c->slot_stream[i]); }
+        for (int j = 0; j < 6; ++j) if (c->stage[i][j]) cudaFree(c->stage[i][j]);
     }
-    REQUIRE(device >= 0 && device < n, MNR_ERR_NO_DEVICE, "device %d out of range (have %d)", device, n);
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    REQUIRE(prop.major >= 10, MNR_ERR_NO_DEVICE,
-            "device %d is sm_%d%d; this library carries sm_100a code only (no fallback path)", device, prop.major,
-            prop.minor);
-    CU(cudaSetDevice(device));
-    mnr_ctx* c = new mnr_ctx();
-    c->device = device;
-    c->own_stream = own;
+    for (int i = 0; i < 4; ++i) { if (c->partials[i]) cudaFree(c->partials[i]); if (c->ticket[i]) cudaFree(c->ticket[i]); }
+    if (c->chunk_aggs) cudaFree(c->chunk_aggs);
+    if (c->ew_segs) cudaFree(c->ew_segs);
+    if (c->batch_partials) cudaFree(c->batch_partials);
+    if (c->batch_segs) cudaFree(c->batch_segs);
+    if (c->batch_tickets) cudaFree(c->batch_tickets);
+    if (c->fold_desc) cudaFree(c->fold_desc);
+    if (c->fold_local) cudaFree(c->fold_local);
+    if (c->fold_result) cudaFree(c->fold_result);
+    if (c->d_agg) cudaFree(c->d_agg);
+    if (c->d_count) cudaFree(c->d_count);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+static int ctx_alloc(mnr_ctx* c, cudaStream_t stream, bool own) {
     if (own) CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     else c->stream = stream;
     for (int i = 0; i < 3; ++i) CU(cudaStreamCreateWithFlags(&c->slot_stream[i], cudaStreamNonBlocking));
@@ -107,11 +108,39 @@ static int ctx_init(int device, cudaStream_t stream, bool own, mnr_ctx** out) {
     }
     CU(cudaMalloc(&c->d_agg, sizeof(AggRaw)));
     CU(cudaMalloc(&c->d_count, 64));
+    CU(cudaMalloc(&c->fold_local, sizeof(AggRaw) * MNR_XCHG_MAX_AGGS));
+    CU(cudaMalloc(&c->fold_result, sizeof(AggRaw) * MNR_XCHG_MAX_AGGS));
     CU(cudaHostAlloc(&c->h_scratch, 256, cudaHostAllocMapped | cudaHostAllocPortable));   // kernels store results here directly
     cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    CU(cudaDeviceGetDefaultMemPool(&pool, c->device));
     uint64_t thr = UINT64_MAX;   // keep freed blocks cached: fresh outputs per call without cudaMalloc cost
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    return MNR_OK;
+}
+
+static int ctx_init(int device, cudaStream_t stream, bool own, mnr_ctx** out) {
+    REQUIRE(out, MNR_ERR_INVALID_ARGUMENTS, "mnr_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MNR_ERR_NO_DEVICE, "no CUDA device (%s); minarrow_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    REQUIRE(device >= 0 && device < n, MNR_ERR_NO_DEVICE, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    // The library carries sm_100a SASS only: arch-specific ("a") code runs on exactly that compute capability —
+    // an sm_103 / sm_120 part would pass a ">= 10" test and fail at the first launch.
+    REQUIRE(prop.major == 10 && prop.minor == 0, MNR_ERR_NO_DEVICE,
+            "device %d is sm_%d%d; this library carries sm_100a code only (no fallback path)", device, prop.major,
+            prop.minor);
+    CU(cudaSetDevice(device));
+    mnr_ctx* c = new mnr_ctx();
+    c->device = device;
+    c->own_stream = own;
+    const int rc = ctx_alloc(c, stream, own);
+    if (rc) { ctx_release(c); return rc; }   // nothing leaks when a later allocation fails
     *out = c;
     return MNR_OK;
 }
@@ -123,23 +152,7 @@ int mnr_ctx_create_on_stream(int device, void* cuda_stream, mnr_ctx** out) {
 
 void mnr_ctx_destroy(mnr_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 3; ++i) {
-        if (c->slot_stream[i]) { cudaStreamSynchronize(c->slot_stream[i]); cudaStreamDestroy(c->slot_stream[i]); }
-        for (int j = 0; j < 6; ++j) if (c->stage[i][j]) cudaFree(c->stage[i][j]);
-    }
-    for (int i = 0; i < 4; ++i) { cudaFree(c->partials[i]); cudaFree(c->ticket[i]); }
-    if (c->chunk_aggs) cudaFree(c->chunk_aggs);
-    if (c->ew_segs) cudaFree(c->ew_segs);
-    if (c->batch_partials) cudaFree(c->batch_partials);
-    if (c->batch_segs) cudaFree(c->batch_segs);
-    if (c->batch_tickets) cudaFree(c->batch_tickets);
-    cudaFree(c->d_agg);
-    cudaFree(c->d_count);
-    cudaFreeHost(c->h_scratch);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
-    delete c;
+    ctx_release(c);
 }
 
 int mnr_ctx_synchronize(mnr_ctx* c) {
@@ -154,11 +167,12 @@ uint64_t mnr_ctx_launch_count(const mnr_ctx* c) { return c ? c->launches : 0; }
 
 int mnr_ctx_set_option(mnr_ctx* c, const char* key, int64_t value) {
     REQUIRE(c && key, MNR_ERR_INVALID_ARGUMENTS, "ctx/key is NULL");
-    if (!strcmp(key, "ew_grid_cap")) { g_ew_grid_cap = (int)value; return MNR_OK; }
-    if (!strcmp(key, "ew_max_tier")) { g_ew_max_tier = (int)value; return MNR_OK; }
-    if (!strcmp(key, "ew_sdiv64_cfg")) { g_ew_sdiv64_cfg = (int)value; return MNR_OK; }
-    if (!strcmp(key, "ew_fdiv_cfg")) { g_ew_fdiv_cfg = (int)value; return MNR_OK; }
-    if (!strcmp(key, "ew_heavy_cfg")) { g_ew_heavy_cfg = (int)value; return MNR_OK; }
+    if (!strcmp(key, "ew_grid_cap")) { c->knobs.grid_cap = (int)value; return MNR_OK; }
+    if (!strcmp(key, "ew_max_tier")) { c->knobs.max_tier = (int)value; return MNR_OK; }
+    if (!strcmp(key, "ew_sdiv64_cfg")) { c->knobs.sdiv64_cfg = (int)value; return MNR_OK; }
+    if (!strcmp(key, "ew_fdiv_cfg")) { c->knobs.fdiv_cfg = (int)value; return MNR_OK; }
+    if (!strcmp(key, "ew_heavy_cfg")) { c->knobs.heavy_cfg = (int)value; return MNR_OK; }
+    if (!strcmp(key, "reduce_overlap")) { c->reduce_overlap = value != 0; return MNR_OK; }
     if (!strcmp(key, "host_chunk_rows")) {
         REQUIRE(value >= 1024 && value % 1024 == 0, MNR_ERR_INVALID_ARGUMENTS, "host_chunk_rows must be a multiple of 1024");
         c->host_chunk_rows = (size_t)value;
@@ -184,14 +198,21 @@ int mnr_buf_alloc(mnr_ctx* c, mnr_dtype dtype, size_t len, mnr_buf** out) {
     return MNR_OK;
 }
 
-int mnr_buf_upload(mnr_ctx* c, mnr_dtype dtype, const void* host, size_t len, mnr_buf** out) {
+int mnr_buf_upload_async(mnr_ctx* c, mnr_dtype dtype, const void* host, size_t len, mnr_buf** out) {
     REQUIRE(host || len == 0, MNR_ERR_INVALID_ARGUMENTS, "host pointer is NULL");
     int rc = mnr_buf_alloc(c, dtype, len, out);
     if (rc) return rc;
     if (len) {
-        CU(cudaMemcpyAsync((*out)->ptr, host, len * dtype_size(dtype), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));   // the caller may reuse `host` on return
+        cudaError_t e = cudaMemcpyAsync((*out)->ptr, host, len * dtype_size(dtype), cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { mnr_buf_free(*out); *out = nullptr; return fail_cuda(e, "cudaMemcpyAsync (upload)"); }
     }
+    return MNR_OK;
+}
+
+int mnr_buf_upload(mnr_ctx* c, mnr_dtype dtype, const void* host, size_t len, mnr_buf** out) {
+    int rc = mnr_buf_upload_async(c, dtype, host, len, out);
+    if (rc) return rc;
+    if (len) CU(cudaStreamSynchronize(c->stream));   // the caller may reuse `host` on return
     return MNR_OK;
 }
 
@@ -250,16 +271,26 @@ int mnr_bits_new_set_all(mnr_ctx* c, size_t len_bits, int value, mnr_bits** out)
     return MNR_OK;
 }
 
-int mnr_bits_upload(mnr_ctx* c, const uint8_t* host_bytes, size_t len_bits, mnr_bits** out) {
+int mnr_bits_upload_async(mnr_ctx* c, const uint8_t* host_bytes, size_t len_bits, mnr_bits** out) {
     REQUIRE(host_bytes || len_bits == 0, MNR_ERR_INVALID_ARGUMENTS, "host pointer is NULL");
     int rc = mnr_bits_alloc(c, len_bits, out);
     if (rc) return rc;
     if (len_bits) {
-        CU(cudaMemcpyAsync((*out)->ptr, host_bytes, mask_bytes(len_bits), cudaMemcpyHostToDevice, c->stream));
-        if (len_bits & 7) { clear_trailing_kernel<<<1, 1, 0, c->stream>>>((*out)->ptr, len_bits); c->launches++; }
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(c->stream));
+        cudaError_t e = cudaMemcpyAsync((*out)->ptr, host_bytes, mask_bytes(len_bits), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && (len_bits & 7)) {
+            clear_trailing_kernel<<<1, 1, 0, c->stream>>>((*out)->ptr, len_bits);
+            c->launches++;
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) { mnr_bits_free(*out); *out = nullptr; return fail_cuda(e, "mnr_bits_upload"); }
     }
+    return MNR_OK;
+}
+
+int mnr_bits_upload(mnr_ctx* c, const uint8_t* host_bytes, size_t len_bits, mnr_bits** out) {
+    int rc = mnr_bits_upload_async(c, host_bytes, len_bits, out);
+    if (rc) return rc;
+    if (len_bits) CU(cudaStreamSynchronize(c->stream));
     return MNR_OK;
 }
 
@@ -361,7 +392,7 @@ int mnr_ew_binary_into(mnr_ctx* c, mnr_op op, const mnr_buf* lhs, const mnr_buf*
     EwArgs a{};
     a.dtype = lhs->dtype; a.op = op; a.lhs = lhs->ptr; a.rhs = rhs->ptr;
     a.lmask = lm ? lm->ptr : nullptr; a.rmask = rm ? rm->ptr : nullptr; a.mask_or = mode == MNR_MASK_OR;
-    a.out = out->ptr; a.out_mask = masked ? out_mask->ptr : nullptr; a.n = lhs->len;
+    a.out = out->ptr; a.out_mask = masked ? out_mask->ptr : nullptr; a.n = lhs->len; a.k = c->knobs;
     return run_ew(c, a, c->stream, false, lhs->dtype, rhs->dtype);
 }
 
@@ -407,7 +438,7 @@ int mnr_ew_scalar_into(mnr_ctx* c, mnr_op op, const mnr_buf* arr, const void* sc
     a.rhs = scalar_is_lhs ? arr->ptr : nullptr;
     a.scalar_bits = scalar_to_bits(arr->dtype, scalar);
     a.lmask = mask ? mask->ptr : nullptr; a.rmask = nullptr; a.mask_or = 0;
-    a.out = out->ptr; a.out_mask = mask ? out_mask->ptr : nullptr; a.n = arr->len;
+    a.out = out->ptr; a.out_mask = mask ? out_mask->ptr : nullptr; a.n = arr->len; a.k = c->knobs;
     return run_ew(c, a, c->stream, false, arr->dtype, arr->dtype);
 }
 
@@ -469,7 +500,7 @@ int mnr_ew_binary_promote(mnr_ctx* c, mnr_op op, const mnr_buf* lhs, const mnr_b
     EwArgs a{};
     a.dtype = ot; a.op = op; a.lhs = lhs->ptr; a.rhs = rhs->ptr;
     a.lmask = lm ? lm->ptr : nullptr; a.rmask = rm ? rm->ptr : nullptr; a.mask_or = mode == MNR_MASK_OR;
-    a.out = (*out)->ptr; a.out_mask = (lm || rm) ? (*out_mask)->ptr : nullptr; a.n = lhs->len;
+    a.out = (*out)->ptr; a.out_mask = (lm || rm) ? (*out_mask)->ptr : nullptr; a.n = lhs->len; a.k = c->knobs;
     return drop_outputs(run_ew(c, a, c->stream, true, l, r), out, out_mask);
 }
 
@@ -503,7 +534,7 @@ static int run_ew_batch(mnr_ctx* c, std::vector<EwArgs>& items) {
     std::vector<uint64_t> max_n;
     for (const auto& a : items) {
         if (a.n == 0) continue;
-        const int tier = ew_batch_tier(a.dtype, a.op, a.sdiv != 0, a.lhs, a.rhs, a.out);
+        const int tier = ew_batch_tier(a.dtype, a.op, a.sdiv != 0, a.lhs, a.rhs, a.out, c->knobs.max_tier);
         if (tier == 0) {
             CU(launch_ew_binary(a, c->stream));
             c->launches++;
@@ -529,7 +560,7 @@ static int run_ew_batch(mnr_ctx* c, std::vector<EwArgs>& items) {
             c->ew_flip ^= 1;
             CU(cudaMemcpyAsync(dst, groups[g].data() + off, cnt * sizeof(EwDev), cudaMemcpyHostToDevice, c->stream));
             CU(launch_ew_batch((mnr_dtype)keys[g].dtype, items[0].op, keys[g].tier, keys[g].masked != 0, keys[g].sdiv != 0,
-                               reinterpret_cast<const EwDev*>(dst), (uint32_t)cnt, max_n[g], c->stream));
+                               reinterpret_cast<const EwDev*>(dst), (uint32_t)cnt, max_n[g], c->knobs.grid_cap, c->stream));
             c->launches++;
         }
     }
@@ -567,7 +598,7 @@ int mnr_ew_binary_batch_into(mnr_ctx* c, mnr_op op, size_t n, const mnr_buf* con
         a = EwArgs{};
         a.dtype = l->dtype; a.op = op; a.lhs = l->ptr; a.rhs = r->ptr;
         a.lmask = lm ? lm->ptr : nullptr; a.rmask = rm ? rm->ptr : nullptr; a.mask_or = mode == MNR_MASK_OR;
-        a.out = out[i]->ptr; a.out_mask = masked ? om->ptr : nullptr; a.n = l->len;
+        a.out = out[i]->ptr; a.out_mask = masked ? om->ptr : nullptr; a.n = l->len; a.k = c->knobs;
     }
     return run_ew_batch(c, items);
 }
@@ -592,7 +623,7 @@ int mnr_ew_scalar_batch_into(mnr_ctx* c, mnr_op op, size_t n, const mnr_buf* con
         a.lhs = scalar_is_lhs ? nullptr : arr->ptr;
         a.rhs = scalar_is_lhs ? arr->ptr : nullptr;
         a.scalar_bits = scalar_to_bits(arr->dtype, scalars[i]);
-        a.lmask = m ? m->ptr : nullptr; a.out = out[i]->ptr; a.out_mask = m ? om->ptr : nullptr; a.n = arr->len;
+        a.lmask = m ? m->ptr : nullptr; a.out = out[i]->ptr; a.out_mask = m ? om->ptr : nullptr; a.n = arr->len; a.k = c->knobs;
     }
     return run_ew_batch(c, items);
 }
@@ -930,23 +961,77 @@ int mnr_reduce_sum(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, mnr_scalar64
 
 
 // ---- batched reductions: one launch per (dtype, alignment tier, masked) class -----------------------------------------
-static int ensure_batch_scratch(mnr_ctx* c, size_t nseg, size_t max_blk) {
-    const size_t need_p = nseg * max_blk * sizeof(AggRaw), need_s = nseg * sizeof(ReduceSeg), need_t = nseg * sizeof(unsigned int);
+static int ensure_batch_scratch(mnr_ctx* c, size_t nseg_total, size_t nseg_launch, size_t partial_slots) {
+    const size_t need_p = partial_slots * sizeof(AggRaw), need_s = nseg_total * sizeof(ReduceSeg), need_t = nseg_launch * sizeof(unsigned int);
     if (c->batch_partials_bytes < need_p) {
-        if (c->batch_partials) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_partials)); c->batch_partials = nullptr; }
+        if (c->batch_partials) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_partials)); c->batch_partials = nullptr; c->batch_partials_bytes = 0; }
         CU(cudaMalloc(&c->batch_partials, need_p));
         c->batch_partials_bytes = need_p;
     }
-    if (c->batch_segs_bytes < need_s) {
-        if (c->batch_segs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_segs)); c->batch_segs = nullptr; }
+    if (c->batch_segs_bytes < need_s * 2) {
+        if (c->batch_segs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_segs)); c->batch_segs = nullptr; c->batch_segs_bytes = 0; }
         CU(cudaMalloc(&c->batch_segs, need_s * 2));
         c->batch_segs_bytes = need_s * 2;
     }
     if (c->batch_tickets_bytes < need_t) {
-        if (c->batch_tickets) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_tickets)); c->batch_tickets = nullptr; }
+        if (c->batch_tickets) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->batch_tickets)); c->batch_tickets = nullptr; c->batch_tickets_bytes = 0; }
         CU(cudaMalloc(&c->batch_tickets, need_t * 2));
         CU(cudaMemset(c->batch_tickets, 0, need_t * 2));   // tickets re-arm themselves after every launch
         c->batch_tickets_bytes = need_t * 2;
+    }
+    return MNR_OK;
+}
+
+// Batched launch(es) over validated chunks.  `f` / `x`: optional second stage (per-column fold + cross-GPU exchange) run
+// by the block that writes the last chunk aggregate of the call.
+static int reduce_batch_launch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
+                               bool minmax, AggRaw* outs, const FoldArgs& f, const XchgDev& x) {
+    // Group the segments by kernel instantiation; order inside a group is the caller's order.
+    struct Key { int dtype, tier, masked; };
+    std::vector<Key> keys;
+    std::vector<std::vector<ReduceSeg>> groups;
+    for (size_t i = 0; i < n; ++i) {
+        const mnr_buf* b = bufs[i];
+        const mnr_bits* v = validities ? validities[i] : nullptr;
+        const Key k{(int)b->dtype, reduce_tier(b->ptr, minmax), v ? 1 : 0};
+        size_t g = 0;
+        for (; g < keys.size(); ++g) if (keys[g].dtype == k.dtype && keys[g].tier == k.tier && keys[g].masked == k.masked) break;
+        if (g == keys.size()) { keys.push_back(k); groups.emplace_back(); }
+        ReduceSeg s;
+        s.data = b->ptr; s.mask = v ? v->ptr : nullptr; s.n = b->len;
+        s.nblk = reduce_nblk(b->dtype, b->len, k.tier, minmax); s.out_index = (uint32_t)i;
+        groups[g].push_back(s);
+    }
+    // One descriptor upload for the whole call (launch order = group order, gridDim.y <= 65535 per launch), so the
+    // launches sit back to back on the stream.  The area is double-buffered; a pageable-source cudaMemcpyAsync stages the
+    // bytes before it returns, so the host vector may die right after; stream order protects the device copy.
+    struct Launch { size_t g, off, cnt; uint32_t max_blk; size_t seg0; };
+    std::vector<Launch> launches;
+    std::vector<ReduceSeg> flat;
+    size_t max_cnt = 0, max_pblk = 0;
+    for (size_t g = 0; g < groups.size(); ++g)
+        for (size_t off = 0; off < groups[g].size(); off += 65535) {
+            const size_t cnt = std::min<size_t>(65535, groups[g].size() - off);
+            uint32_t max_blk = 1;
+            for (size_t i = 0; i < cnt; ++i) max_blk = std::max(max_blk, groups[g][off + i].nblk);
+            launches.push_back(Launch{g, off, cnt, max_blk, flat.size()});
+            flat.insert(flat.end(), groups[g].begin() + off, groups[g].begin() + off + cnt);
+            max_cnt = std::max(max_cnt, cnt);
+            max_pblk = std::max<size_t>(max_pblk, cnt * max_blk);
+        }
+    // Launches of one call run one after the other on the stream, so they share the partials area; tickets are per
+    // segment of a launch and re-arm themselves.
+    int rc = ensure_batch_scratch(c, n, max_cnt, max_pblk);
+    if (rc) return rc;
+    char* dst = static_cast<char*>(c->batch_segs) + (c->batch_flip ? c->batch_segs_bytes / 2 : 0);
+    c->batch_flip ^= 1;
+    CU(cudaMemcpyAsync(dst, flat.data(), flat.size() * sizeof(ReduceSeg), cudaMemcpyHostToDevice, c->stream));
+    for (const Launch& L : launches) {
+        CU(launch_reduce_stats_batch((mnr_dtype)keys[L.g].dtype, keys[L.g].tier, keys[L.g].masked != 0, minmax,
+                                     reinterpret_cast<const ReduceSeg*>(dst) + L.seg0, (uint32_t)L.cnt, L.max_blk,
+                                     static_cast<AggRaw*>(c->batch_partials), static_cast<unsigned int*>(c->batch_tickets),
+                                     outs, f, x, c->stream));
+        c->launches++;
     }
     return MNR_OK;
 }
@@ -956,49 +1041,12 @@ int mnr_reduce_stats_batch_async(mnr_ctx* c, size_t n, const mnr_buf* const* buf
     REQUIRE(c && (bufs || n == 0) && (out_device || n == 0), MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
     REQUIRE((reinterpret_cast<uintptr_t>(out_device) & 15u) == 0, MNR_ERR_INVALID_ARGUMENTS, "out_device must be 16-byte aligned");
     if (n == 0) return MNR_OK;
-    const bool minmax = with_minmax != 0;
     for (size_t i = 0; i < n; ++i) {
         int rc = check_reduce(c, bufs[i], validities ? validities[i] : nullptr);
         if (rc) return rc;
     }
     CU(cudaSetDevice(c->device));
-    // Group the segments by kernel instantiation; order inside a group is the caller's order.
-    struct Key { int dtype, tier, masked, sdiv; };
-    std::vector<Key> keys;
-    std::vector<std::vector<ReduceSeg>> groups;
-    for (size_t i = 0; i < n; ++i) {
-        const mnr_buf* b = bufs[i];
-        const mnr_bits* v = validities ? validities[i] : nullptr;
-        const Key k{(int)b->dtype, reduce_tier(b->ptr, minmax), v ? 1 : 0};
-        size_t g = 0;
-        for (; g < keys.size(); ++g) if (keys[g].dtype == k.dtype && keys[g].tier == k.tier && keys[g].masked == k.masked && keys[g].sdiv == k.sdiv) break;
-        if (g == keys.size()) { keys.push_back(k); groups.emplace_back(); }
-        ReduceSeg s;
-        s.data = b->ptr; s.mask = v ? v->ptr : nullptr; s.n = b->len;
-        s.nblk = reduce_nblk(b->dtype, b->len, k.tier, minmax); s.out_index = (uint32_t)i;
-        groups[g].push_back(s);
-    }
-    for (size_t g = 0; g < groups.size(); ++g) {
-        // gridDim.y <= 65535
-        for (size_t off = 0; off < groups[g].size(); off += 65535) {
-            const size_t cnt = std::min<size_t>(65535, groups[g].size() - off);
-            uint32_t max_blk = 1;
-            for (size_t i = 0; i < cnt; ++i) max_blk = std::max(max_blk, groups[g][off + i].nblk);
-            int rc = ensure_batch_scratch(c, cnt, max_blk);
-            if (rc) return rc;
-            // The descriptor area is double-buffered; pageable-source cudaMemcpyAsync stages the bytes before returning,
-            // so the host vector may die right after.  Stream order protects the device copy between launches.
-            char* dst = static_cast<char*>(c->batch_segs) + (c->batch_flip ? c->batch_segs_bytes / 2 : 0);
-            c->batch_flip ^= 1;
-            CU(cudaMemcpyAsync(dst, groups[g].data() + off, cnt * sizeof(ReduceSeg), cudaMemcpyHostToDevice, c->stream));
-            CU(launch_reduce_stats_batch((mnr_dtype)keys[g].dtype, keys[g].tier, keys[g].masked != 0, minmax,
-                                         reinterpret_cast<const ReduceSeg*>(dst), (uint32_t)cnt, max_blk,
-                                         static_cast<AggRaw*>(c->batch_partials), static_cast<unsigned int*>(c->batch_tickets),
-                                         static_cast<AggRaw*>(out_device), c->stream));
-            c->launches++;
-        }
-    }
-    return MNR_OK;
+    return reduce_batch_launch(c, n, bufs, validities, with_minmax != 0, static_cast<AggRaw*>(out_device), FoldArgs{}, XchgDev{});
 }
 
 int mnr_reduce_stats_batch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
@@ -1007,7 +1055,8 @@ int mnr_reduce_stats_batch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, con
     if (n == 0) return MNR_OK;
     CU(cudaSetDevice(c->device));
     if (c->chunk_aggs_cap < n) {
-        if (c->chunk_aggs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->chunk_aggs)); c->chunk_aggs = nullptr; }
+        if (c->chunk_aggs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->chunk_aggs)); }
+        c->chunk_aggs = nullptr; c->chunk_aggs_cap = 0;
         CU(cudaMalloc(&c->chunk_aggs, sizeof(AggRaw) * n));
         c->chunk_aggs_cap = n;
     }
@@ -1018,18 +1067,10 @@ int mnr_reduce_stats_batch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, con
     return MNR_OK;
 }
 
-// ---- fused reduction + cross-GPU exchange (one process per GPU; peers' mailboxes mapped through CUDA IPC) ----------------
-struct mnr_xchg {
-    mnr_ctx* ctx = nullptr;
-    int world = 0, rank = 0;
-    unsigned long long epoch = 0;
-    char* mailbox = nullptr;                 // own mailbox (cudaMalloc: IPC-exportable)
-    char* peers[kMaxPeers] = {};             // every rank's mailbox as mapped here (peers[rank] == mailbox)
-    bool opened[kMaxPeers] = {};
-    unsigned int* err = nullptr;             // device word: a peer's flag never arrived
-    bool connected = false;
-};
-static constexpr size_t kMailboxBytes = 2 * kMaxPeers * 64;
+// ---- fused reduction + cross-GPU exchange ---------------------------------------------------------------------------------
+// One mailbox per rank; peers map it through CUDA IPC (one process per GPU) or plain peer access (one process, many GPUs).
+static constexpr unsigned kSlotBytes = (kXchgHeader + 32u * MNR_XCHG_MAX_AGGS + 63u) & ~63u;
+static constexpr size_t kMailboxBytes = (size_t)2 * kMaxPeers * kSlotBytes;
 
 int mnr_xchg_create(mnr_ctx* c, int world, int rank, mnr_xchg** out) {
     REQUIRE(c && out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
@@ -1038,11 +1079,17 @@ int mnr_xchg_create(mnr_ctx* c, int world, int rank, mnr_xchg** out) {
     CU(cudaSetDevice(c->device));
     mnr_xchg* x = new mnr_xchg();
     x->ctx = c; x->world = world; x->rank = rank;
-    CU(cudaMalloc(&x->mailbox, kMailboxBytes));
-    CU(cudaMemset(x->mailbox, 0, kMailboxBytes));
-    CU(cudaMalloc(&x->err, 64));
-    CU(cudaMemset(x->err, 0, 64));
-    CU(cudaDeviceSynchronize());
+    cudaError_t e = cudaMalloc(&x->mailbox, kMailboxBytes);
+    if (e == cudaSuccess) e = cudaMemset(x->mailbox, 0, kMailboxBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&x->err, 64);
+    if (e == cudaSuccess) e = cudaMemset(x->err, 0, 64);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        if (x->mailbox) cudaFree(x->mailbox);
+        if (x->err) cudaFree(x->err);
+        delete x;
+        return fail_cuda(e, "mnr_xchg_create");
+    }
     x->peers[rank] = x->mailbox;
     x->connected = world == 1;
     *out = x;
@@ -1063,7 +1110,7 @@ int mnr_xchg_connect(mnr_xchg* x, const uint8_t* handles) {
     REQUIRE(x && handles, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
     CU(cudaSetDevice(x->ctx->device));
     for (int r = 0; r < x->world; ++r) {
-        if (r == x->rank || x->opened[r]) continue;
+        if (r == x->rank || x->opened[r] || x->peers[r]) continue;
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + (size_t)r * MNR_IPC_HANDLE_BYTES, sizeof h);
         void* p = nullptr;
@@ -1072,6 +1119,40 @@ int mnr_xchg_connect(mnr_xchg* x, const uint8_t* handles) {
         x->opened[r] = true;
     }
     x->connected = true;
+    return MNR_OK;
+}
+
+int mnr_xchg_connect_local(mnr_xchg* x, mnr_xchg* const* peers) {
+    REQUIRE(x && peers, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    CU(cudaSetDevice(x->ctx->device));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        REQUIRE(peers[r] && peers[r]->world == x->world && peers[r]->rank == r, MNR_ERR_INVALID_ARGUMENTS,
+                "peers[%d] is not rank %d of a %d-rank exchange", r, r, x->world);
+        const int pd = peers[r]->ctx->device;
+        if (pd == x->ctx->device) x->shares_device = true;   // two "virtual ranks" on one GPU: nothing to enable
+        else {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, x->ctx->device, pd));
+            REQUIRE(can, MNR_ERR_CUDA, "device %d cannot access device %d (no P2P path)", x->ctx->device, pd);
+            cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+        }
+        x->peers[r] = peers[r]->mailbox;
+    }
+    x->connected = true;
+    return MNR_OK;
+}
+
+int mnr_xchg_status(mnr_xchg* x, int clear, int* timed_out) {
+    REQUIRE(x && timed_out, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    CU(cudaSetDevice(x->ctx->device));
+    unsigned int h = 0;
+    CU(cudaMemcpyAsync(&h, x->err, 4, cudaMemcpyDeviceToHost, x->ctx->stream));
+    CU(cudaStreamSynchronize(x->ctx->stream));
+    if (h && clear) { CU(cudaMemsetAsync(x->err, 0, 4, x->ctx->stream)); CU(cudaStreamSynchronize(x->ctx->stream)); }
+    *timed_out = h != 0;
     return MNR_OK;
 }
 
@@ -1085,20 +1166,49 @@ void mnr_xchg_destroy(mnr_xchg* x) {
     delete x;
 }
 
+static int check_xchg(const mnr_ctx* c, const mnr_xchg* x) {
+    REQUIRE(x->ctx == c, MNR_ERR_INVALID_ARGUMENTS, "exchange handle belongs to another context");
+    REQUIRE(x->connected, MNR_ERR_INVALID_ARGUMENTS, "mnr_xchg_connect has not been called");
+    return MNR_OK;
+}
+static XchgDev xchg_dev(const mnr_xchg* x, unsigned long long epoch) {
+    XchgDev d{};
+    d.world = x->world; d.rank = x->rank; d.epoch = epoch; d.err = x->err; d.slot_bytes = kSlotBytes;
+    for (int r = 0; r < x->world; ++r) d.mailbox[r] = x->peers[r];
+    return d;
+}
+
 int mnr_reduce_stats_exchange(mnr_ctx* c, mnr_xchg* x, const mnr_buf* b, const mnr_bits* v, int with_minmax, void* out_device) {
     int rc = check_reduce(c, b, v);
     if (rc) return rc;
-    REQUIRE(x && x->ctx == c, MNR_ERR_INVALID_ARGUMENTS, "exchange handle belongs to another context");
-    REQUIRE(x->connected, MNR_ERR_INVALID_ARGUMENTS, "mnr_xchg_connect has not been called");
+    REQUIRE(x, MNR_ERR_INVALID_ARGUMENTS, "exchange handle is NULL");
+    rc = check_xchg(c, x);
+    if (rc) return rc;
     REQUIRE(out_device && (reinterpret_cast<uintptr_t>(out_device) & 15u) == 0, MNR_ERR_INVALID_ARGUMENTS,
             "out_device must be a 16-byte aligned device pointer");
     CU(cudaSetDevice(c->device));
-    XchgDev d{};
-    d.world = x->world; d.rank = x->rank; d.epoch = ++x->epoch; d.err = x->err;
-    for (int r = 0; r < x->world; ++r) d.mailbox[r] = x->peers[r];
+    // Overlap with the previous reduction (late dependency wait) only when the caller opted in AND nothing else of this
+    // library was launched on the stream since that reduction — an element-wise kernel could be producing this column.
+    const bool late = c->reduce_overlap && c->last_reduce_launch == c->launches && c->launches != 0;
     CU(launch_reduce_stats_xchg(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, with_minmax != 0, c->partials[3], c->ticket[3],
-                                static_cast<AggRaw*>(out_device), nullptr, d, c->stream));
+                                static_cast<AggRaw*>(out_device), nullptr, xchg_dev(x, x->epoch + 1), late, !x->shares_device,
+                                c->stream));
+    x->epoch++;   // only a launch that happened consumes an epoch (a failed one would leave this rank ahead of its peers)
     c->launches++;
+    c->last_reduce_launch = c->launches;
+    return MNR_OK;
+}
+
+// Read-and-clear the exchange's error word after the stream has drained.
+static int finish_exchange_sync(mnr_ctx* c, mnr_xchg* x) {
+    unsigned int* herr = reinterpret_cast<unsigned int*>(static_cast<char*>(c->h_scratch) + 128);
+    CU(cudaMemcpyAsync(herr, x->err, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (*herr) {
+        CU(cudaMemsetAsync(x->err, 0, 4, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return fail(MNR_ERR_CUDA, "fused exchange timed out waiting for a peer's partial (epoch %llu); the result is unusable", x->epoch);
+    }
     return MNR_OK;
 }
 
@@ -1106,12 +1216,111 @@ int mnr_reduce_stats_exchange_sync(mnr_ctx* c, mnr_xchg* x, const mnr_buf* b, co
     REQUIRE(out_host, MNR_ERR_INVALID_ARGUMENTS, "out is NULL");
     int rc = mnr_reduce_stats_exchange(c, x, b, v, with_minmax, c->d_agg);
     if (rc) return rc;
-    unsigned int* herr = reinterpret_cast<unsigned int*>(static_cast<char*>(c->h_scratch) + 128);
     CU(cudaMemcpyAsync(c->h_scratch, c->d_agg, sizeof(AggRaw), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(herr, x->err, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (*herr) return fail(MNR_ERR_CUDA, "fused exchange timed out waiting for a peer's partial (epoch %llu)", x->epoch);
+    rc = finish_exchange_sync(c, x);
+    if (rc) return rc;
     memcpy(out_host, c->h_scratch, sizeof(mnr_agg));
+    return MNR_OK;
+}
+
+// ---- sharded SuperArray / SuperTable reduction: chunk aggregates -> per-column fold -> exchange, one call ---------------
+static void agg_identity(mnr_dtype dt, AggRaw* a) {
+    a->sum = 0; a->count = 0;
+    const uint64_t nan = 0x7ff8000000000000ull;
+    switch (dt) {
+        case MNR_I8: a->mn = (uint64_t)(int64_t)INT8_MAX; a->mx = (uint64_t)(int64_t)INT8_MIN; break;
+        case MNR_I16: a->mn = (uint64_t)(int64_t)INT16_MAX; a->mx = (uint64_t)(int64_t)INT16_MIN; break;
+        case MNR_I32: a->mn = (uint64_t)(int64_t)INT32_MAX; a->mx = (uint64_t)(int64_t)INT32_MIN; break;
+        case MNR_I64: a->mn = (uint64_t)INT64_MAX; a->mx = (uint64_t)INT64_MIN; break;
+        case MNR_U8: a->mn = UINT8_MAX; a->mx = 0; break;
+        case MNR_U16: a->mn = UINT16_MAX; a->mx = 0; break;
+        case MNR_U32: a->mn = UINT32_MAX; a->mx = 0; break;
+        case MNR_U64: a->mn = UINT64_MAX; a->mx = 0; break;
+        default: a->mn = nan; a->mx = nan; break;
+    }
+}
+static int dtype_kind(mnr_dtype dt);
+
+int mnr_reduce_stats_batch_exchange(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr_buf* const* bufs,
+                                    const mnr_bits* const* validities, int with_minmax, size_t n_cols,
+                                    const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes, void* out_device) {
+    REQUIRE(c && (bufs || n == 0) && (col_of_chunk || n == 0) && col_dtypes && out_device, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    REQUIRE(n_cols >= 1 && n_cols <= MNR_XCHG_MAX_AGGS, MNR_ERR_INVALID_ARGUMENTS, "n_cols %zu out of range (1..%d)", n_cols, MNR_XCHG_MAX_AGGS);
+    REQUIRE((reinterpret_cast<uintptr_t>(out_device) & 15u) == 0, MNR_ERR_INVALID_ARGUMENTS, "out_device must be 16-byte aligned");
+    REQUIRE(n <= 0xffffffffull, MNR_ERR_INVALID_ARGUMENTS, "too many chunks");
+    if (x) { int rc = check_xchg(c, x); if (rc) return rc; }
+    for (size_t g = 0; g < n_cols; ++g) REQUIRE(valid_dtype(col_dtypes[g]), MNR_ERR_UNSUPPORTED_TYPE, "column %zu: unknown dtype %d", g, (int)col_dtypes[g]);
+    for (size_t i = 0; i < n; ++i) {
+        int rc = check_reduce(c, bufs[i], validities ? validities[i] : nullptr);
+        if (rc) return rc;
+        REQUIRE(col_of_chunk[i] < n_cols, MNR_ERR_OUT_OF_BOUNDS, "chunk %zu: column %u of %zu", i, col_of_chunk[i], n_cols);
+        REQUIRE(bufs[i]->dtype == col_dtypes[col_of_chunk[i]], MNR_ERR_TYPE_MISMATCH, "chunk %zu has dtype %d, its column %u has %d", i,
+                (int)bufs[i]->dtype, col_of_chunk[i], (int)col_dtypes[col_of_chunk[i]]);
+    }
+    CU(cudaSetDevice(c->device));
+    // fold descriptor: [grp_off (n_cols+1) u32][grp_idx n u32][pad to 16][identity n_cols x 32 B][kind n_cols u8]
+    const size_t off_idx = (n_cols + 1) * 4, off_id = (off_idx + n * 4 + 15) & ~(size_t)15, off_kind = off_id + n_cols * 32;
+    const size_t desc_bytes = (off_kind + n_cols + 15) & ~(size_t)15;
+    std::vector<unsigned char> desc(desc_bytes, 0);
+    uint32_t* grp_off = reinterpret_cast<uint32_t*>(desc.data());
+    uint32_t* grp_idx = reinterpret_cast<uint32_t*>(desc.data() + off_idx);
+    for (size_t i = 0; i < n; ++i) grp_off[col_of_chunk[i] + 1]++;
+    for (size_t g = 0; g < n_cols; ++g) grp_off[g + 1] += grp_off[g];
+    {
+        std::vector<uint32_t> fill(grp_off, grp_off + n_cols);
+        for (size_t i = 0; i < n; ++i) grp_idx[fill[col_of_chunk[i]]++] = (uint32_t)i;   // chunk order inside a column
+    }
+    for (size_t g = 0; g < n_cols; ++g) {
+        agg_identity(col_dtypes[g], reinterpret_cast<AggRaw*>(desc.data() + off_id) + g);
+        desc[off_kind + g] = (unsigned char)dtype_kind(col_dtypes[g]);
+    }
+    const size_t need_aggs = n ? n : 1;
+    if (c->chunk_aggs_cap < need_aggs) {
+        if (c->chunk_aggs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->chunk_aggs)); }
+        c->chunk_aggs = nullptr; c->chunk_aggs_cap = 0;
+        CU(cudaMalloc(&c->chunk_aggs, sizeof(AggRaw) * need_aggs));
+        c->chunk_aggs_cap = need_aggs;
+    }
+    if (c->fold_desc_bytes < desc_bytes * 2) {
+        if (c->fold_desc) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->fold_desc)); }
+        c->fold_desc = nullptr; c->fold_desc_bytes = 0;
+        CU(cudaMalloc(&c->fold_desc, desc_bytes * 2));
+        c->fold_desc_bytes = desc_bytes * 2;
+    }
+    char* dd = static_cast<char*>(c->fold_desc) + (c->fold_flip ? c->fold_desc_bytes / 2 : 0);
+    c->fold_flip ^= 1;
+    CU(cudaMemcpyAsync(dd, desc.data(), desc_bytes, cudaMemcpyHostToDevice, c->stream));
+    FoldArgs f{};
+    f.gticket = c->ticket[3] + 12;
+    f.total_segs = (uint32_t)n; f.n_groups = (uint32_t)n_cols;
+    f.grp_off = reinterpret_cast<const uint32_t*>(dd);
+    f.grp_idx = reinterpret_cast<const uint32_t*>(dd + off_idx);
+    f.identity = reinterpret_cast<const AggRaw*>(dd + off_id);
+    f.kind = reinterpret_cast<const uint8_t*>(dd + off_kind);
+    f.local = c->fold_local;
+    f.result = static_cast<AggRaw*>(out_device);
+    f.result_host = nullptr;
+    const XchgDev xd = x ? xchg_dev(x, x->epoch + 1) : XchgDev{};
+    if (n == 0) {
+        CU(launch_fold_exchange(c->chunk_aggs, f, xd, c->stream));
+        c->launches++;
+    } else {
+        int rc = reduce_batch_launch(c, n, bufs, validities, with_minmax != 0, c->chunk_aggs, f, xd);
+        if (rc) { cudaMemsetAsync(f.gticket, 0, 4, c->stream); return rc; }   // the fold only fires after the LAST launch: no epoch was consumed
+    }
+    if (x) x->epoch++;
+    return MNR_OK;
+}
+
+int mnr_reduce_stats_batch_exchange_sync(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr_buf* const* bufs,
+                                         const mnr_bits* const* validities, int with_minmax, size_t n_cols,
+                                         const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes, mnr_agg* out_host) {
+    REQUIRE(c && out_host, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+    int rc = mnr_reduce_stats_batch_exchange(c, x, n, bufs, validities, with_minmax, n_cols, col_of_chunk, col_dtypes, c->fold_result);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_host, c->fold_result, sizeof(mnr_agg) * n_cols, cudaMemcpyDeviceToHost, c->stream));
+    if (x) return finish_exchange_sync(c, x);
+    CU(cudaStreamSynchronize(c->stream));
     return MNR_OK;
 }
 
@@ -1230,7 +1439,7 @@ static int apply_host_impl(mnr_ctx* c, mnr_dtype dtype, int op, bool is_fma, con
             EwArgs a{};
             a.dtype = dtype; a.op = op; a.lhs = st[0]; a.rhs = st[1];
             a.lmask = mask ? static_cast<uint8_t*>(st[4]) : nullptr;
-            a.out = st[3]; a.out_mask = mask ? static_cast<uint8_t*>(st[5]) : nullptr; a.n = rows; a.div0_flag = flag;
+            a.out = st[3]; a.out_mask = mask ? static_cast<uint8_t*>(st[5]) : nullptr; a.n = rows; a.div0_flag = flag; a.k = c->knobs;
             CU(launch_ew_binary(a, s));
         }
         c->launches++;
@@ -1281,7 +1490,8 @@ int mnr_stats_host(mnr_ctx* c, mnr_dtype dtype, const void* data, size_t len, co
     int rc = ensure_stage(c, chunk * 8);
     if (rc) return rc;
     if (c->chunk_aggs_cap < nchunks) {
-        if (c->chunk_aggs) CU(cudaFree(c->chunk_aggs));
+        if (c->chunk_aggs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->chunk_aggs)); }
+        c->chunk_aggs = nullptr; c->chunk_aggs_cap = 0;   // never leave a dangling pointer behind a failed cudaMalloc
         CU(cudaMalloc(&c->chunk_aggs, sizeof(AggRaw) * nchunks));
         c->chunk_aggs_cap = nchunks;
     }

@@ -11,20 +11,6 @@
 
 namespace mnr {
 
-#if MNR_EW_DTYPE == 100
-int g_ew_grid_cap = 0;   // >0: cap every element-wise grid at this many blocks (tuning knob, mnr_ctx_set_option)
-int g_ew_max_tier = 2;   // 1: never use the 256-bit tier (tuning knob)
-int g_ew_sdiv64_cfg = 0; // launch geometry of 64-bit column / scalar (tuning knob, see CfgSdiv64)
-int g_ew_fdiv_cfg = 0;   // launch geometry of float Div / FloorDiv (tuning knob, see CfgFdiv2 / CfgFdiv3)
-int g_ew_heavy_cfg = 0;  // launch geometry of integer Div/Rem/FloorDiv, float Rem, Power (tuning knob, 2 / 3 = CfgFdiv2 / CfgFdiv3)
-#else
-extern int g_ew_grid_cap;
-extern int g_ew_max_tier;
-extern int g_ew_sdiv64_cfg;
-extern int g_ew_fdiv_cfg;
-extern int g_ew_heavy_cfg;
-#endif
-
 // MINB = 4 caps the kernel at 128 registers (4 blocks/SM).  1-byte columns carry the packed SIMD-in-register path (~150
 // registers uncapped) and gain from the cap; 4/8-byte kernels fit 128 registers on their own, the cap only matters for
 // their batched variants (C5 scalar broadcast 6.30 -> 6.77 TB/s, r01j -> r01s); 2-byte columns LOSE with it (r01v:
@@ -62,13 +48,13 @@ static EwDev to_dev(const EwArgs& a) {
 }
 
 template <int BLOCK, int U, int MINB, bool RESIDENT>
-static unsigned ew_grid(uint64_t n, int vec) {
+static unsigned ew_grid(uint64_t n, int vec, int grid_cap = 0) {
     const uint64_t nvec = (n + vec - 1) / vec;
     const uint64_t tiles = (nvec + 32ull * U - 1) / (32ull * U);
     uint64_t blocks = (tiles + (BLOCK / 32) - 1) / (BLOCK / 32);
     if (blocks < 1) blocks = 1;
     if (RESIDENT && blocks > (uint64_t)kSMs * MINB) blocks = (uint64_t)kSMs * MINB;
-    if (g_ew_grid_cap > 0 && blocks > (uint64_t)g_ew_grid_cap) blocks = (uint64_t)g_ew_grid_cap;
+    if (grid_cap > 0 && blocks > (uint64_t)grid_cap) blocks = (uint64_t)grid_cap;
     if (blocks > 0x7fffffffull) blocks = 0x7fffffffull;
     return (unsigned)blocks;
 }
@@ -77,17 +63,17 @@ template <typename T, typename TL, typename TR, typename VecT, int CLS, typename
 static cudaError_t go(const EwArgs& a, cudaStream_t s) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     const bool masked = a.lmask || a.rmask;
-    const unsigned grid = ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(a.n, VEC);
+    const unsigned grid = ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(a.n, VEC, a.k.grid_cap);
     if (masked) ew_binary_kernel<T, TL, TR, VecT, CLS, true, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(to_dev(a));
     else ew_binary_kernel<T, TL, TR, VecT, CLS, false, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(to_dev(a));
     return cudaGetLastError();
 }
 
 template <typename T, typename VecT, int CLS>
-static cudaError_t go_batch(bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
+static cudaError_t go_batch(bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, int grid_cap, cudaStream_t s) {
     using Cfg = typename CfgOf<CLS, (int)sizeof(T)>::type;
     constexpr int VEC = sizeof(VecT) / sizeof(T);
-    const dim3 grid(ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(max_n, VEC), nseg, 1);
+    const dim3 grid(ew_grid<Cfg::BLOCK, Cfg::U, Cfg::MINB, Cfg::RESIDENT>(max_n, VEC, grid_cap), nseg, 1);
     if (masked) ew_binary_batch_kernel<T, T, T, VecT, CLS, true, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(segs);
     else ew_binary_batch_kernel<T, T, T, VecT, CLS, false, Cfg::BLOCK, Cfg::U, Cfg::MINB><<<grid, Cfg::BLOCK, 0, s>>>(segs);
     return cudaGetLastError();
@@ -95,23 +81,23 @@ static cudaError_t go_batch(bool masked, const EwDev* segs, uint32_t nseg, uint6
 
 // tier 2 = the class's wide vector (256-bit for cheap ops), tier 1 = 128-bit.  Unaligned items are launched one by one.
 template <typename T, int CLS>
-static cudaError_t go_batch_tier(int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
+static cudaError_t go_batch_tier(int tier, bool masked, const EwDev* segs, uint32_t nseg, uint64_t max_n, int grid_cap, cudaStream_t s) {
     using Wide = typename CfgOf<CLS, (int)sizeof(T)>::type::Wide;
-    if (tier == 2) return go_batch<T, Wide, CLS>(masked, segs, nseg, max_n, s);
-    return go_batch<T, V16, CLS>(masked, segs, nseg, max_n, s);
+    if (tier == 2) return go_batch<T, Wide, CLS>(masked, segs, nseg, max_n, grid_cap, s);
+    return go_batch<T, V16, CLS>(masked, segs, nseg, max_n, grid_cap, s);
 }
 
 template <typename T>
-static cudaError_t go_batch_t(int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg, uint64_t max_n, cudaStream_t s) {
+static cudaError_t go_batch_t(int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg, uint64_t max_n, int grid_cap, cudaStream_t s) {
     if constexpr (!Traits<T>::is_float) {
-        if (sdiv) return go_batch_tier<T, CLS_SDIV>(tier, masked, segs, nseg, max_n, s);
+        if (sdiv) return go_batch_tier<T, CLS_SDIV>(tier, masked, segs, nseg, max_n, grid_cap, s);
     }
     switch (op_class(Traits<T>::is_float, op)) {
-        case CLS_CHEAP: return go_batch_tier<T, CLS_CHEAP>(tier, masked, segs, nseg, max_n, s);
-        case CLS_DIV: return go_batch_tier<T, CLS_DIV>(tier, masked, segs, nseg, max_n, s);
-        case CLS_POW: return go_batch_tier<T, CLS_POW>(tier, masked, segs, nseg, max_n, s);
+        case CLS_CHEAP: return go_batch_tier<T, CLS_CHEAP>(tier, masked, segs, nseg, max_n, grid_cap, s);
+        case CLS_DIV: return go_batch_tier<T, CLS_DIV>(tier, masked, segs, nseg, max_n, grid_cap, s);
+        case CLS_POW: return go_batch_tier<T, CLS_POW>(tier, masked, segs, nseg, max_n, grid_cap, s);
         case CLS_REM:
-            if constexpr (Traits<T>::is_float) return go_batch_tier<T, CLS_REM>(tier, masked, segs, nseg, max_n, s);
+            if constexpr (Traits<T>::is_float) return go_batch_tier<T, CLS_REM>(tier, masked, segs, nseg, max_n, grid_cap, s);
             break;
     }
     return cudaErrorInvalidValue;
@@ -124,7 +110,7 @@ static cudaError_t go_align(const EwArgs& a, cudaStream_t s) {
     using Wide = typename Cfg::Wide;
     auto ok = [](const void* p, size_t align) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % align) == 0; };
     constexpr int VW = sizeof(Wide) / sizeof(T);
-    if (sizeof(Wide) > 16 && g_ew_max_tier >= 2 && ok(a.lhs, sizeof(TL) * VW) && ok(a.rhs, sizeof(TR) * VW) && ok(a.out, sizeof(Wide)))
+    if (sizeof(Wide) > 16 && a.k.max_tier >= 2 && ok(a.lhs, sizeof(TL) * VW) && ok(a.rhs, sizeof(TR) * VW) && ok(a.out, sizeof(Wide)))
         return go<T, TL, TR, Wide, CLS, Cfg>(a, s);
     constexpr int V = 16 / sizeof(T);
     if (ok(a.lhs, sizeof(TL) * V) && ok(a.rhs, sizeof(TR) * V) && ok(a.out, 16)) return go<T, TL, TR, V16, CLS, Cfg>(a, s);
@@ -143,7 +129,7 @@ static cudaError_t go_align(const EwArgs& a, cudaStream_t s) {
 // ew_heavy_cfg: 0 = the choice below, 1 = CfgHeavy, 2 / 3 = force CfgFdiv2 / CfgFdiv3.
 template <typename T, int CLS>
 static cudaError_t go_heavy(const EwArgs& a, cudaStream_t s) {
-    int cfg = g_ew_heavy_cfg;
+    int cfg = a.k.heavy_cfg;
     if (cfg == 0) {
         const bool masked = a.lmask || a.rmask;
         if (CLS == CLS_POW) cfg = 2;
@@ -165,7 +151,7 @@ static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
             if constexpr (sizeof(T) == 8) {
                 // 0 = masked -> CfgSdiv64, dense -> CfgCheap; 1 / 2 force one of them (tools/sdiv64_exp.py)
                 const bool masked = a.lmask || a.rmask;
-                if (g_ew_sdiv64_cfg == 2 || (g_ew_sdiv64_cfg == 0 && masked)) return go_align<T, T, T, CLS_SDIV, CfgSdiv64>(a, s);
+                if (a.k.sdiv64_cfg == 2 || (a.k.sdiv64_cfg == 0 && masked)) return go_align<T, T, T, CLS_SDIV, CfgSdiv64>(a, s);
             }
             return go_align<T, T, T, CLS_SDIV>(a, s);
         }
@@ -175,7 +161,7 @@ static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
         case CLS_DIV:
             if constexpr (Traits<T>::is_float) {
                 // ew_fdiv_cfg: 0 = the table above, 1 = CfgHeavy, 2 / 3 = force CfgFdiv2 / CfgFdiv3
-                int cfg = g_ew_fdiv_cfg;
+                int cfg = a.k.fdiv_cfg;
                 if (cfg == 0) {
                     const bool masked = a.lmask || a.rmask, scalar = !a.lhs || !a.rhs;
                     cfg = scalar ? (masked ? 3 : 2) : (masked ? (sizeof(T) == 8 ? 2 : 3) : 2);
@@ -196,8 +182,8 @@ static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
 #define MNR_EW_ENTRY(NAME, T)                                                                                         \
     cudaError_t NAME(const EwArgs& a, cudaStream_t s) { return go_t<T>(a, s); }                                       \
     cudaError_t NAME##_batch(int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg,              \
-                             uint64_t max_n, cudaStream_t s) {                                                        \
-        return go_batch_t<T>(op, tier, masked, sdiv, segs, nseg, max_n, s);                                           \
+                             uint64_t max_n, int grid_cap, cudaStream_t s) {                                          \
+        return go_batch_t<T>(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);                                 \
     }
 
 #if MNR_EW_DTYPE == 6
@@ -224,15 +210,15 @@ MNR_EW_ENTRY(launch_ew_f64, double)
 
 #define MNR_EW_DECL(NAME)                                 \
     cudaError_t NAME(const EwArgs&, cudaStream_t);         \
-    cudaError_t NAME##_batch(int, int, bool, bool, const EwDev*, uint32_t, uint64_t, cudaStream_t);
+    cudaError_t NAME##_batch(int, int, bool, bool, const EwDev*, uint32_t, uint64_t, int, cudaStream_t);
 MNR_EW_DECL(launch_ew_i8) MNR_EW_DECL(launch_ew_u8) MNR_EW_DECL(launch_ew_i16) MNR_EW_DECL(launch_ew_u16)
 MNR_EW_DECL(launch_ew_i32) MNR_EW_DECL(launch_ew_u32) MNR_EW_DECL(launch_ew_i64) MNR_EW_DECL(launch_ew_u64)
 MNR_EW_DECL(launch_ew_f32) MNR_EW_DECL(launch_ew_f64)
 
 // 2: every pointer allows the op class's wide vector; 1: 128-bit; 0: element loads (not batched).
-int ew_batch_tier(mnr_dtype dt, int op, bool sdiv, const void* lhs, const void* rhs, const void* out) {
+int ew_batch_tier(mnr_dtype dt, int op, bool sdiv, const void* lhs, const void* rhs, const void* out, int max_tier) {
     const bool is_float = dt == MNR_F32 || dt == MNR_F64;
-    const unsigned wide = (sdiv || op_class(is_float, op) == CLS_CHEAP) ? 32u : 16u;
+    const unsigned wide = ((sdiv || op_class(is_float, op) == CLS_CHEAP) && max_tier >= 2) ? 32u : 16u;
     auto ok = [](const void* p, unsigned al) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (al - 1)) == 0; };
     if (wide > 16 && ok(lhs, wide) && ok(rhs, wide) && ok(out, wide)) return 2;
     if (ok(lhs, 16) && ok(rhs, 16) && ok(out, 16)) return wide == 16 ? 2 : 1;
@@ -240,18 +226,18 @@ int ew_batch_tier(mnr_dtype dt, int op, bool sdiv, const void* lhs, const void* 
 }
 
 cudaError_t launch_ew_batch(mnr_dtype dt, int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg,
-                            uint64_t max_n, cudaStream_t s) {
+                            uint64_t max_n, int grid_cap, cudaStream_t s) {
     switch (dt) {
-        case MNR_I8: return launch_ew_i8_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_U8: return launch_ew_u8_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_I16: return launch_ew_i16_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_U16: return launch_ew_u16_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_I32: return launch_ew_i32_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_U32: return launch_ew_u32_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_I64: return launch_ew_i64_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_U64: return launch_ew_u64_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_F32: return launch_ew_f32_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
-        case MNR_F64: return launch_ew_f64_batch(op, tier, masked, sdiv, segs, nseg, max_n, s);
+        case MNR_I8: return launch_ew_i8_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_U8: return launch_ew_u8_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_I16: return launch_ew_i16_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_U16: return launch_ew_u16_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_I32: return launch_ew_i32_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_U32: return launch_ew_u32_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_I64: return launch_ew_i64_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_U64: return launch_ew_u64_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_F32: return launch_ew_f32_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
+        case MNR_F64: return launch_ew_f64_batch(op, tier, masked, sdiv, segs, nseg, max_n, grid_cap, s);
     }
     return cudaErrorInvalidValue;
 }

@@ -17,20 +17,33 @@ cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* m
                                 AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s);
 // Fused reduction + cross-GPU exchange over peer memory (reduce_kernels.cuh "fused cross-GPU finish").
 struct XchgDev;
+// late_wait: take the programmatic-dependency wait after the streaming phase (column known to be at rest).
+// pdl: launch with the programmatic-stream-serialization attribute (see mnr_xchg::shares_device for when not to).
 cudaError_t launch_reduce_stats_xchg(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
                                      AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host,
-                                     const XchgDev& x, cudaStream_t s);
+                                     const XchgDev& x, bool late_wait, bool pdl, cudaStream_t s);
 // Batched form: one launch for `nseg` columns/chunks of one (dtype, alignment tier, masked) class.
 struct ReduceSeg;
 int reduce_tier(const void* data, bool minmax);
 uint32_t reduce_nblk(mnr_dtype dt, uint64_t n, int tier, bool minmax);
+// f.gticket != NULL adds the second stage: per-column fold of the chunk aggregates + cross-GPU exchange (FoldArgs).
+struct FoldArgs;
 cudaError_t launch_reduce_stats_batch(mnr_dtype dt, int tier, bool masked, bool minmax, const ReduceSeg* segs,
                                       uint32_t nseg, uint32_t max_blk, AggRaw* partials, unsigned int* tickets,
-                                      AggRaw* outs, cudaStream_t s);
+                                      AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s);
+cudaError_t launch_fold_exchange(const AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s);
 
 // Element-wise binary op.  lhs/rhs: device pointers, or NULL for the side held in `scalar_bits`
 // (at most one).  lmask/rmask: NULL or validity bytes indexed from bit 0.  out_mask: required iff a mask is
 // given.  div0_flag: device word set to 1 when a dense integer Div/Rem/FloorDiv meets a zero divisor.
+// Launch-geometry knobs of the element-wise kernels (mnr_ctx_set_option; per context, carried by value in EwArgs).
+struct EwKnobs {
+    int grid_cap = 0;     // > 0: cap every element-wise grid at this many blocks
+    int max_tier = 2;     // 1: never use the 256-bit tier
+    int sdiv64_cfg = 0;   // geometry of 64-bit column / scalar (elementwise.cu CfgSdiv64)
+    int fdiv_cfg = 0;     // geometry of float Div / FloorDiv (CfgFdiv2 / CfgFdiv3)
+    int heavy_cfg = 0;    // geometry of integer Div/Rem/FloorDiv, float Rem, Power
+};
 struct EwArgs {
     mnr_dtype dtype;
     int op;
@@ -49,15 +62,16 @@ struct EwArgs {
     int sdiv;
     uint64_t magic_m;
     uint32_t magic_s1, magic_s2;
+    EwKnobs k;
 };
 cudaError_t launch_ew_binary(const EwArgs& a, cudaStream_t s);
 // I32 operand promoted on load against an F32/F64 operand (routing/arithmetic.rs:244-269).
 cudaError_t launch_ew_promote(const EwArgs& a, mnr_dtype lhs_dtype, mnr_dtype rhs_dtype, cudaStream_t s);
 // Batched element-wise launch: `segs` = device array of EwDev descriptors of one (dtype, op class, masked, tier) class.
 struct EwDev;
-int ew_batch_tier(mnr_dtype dt, int op, bool sdiv, const void* lhs, const void* rhs, const void* out);
+int ew_batch_tier(mnr_dtype dt, int op, bool sdiv, const void* lhs, const void* rhs, const void* out, int max_tier);
 cudaError_t launch_ew_batch(mnr_dtype dt, int op, int tier, bool masked, bool sdiv, const EwDev* segs, uint32_t nseg,
-                            uint64_t max_n, cudaStream_t s);
+                            uint64_t max_n, int grid_cap, cudaStream_t s);
 cudaError_t launch_ew_fma(mnr_dtype dt, const void* a, const void* b, const void* c, const uint8_t* mask, void* out,
                           uint8_t* out_mask, uint64_t n, cudaStream_t s);
 
@@ -118,6 +132,33 @@ struct mnr_ctx {
     void* ew_segs = nullptr;               // batched element-wise descriptors (double-buffered)
     size_t ew_segs_bytes = 0;
     int ew_flip = 0;
+    mnr::EwKnobs knobs;                    // per-context launch-geometry knobs (mnr_ctx_set_option)
+    // sharded reductions: per-column fold descriptors (double-buffered), this rank's column partials, results
+    void* fold_desc = nullptr;
+    size_t fold_desc_bytes = 0;
+    int fold_flip = 0;
+    mnr::AggRaw* fold_local = nullptr;     // MNR_XCHG_MAX_AGGS aggregates
+    mnr::AggRaw* fold_result = nullptr;    // MNR_XCHG_MAX_AGGS aggregates
+    // consecutive reductions may overlap (programmatic dependent launch) when the caller opted in and no other kernel of
+    // this library was launched on the stream in between
+    int reduce_overlap = 0;
+    uint64_t last_reduce_launch = 0;       // value of `launches` right after the last exchange reduction
+};
+
+// Cross-GPU mailbox set of one rank (reduce_kernels.cuh "fused cross-GPU finish").
+struct mnr_xchg {
+    mnr_ctx* ctx = nullptr;
+    int world = 0, rank = 0;
+    unsigned long long epoch = 0;
+    char* mailbox = nullptr;                 // own mailbox (cudaMalloc: IPC-exportable)
+    char* peers[16] = {};                    // every rank's mailbox as mapped here (peers[rank] == mailbox)
+    bool opened[16] = {};                    // mapped through CUDA IPC (to be closed)
+    unsigned int* err = nullptr;             // device word: a peer's flag never arrived
+    bool connected = false;
+    // Another rank of this exchange lives on the SAME device (virtual ranks).  Then reductions are launched without the
+    // programmatic-launch attribute: an early-scheduled successor kernel parks resident blocks at its dependency wait,
+    // and on a shared device those blocks can starve the co-located peer whose flag the predecessor is waiting for.
+    bool shares_device = false;
 };
 
 struct mnr_buf {

@@ -26,19 +26,31 @@ template <typename T, typename VecT, bool MINMAX> static uint32_t nblk_of(uint64
     return (uint32_t)blocks;
 }
 
+// Reductions are launched with the programmatic-stream-serialization attribute (see pdl_* in reduce_kernels.cuh): the
+// kernel after a reduction may be scheduled while the reduction drains.  The kernel itself waits for its predecessor
+// (griddepcontrol.wait) before it reads anything (default) or before it touches the scratch it shares with it (flags bit
+// kReduceLateWait — only when the caller vouches that the column is at rest).
 template <typename T, typename VecT, bool MASKED, bool MINMAX>
 static cudaError_t launch_one(const void* data, const uint8_t* mask, uint64_t n, AggRaw* partials, unsigned int* ticket,
-                              AggRaw* out, AggRaw* out_host, const XchgDev& x, cudaStream_t s) {
-    reduce_stats_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>
-        <<<nblk_of<T, VecT, MINMAX>(n), kRBlock, 0, s>>>(static_cast<const T*>(data), mask, n, partials, ticket, out, out_host, x);
-    return cudaGetLastError();
+                              AggRaw* out, AggRaw* out_host, const XchgDev& x, int flags, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblk_of<T, VecT, MINMAX>(n), 1, 1);
+    cfg.blockDim = dim3(kRBlock, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (flags & kReduceNoPdl) ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, reduce_stats_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>,
+                              static_cast<const T*>(data), mask, n, partials, ticket, out, out_host, x, flags & kReduceLateWait);
 }
 
 template <typename T, typename VecT, bool MASKED, bool MINMAX>
 static cudaError_t launch_batch_one(const ReduceSeg* segs, uint32_t nseg, uint32_t max_blk, AggRaw* partials,
-                                    unsigned int* tickets, AggRaw* outs, cudaStream_t s) {
+                                    unsigned int* tickets, AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s) {
     reduce_stats_batch_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>
-        <<<dim3(max_blk, nseg, 1), kRBlock, 0, s>>>(segs, partials, tickets, outs, max_blk);
+        <<<dim3(max_blk, nseg, 1), kRBlock, 0, s>>>(segs, partials, tickets, outs, max_blk, f, x);
     return cudaGetLastError();
 }
 
@@ -57,10 +69,10 @@ static cudaError_t launch_batch_one(const ReduceSeg* segs, uint32_t nseg, uint32
 
 template <typename T>
 static cudaError_t launch_t(const void* data, const uint8_t* mask, uint64_t n, bool minmax, AggRaw* partials,
-                            unsigned int* ticket, AggRaw* out, AggRaw* out_host, const XchgDev& x, cudaStream_t s) {
+                            unsigned int* ticket, AggRaw* out, AggRaw* out_host, const XchgDev& x, int flags, cudaStream_t s) {
     const int tier = reduce_tier(data, minmax);
     const bool masked = mask != nullptr;
-#define CALL1(V, M, X) return launch_one<T, V, M, X>(data, mask, n, partials, ticket, out, out_host, x, s)
+#define CALL1(V, M, X) return launch_one<T, V, M, X>(data, mask, n, partials, ticket, out, out_host, x, flags, s)
     MNR_REDUCE_DISPATCH(CALL1);
 #undef CALL1
 }
@@ -77,8 +89,8 @@ static uint32_t nblk_t(uint64_t n, int tier, bool minmax) {
 
 template <typename T>
 static cudaError_t batch_t(int tier, bool masked, bool minmax, const ReduceSeg* segs, uint32_t nseg, uint32_t max_blk,
-                           AggRaw* partials, unsigned int* tickets, AggRaw* outs, cudaStream_t s) {
-#define CALLB(V, M, X) return launch_batch_one<T, V, M, X>(segs, nseg, max_blk, partials, tickets, outs, s)
+                           AggRaw* partials, unsigned int* tickets, AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s) {
+#define CALLB(V, M, X) return launch_batch_one<T, V, M, X>(segs, nseg, max_blk, partials, tickets, outs, f, x, s)
     MNR_REDUCE_DISPATCH(CALLB);
 #undef CALLB
 }
@@ -87,19 +99,21 @@ static cudaError_t batch_t(int tier, bool masked, bool minmax, const ReduceSeg* 
 // that switches on the runtime dtype; see the Makefile.
 #define MNR_RED_DECL(NAME)                                                                                                   \
     cudaError_t reduce_single_##NAME(const void*, const uint8_t*, uint64_t, bool, AggRaw*, unsigned int*, AggRaw*, AggRaw*, \
-                                     const XchgDev&, cudaStream_t);                                                          \
+                                     const XchgDev&, int, cudaStream_t);                                                     \
     uint32_t reduce_nblk_##NAME(uint64_t, int, bool);                                                                        \
     cudaError_t reduce_batch_##NAME(int, bool, bool, const ReduceSeg*, uint32_t, uint32_t, AggRaw*, unsigned int*, AggRaw*,  \
-                                    cudaStream_t);
+                                    const FoldArgs&, const XchgDev&, cudaStream_t);
 #define MNR_RED_DEF(NAME, T)                                                                                                  \
     cudaError_t reduce_single_##NAME(const void* data, const uint8_t* mask, uint64_t n, bool minmax, AggRaw* partials,       \
-                                     unsigned int* ticket, AggRaw* out, AggRaw* out_host, const XchgDev& x, cudaStream_t s) { \
-        return launch_t<T>(data, mask, n, minmax, partials, ticket, out, out_host, x, s);                                    \
+                                     unsigned int* ticket, AggRaw* out, AggRaw* out_host, const XchgDev& x, int flags,       \
+                                     cudaStream_t s) {                                                                       \
+        return launch_t<T>(data, mask, n, minmax, partials, ticket, out, out_host, x, flags, s);                             \
     }                                                                                                                         \
     uint32_t reduce_nblk_##NAME(uint64_t n, int tier, bool minmax) { return nblk_t<T>(n, tier, minmax); }                    \
     cudaError_t reduce_batch_##NAME(int tier, bool masked, bool minmax, const ReduceSeg* segs, uint32_t nseg,                \
-                                    uint32_t max_blk, AggRaw* partials, unsigned int* tickets, AggRaw* outs, cudaStream_t s) { \
-        return batch_t<T>(tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, s);                            \
+                                    uint32_t max_blk, AggRaw* partials, unsigned int* tickets, AggRaw* outs,                 \
+                                    const FoldArgs& f, const XchgDev& x, cudaStream_t s) {                                   \
+        return batch_t<T>(tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, f, x, s);                      \
     }
 
 #if MNR_RED_DTYPE == 0
@@ -152,14 +166,15 @@ int reduce_tier(const void* data, bool minmax) {
 cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
                                 AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s) {
     const XchgDev none{};
-    MNR_DTYPE_SWITCH(dt, reduce_single, data, mask, n, minmax, partials, ticket, out, out_host, none, s);
+    MNR_DTYPE_SWITCH(dt, reduce_single, data, mask, n, minmax, partials, ticket, out, out_host, none, 0, s);
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_reduce_stats_xchg(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
                                      AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host,
-                                     const XchgDev& x, cudaStream_t s) {
-    MNR_DTYPE_SWITCH(dt, reduce_single, data, mask, n, minmax, partials, ticket, out, out_host, x, s);
+                                     const XchgDev& x, bool late_wait, bool pdl, cudaStream_t s) {
+    const int flags = pdl ? (late_wait ? kReduceLateWait : 0) : kReduceNoPdl;
+    MNR_DTYPE_SWITCH(dt, reduce_single, data, mask, n, minmax, partials, ticket, out, out_host, x, flags, s);
     return cudaErrorInvalidValue;
 }
 
@@ -170,9 +185,14 @@ uint32_t reduce_nblk(mnr_dtype dt, uint64_t n, int tier, bool minmax) {
 
 cudaError_t launch_reduce_stats_batch(mnr_dtype dt, int tier, bool masked, bool minmax, const ReduceSeg* segs,
                                       uint32_t nseg, uint32_t max_blk, AggRaw* partials, unsigned int* tickets,
-                                      AggRaw* outs, cudaStream_t s) {
-    MNR_DTYPE_SWITCH(dt, reduce_batch, tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, s);
+                                      AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s) {
+    MNR_DTYPE_SWITCH(dt, reduce_batch, tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, f, x, s);
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fold_exchange(const AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s) {
+    fold_exchange_kernel<kRBlock><<<1, kRBlock, 0, s>>>(outs, f, x);
+    return cudaGetLastError();
 }
 #else
 #error "compile reduce.cu with -DMNR_RED_DTYPE=<0..9 | 100>"

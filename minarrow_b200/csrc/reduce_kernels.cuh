@@ -292,22 +292,27 @@ __device__ __forceinline__ AggRaw load_partial(const AggRaw* p) {   // L2-cohere
 }
 
 // ---- fused cross-GPU finish over NVLink peer memory ------------------------------------------------------------
-// Every rank owns a 2 KB mailbox (cudaMalloc + CUDA IPC, mapped into every peer process).  Slot (parity p, source rank
-// s) = 64 bytes at ((p * kMaxPeers) + s) * 64: bytes 0..31 the source's AggRaw, bytes 32..39 a flag holding the epoch.
-// The finishing block of rank r's reduction kernel stores its aggregate + flag into slot (epoch & 1, r) of EVERY
-// rank's mailbox (P2P stores through NVSwitch), then waits until the `world` slots of its own mailbox carry this
-// epoch and folds them in rank order — the same fold on every rank, so all ranks hold identical bits.  One kernel:
-// the reduction, the all-gather of partials and the combine; no NCCL call, no host round trip.
-// Parity double-buffering is race-free: a rank can only complete epoch e+1 after every peer has finished epoch e
-// (it needs their e+1 flags, which stream order places after their epoch-e kernel).
+// Every rank owns a mailbox in its own HBM, mapped into every peer (CUDA IPC between processes, plain peer access inside
+// one process).  Slot (parity p, source rank s) lives at ((p * kMaxPeers) + s) * slot_bytes: bytes 0..7 a flag holding the
+// epoch, bytes 32.. up to `max_aggs` AggRaw images (one per column of the exchange).  The finishing block of rank r's
+// reduction stores its aggregates + flag into slot (epoch & 1, r) of EVERY rank's mailbox (P2P stores through NVSwitch),
+// waits until the `world` slots of its own mailbox carry this epoch, and folds them in rank order — the same fold on every
+// rank, so all ranks hold identical bits.  One kernel: the reduction, the all-gather of partials and the combine; no
+// NCCL call, no host round trip.  Parity double-buffering is race-free: a rank can only complete epoch e+1 after every
+// peer has finished epoch e (it needs their e+1 flags, which each peer posts only after its own epoch-e kernel is done).
 constexpr int kMaxPeers = 16;
+constexpr int kXchgHeader = 32;            // flag + padding in front of the aggregates of a slot
 struct XchgDev {
     int world;                 // 0 = no exchange (plain single-GPU finish)
     int rank;
     unsigned long long epoch;  // 1, 2, 3, ... identical sequence on every rank
     unsigned int* err;         // device word, set to 1 if a peer's flag never arrives (bounded spin)
+    unsigned int slot_bytes;   // kXchgHeader + 32 * max_aggs, rounded up to 64
     char* mailbox[kMaxPeers];  // mailbox[r]: rank r's mailbox as mapped in this process
 };
+// A result whose exchange timed out carries this count (no column has 2^64 - 1 rows), so an asynchronous caller that
+// never looks at mnr_xchg_status still cannot mistake it for an aggregate.
+constexpr unsigned long long kAggPoison = ~0ull;
 
 __device__ __forceinline__ void st_sys_v2(void* p, uint64_t a, uint64_t b) {
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
@@ -326,15 +331,82 @@ __device__ __forceinline__ AggRaw ld_sys_agg(const void* p) {
     asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.mx), "=l"(r.count) : "l"(static_cast<const char*>(p) + 16) : "memory");
     return r;
 }
+__device__ __forceinline__ void st_sys_agg(void* p, const AggRaw& a) {
+    st_sys_v2(p, a.sum, a.mn);
+    st_sys_v2(static_cast<char*>(p) + 16, a.mx, a.count);
+}
+
+// Programmatic dependent launch (griddepcontrol): reductions are launched with the programmatic-stream-serialization
+// attribute, so the NEXT kernel on the stream may be scheduled as soon as every block of this one has started, and its
+// blocks take over SM slots as ours exit — the launch ramp, the ticket finish and the cross-GPU flag wait of reduction k
+// overlap the streaming phase of reduction k+1.  `pdl_wait` blocks until the previous kernel on the stream has completed
+// and its writes are visible; both instructions are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Post `n` aggregates (`mine`: shared or global memory written before the call by this block) to every rank, raise the
+// epoch flag, and wait until every rank's flag for this epoch sits in the own mailbox.  Called by all threads of the
+// finishing block.  Returns false (block-uniform) on a timeout; afterwards xchg_slot(x, src, g) is rank src's aggregate g.
+template <int BLOCK>
+__device__ __forceinline__ bool xchg_exchange(const XchgDev& x, const AggRaw* mine, const unsigned n) {
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    const size_t par = (size_t)(x.epoch & 1ull) * kMaxPeers;
+    __syncthreads();
+    for (unsigned t = threadIdx.x; t < (unsigned)x.world * n; t += BLOCK) {
+        const unsigned peer = t / n, g = t - peer * n;
+        st_sys_agg(x.mailbox[peer] + (par + (size_t)x.rank) * x.slot_bytes + kXchgHeader + (size_t)g * 32, mine[g]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < (unsigned)x.world) {
+        st_release_sys(x.mailbox[threadIdx.x] + (par + (size_t)x.rank) * x.slot_bytes, x.epoch);
+        const char* src = x.mailbox[x.rank] + (par + threadIdx.x) * x.slot_bytes;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(src) != x.epoch) {
+            if (clock64() - t0 > (20ll << 30)) { timed_out = 1; atomicExch(x.err, 1u); break; }   // ~10 s: a peer never launched
+        }
+    }
+    __syncthreads();
+    return timed_out == 0;
+}
+__device__ __forceinline__ AggRaw xchg_slot(const XchgDev& x, unsigned src, unsigned g) {
+    const size_t par = (size_t)(x.epoch & 1ull) * kMaxPeers;
+    return ld_sys_agg(x.mailbox[x.rank] + (par + src) * x.slot_bytes + kXchgHeader + (size_t)g * 32);
+}
+
+// Run-time typed combine of two aggregate images (the batched fold handles columns of different dtypes in one block).
+// kind: 0 signed, 1 unsigned, 2 float.  Same arithmetic as Partial<T>::merge / mnr_agg_combine: integer sums wrap, float
+// sums add in double, float min/max are IEEE minNum/maxNum (NaN = "empty" never wins, -0.0 < +0.0).
+__device__ __forceinline__ void agg_merge_rt(int kind, AggRaw& a, const AggRaw& b) {
+    a.count += b.count;
+    if (kind == 2) {
+        a.sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)a.sum) + __longlong_as_double((long long)b.sum));
+        a.mn = (uint64_t)__double_as_longlong(fmin(__longlong_as_double((long long)a.mn), __longlong_as_double((long long)b.mn)));
+        a.mx = (uint64_t)__double_as_longlong(fmax(__longlong_as_double((long long)a.mx), __longlong_as_double((long long)b.mx)));
+    } else if (kind == 1) {
+        a.sum += b.sum;
+        a.mn = b.mn < a.mn ? b.mn : a.mn;
+        a.mx = b.mx > a.mx ? b.mx : a.mx;
+    } else {
+        a.sum += b.sum;
+        a.mn = (int64_t)b.mn < (int64_t)a.mn ? b.mn : a.mn;
+        a.mx = (int64_t)b.mx > (int64_t)a.mx ? b.mx : a.mx;
+    }
+}
 
 // Body shared by the single-column kernel and the batched (one launch, many chunks) kernel.  `bid` / `nblk` are the
 // block's index and the number of blocks working on THIS column; nblk is a function of (len, dtype) only, so a column
 // reduced inside a batch gives the same bits as the same column reduced alone.
+// Returns true in the block that produced the column's aggregate (the finishing block), false in all others.
+// `late_wait`: the programmatic-dependency wait is taken after the streaming phase (the caller guarantees the column is
+// not being written by the previous kernel on the stream) instead of by the kernel's first instruction.
 template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int U>
-__device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
+__device__ __forceinline__ bool reduce_stats_body(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
                                                   AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket,
                                                   AggRaw* __restrict__ out, AggRaw* __restrict__ out_host,
-                                                  const unsigned int bid, const unsigned int nblk, const XchgDev& x) {
+                                                  const unsigned int bid, const unsigned int nblk, const XchgDev& x,
+                                                  const bool late_wait) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     using A = typename Traits<T>::Acc;
     using P = Partial<T, MINMAX>;
@@ -408,6 +480,8 @@ __device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, co
     }
 
     p = block_combine<P, BLOCK>(p, smem);
+    // Everything below touches memory shared with the previous launch on the stream (partials, ticket, out, mailboxes).
+    if (late_wait) pdl_wait();
     P q;
     if (nblk == 1) {
         q = p;   // small column: the only block is the finishing block — no partials, no ticket, no fences
@@ -419,7 +493,7 @@ __device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, co
             is_last = (done == nblk - 1);
         }
         __syncthreads();
-        if (!is_last) return;
+        if (!is_last) return false;
         __threadfence();
         q.init();
         bool first = true;
@@ -429,41 +503,27 @@ __device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, co
         }
         q = block_combine<P, BLOCK>(q, smem);
     }
+    bool poisoned = false;
     if (x.world > 0) {   // fused cross-GPU finish (block-uniform branch; only the finishing block gets here)
         __shared__ AggRaw mine;
-        __shared__ AggRaw got[kMaxPeers];
         if (threadIdx.x == 0) {
             if constexpr (!MASKED) q.cnt = n;
             mine = q.raw();
         }
-        __syncthreads();
-        const size_t par = (size_t)(x.epoch & 1ull) * kMaxPeers;
-        if (threadIdx.x < (unsigned)x.world) {
-            char* dst = x.mailbox[threadIdx.x] + (par + (size_t)x.rank) * 64;
-            st_sys_v2(dst, mine.sum, mine.mn);
-            st_sys_v2(dst + 16, mine.mx, mine.count);
-            __threadfence_system();
-            st_release_sys(dst + 32, x.epoch);
-            const char* src = x.mailbox[x.rank] + (par + threadIdx.x) * 64;
-            const long long t0 = clock64();
-            bool ok = true;
-            while (ld_acquire_sys(src + 32) != x.epoch) {
-                if (clock64() - t0 > (20ll << 30)) { ok = false; break; }   // ~10 s: a peer never launched
-            }
-            if (!ok) atomicExch(x.err, 1u);
-            got[threadIdx.x] = ld_sys_agg(src);
-        }
-        __syncthreads();
+        const bool ok = xchg_exchange<BLOCK>(x, &mine, 1u);   // starts with a __syncthreads
         if (threadIdx.x == 0) {
-            P acc; acc.from_raw(got[0]);
-            for (int r = 1; r < x.world; ++r) { P t; t.from_raw(got[r]); acc.merge(t); }   // rank order
-            q = acc;
+            if (ok) {
+                P acc; acc.from_raw(xchg_slot(x, 0, 0));
+                for (int r = 1; r < x.world; ++r) { P t; t.from_raw(xchg_slot(x, r, 0)); acc.merge(t); }   // rank order
+                q = acc;
+            } else poisoned = true;   // a peer never answered: the error word is set, the result is marked unusable
         }
     } else if (threadIdx.x == 0) {
         if constexpr (!MASKED) q.cnt = n;
     }
     if (threadIdx.x == 0) {
-        const AggRaw r = q.raw();
+        AggRaw r = q.raw();
+        if (poisoned) r.count = kAggPoison;
         *out = r;
         if (out_host) {   // optional second copy straight into mapped pinned host memory (synchronous APIs: no D2H memcpy)
             *out_host = r;
@@ -471,14 +531,21 @@ __device__ __forceinline__ void reduce_stats_body(const T* __restrict__ data, co
         }
         if (nblk > 1) *ticket = 0;   // re-arm for the next launch on this stream
     }
+    return true;
 }
+
+constexpr int kReduceLateWait = 1;   // flags bit 0 of reduce_stats_kernel
+constexpr int kReduceNoPdl = 2;      // host-side only: launch without the programmatic-launch attribute
 
 template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MINB, int U>
 __global__ void __launch_bounds__(BLOCK, MINB)
 reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask, uint64_t n,
                     AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket, AggRaw* __restrict__ out,
-                    AggRaw* __restrict__ out_host, const XchgDev x) {
-    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(data, mask, n, partials, ticket, out, out_host, blockIdx.x, gridDim.x, x);
+                    AggRaw* __restrict__ out_host, const XchgDev x, const int flags) {
+    pdl_launch_dependents();
+    const bool late = (flags & kReduceLateWait) != 0;
+    if (!late) pdl_wait();
+    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(data, mask, n, partials, ticket, out, out_host, blockIdx.x, gridDim.x, x, late);
 }
 
 // One launch, many columns/chunks (SuperArray / SuperTable fan-out, broadcast/super_table.rs:38-73 walks them one
@@ -491,15 +558,76 @@ struct ReduceSeg {
     uint32_t out_index; // slot in `outs`
 };
 
+// Optional second stage of a batched call (a sharded SuperArray / SuperTable reduction): when the LAST chunk aggregate of
+// the whole call (all launches of it, counted by `gticket`) has been written, that block folds the chunk aggregates per
+// column in chunk order, exchanges the per-column partials with the other ranks (xchg_exchange) and folds those in rank
+// order.  n_groups <= BLOCK.  With x.world == 0 it is a purely local per-column fold.
+struct FoldArgs {
+    unsigned int* gticket;     // NULL = no second stage
+    uint32_t total_segs;       // chunk aggregates of the whole call
+    uint32_t n_groups;         // columns
+    const uint32_t* grp_off;   // [n_groups + 1] offsets into grp_idx
+    const uint32_t* grp_idx;   // slots in `outs`, grouped by column, chunk order inside a column
+    const AggRaw* identity;    // [n_groups] aggregate of an empty column of that dtype (a rank may hold no chunk of it)
+    const uint8_t* kind;       // [n_groups] 0 signed / 1 unsigned / 2 float
+    AggRaw* local;             // [n_groups] scratch: this rank's per-column partials
+    AggRaw* result;            // [n_groups] device result
+    AggRaw* result_host;       // [n_groups] mapped pinned host copy, or NULL
+};
+
+template <int BLOCK>
+__device__ __forceinline__ void fold_and_exchange(const FoldArgs& f, const AggRaw* __restrict__ outs, const XchgDev& x) {
+    const unsigned g = threadIdx.x;
+    AggRaw acc{};
+    int kind = 0;
+    if (g < f.n_groups) {
+        kind = f.kind[g];
+        acc = f.identity[g];
+        for (uint32_t i = f.grp_off[g]; i < f.grp_off[g + 1]; ++i) agg_merge_rt(kind, acc, load_partial(outs + f.grp_idx[i]));
+        f.local[g] = acc;
+    }
+    bool ok = true;
+    if (x.world > 0) {
+        ok = xchg_exchange<BLOCK>(x, f.local, f.n_groups);   // starts with a __syncthreads: f.local is complete
+        if (g < f.n_groups && ok) {
+            acc = xchg_slot(x, 0, g);
+            for (int r = 1; r < x.world; ++r) agg_merge_rt(kind, acc, xchg_slot(x, (unsigned)r, g));   // rank order
+        }
+    }
+    if (g < f.n_groups) {
+        if (!ok) acc.count = kAggPoison;
+        f.result[g] = acc;
+        if (f.result_host) f.result_host[g] = acc;
+    }
+    if (f.result_host) __threadfence_system();
+    if (threadIdx.x == 0) *f.gticket = 0;   // re-arm
+}
+
 template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MINB, int U>
 __global__ void __launch_bounds__(BLOCK, MINB)
 reduce_stats_batch_kernel(const ReduceSeg* __restrict__ segs, AggRaw* __restrict__ partials, unsigned int* __restrict__ tickets,
-                          AggRaw* __restrict__ outs, uint32_t max_blk) {
+                          AggRaw* __restrict__ outs, uint32_t max_blk, const FoldArgs f, const XchgDev x) {
     const ReduceSeg s = segs[blockIdx.y];
     if (blockIdx.x >= s.nblk) return;
-    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(static_cast<const T*>(s.data), s.mask, s.n,
-                                                        partials + (size_t)blockIdx.y * max_blk, tickets + blockIdx.y,
-                                                        outs + s.out_index, nullptr, blockIdx.x, s.nblk, XchgDev{});
+    const bool fin = reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(static_cast<const T*>(s.data), s.mask, s.n,
+                                                                        partials + (size_t)blockIdx.y * max_blk, tickets + blockIdx.y,
+                                                                        outs + s.out_index, nullptr, blockIdx.x, s.nblk, XchgDev{}, false);
+    if (!fin || f.gticket == nullptr) return;
+    __shared__ bool all_done;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        all_done = atomicAdd(f.gticket, 1u) == f.total_segs - 1;
+    }
+    __syncthreads();
+    if (!all_done) return;
+    __threadfence();
+    fold_and_exchange<BLOCK>(f, outs, x);
+}
+
+// A rank that owns no chunk of the sharded container still takes part in the exchange with identity aggregates.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) fold_exchange_kernel(const AggRaw* __restrict__ outs, const FoldArgs f, const XchgDev x) {
+    fold_and_exchange<BLOCK>(f, outs, x);
 }
 
 }  // namespace mnr

@@ -21,34 +21,35 @@ from .core import KernelError, check, dtype_code
 
 
 def chunk_owner(i: int, n_chunks: int, world: int) -> int:
-    """Rank that owns chunk `i`: contiguous block assignment, floor(i * G / n)."""
-    if not 0 <= i < n_chunks:
-        raise KernelError("OutOfBounds", f"chunk {i} of {n_chunks}")
-    return (i * world) // n_chunks
+    """Rank that owns chunk `i`: contiguous block assignment, floor(i * G / n) (`mnr_shard_owner`)."""
+    r = _lib.load().mnr_shard_owner(i, n_chunks, world)
+    if r < 0:
+        check(r)
+    return r
 
 
 def shard_chunks(n_chunks: int, world: int) -> List[range]:
-    """Chunk index range of every rank (may be empty when n_chunks < world)."""
-    owners = [chunk_owner(i, n_chunks, world) for i in range(n_chunks)]
+    """Chunk index range of every rank (may be empty when n_chunks < world) (`mnr_shard_chunk_range`)."""
+    lib = _lib.load()
     out = []
+    lo, hi = C.c_size_t(), C.c_size_t()
     for r in range(world):
-        mine = [i for i, o in enumerate(owners) if o == r]
-        out.append(range(mine[0], mine[-1] + 1) if mine else range(0, 0))
+        check(lib.mnr_shard_chunk_range(n_chunks, world, r, C.byref(lo), C.byref(hi)))
+        out.append(range(lo.value, hi.value) if hi.value > lo.value else range(0, 0))
     return out
 
 
 def shard_rows(n_rows: int, world: int, align: int = 64) -> List[Tuple[int, int]]:
     """Split one big Array into `world` contiguous (offset, len) windows cut on `align`-row boundaries
-    (64 rows = one validity word, so every shard's bitmask starts on a word boundary)."""
+    (64 rows = one validity word, so every shard's bitmask starts on a word boundary) (`mnr_shard_row_range`)."""
     if world < 1 or align < 1:
         raise KernelError("InvalidArguments", "world and align must be >= 1")
-    units = (n_rows + align - 1) // align
-    out, start = [], 0
+    lib = _lib.load()
+    off, ln = C.c_size_t(), C.c_size_t()
+    out = []
     for r in range(world):
-        u = units // world + (1 if r < units % world else 0)
-        length = min(u * align, n_rows - start)
-        out.append((start, max(length, 0)))
-        start += max(length, 0)
+        check(lib.mnr_shard_row_range(n_rows, world, r, align, C.byref(off), C.byref(ln)))
+        out.append((off.value, ln.value))
     return out
 
 
@@ -146,45 +147,9 @@ class ShardedColumn:
             vals.append(None if c.null_mask is None else DeviceBitmask.upload(ctx, c.null_mask))
         return cls(ctx, dtype, bufs, vals)
 
-    def local_partial(self, with_minmax: bool = True):
-        """One `mnr_agg` for this rank: per-chunk partials (batched launch, asynchronous, written straight to a device
-        array) folded in chunk order.  Returns a torch int64[4] tensor on this rank's GPU."""
-        import torch
-        from . import device_ops as dev
-        n = max(1, len(self.chunks))
-        parts = torch.zeros(n, 4, dtype=torch.int64, device=torch.device("cuda", self.ctx.device))
-        torch.cuda.current_stream(parts.device).synchronize()   # torch filled it on ITS stream; the context has its own
-        if self.chunks:   # all local chunks in one batched call (one launch per dtype/alignment/masked class)
-            dev.reduce_stats_batch_async(self.ctx, self.chunks, self.validities, with_minmax, parts.data_ptr())
-        self.ctx.synchronize()
-        if not self.chunks:
-            return None
-        host = parts.cpu().numpy()
-        out = _lib.Agg()
-        arr = (_lib.Agg * len(self.chunks)).from_buffer_copy(host.tobytes())
-        check(self.ctx.lib.mnr_agg_combine(dtype_code(self.dtype), arr, len(self.chunks), C.byref(out)))
-        return torch.from_numpy(agg_to_words(out)).to(parts.device)
-
-    def stats(self, with_minmax: bool = True, group=None) -> dict:
-        """Global {sum, min, max, count, mean} of the column: local partial -> all-gather -> rank-order combine.
-        Ranks that own no chunk contribute nothing (their slot is skipped)."""
-        import torch
-        import torch.distributed as dist
-        lp = self.local_partial(with_minmax)
-        dev_ = torch.device("cuda", self.ctx.device)
-        has = torch.tensor([0 if lp is None else 1], dtype=torch.int64, device=dev_)
-        if lp is None:
-            lp = torch.zeros(4, dtype=torch.int64, device=dev_)
-        allp = exchange_partials(lp, group).cpu().numpy()
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
-            flags = exchange_partials(torch.cat([has, has, has, has]), group).cpu().numpy()[:, 0]
-        else:
-            flags = np.array([int(has.item())])
-        keep = [allp[r] for r in range(allp.shape[0]) if flags[r]]
-        if not keep:
-            raise KernelError("InvalidArguments", "empty SuperArray")
-        return combine_partials(self.dtype, keep)
-
+    def stats(self, with_minmax: bool = True, group=None, exchange: "FusedExchange" = None) -> dict:
+        """Global {sum, min, max, count, mean} of the column (see `sharded_stats`)."""
+        return sharded_stats([self], with_minmax, group, exchange)[0]
 
     def rebalance(self, group=None, align: int = 64) -> "ShardedColumn":
         """Re-cut the column into even contiguous shards (one chunk per rank, cut on `align`-row boundaries), moving rows
@@ -333,9 +298,179 @@ class FusedExchange:
         return {"sum": getattr(agg.sum, f), "min": getattr(agg.min, f), "max": getattr(agg.max, f), "count": int(agg.count),
                 "mean": float(self.ctx.lib.mnr_agg_mean(dtype_code(buf.dtype), C.byref(agg)))}
 
+    def reduce_stats_batch_async(self, bufs, validities, with_minmax: bool, col_of_chunk, col_dtypes, out_device_ptr: int):
+        """Sharded SuperArray / SuperTable reduction, asynchronous: this rank's chunks (chunk i belongs to column
+        col_of_chunk[i]) -> len(col_dtypes) global aggregates at `out_device_ptr` on every rank.  One batched launch
+        per (dtype, alignment, masked) class; the fold and the cross-GPU exchange ride in the last block."""
+        _batch_exchange(self.ctx, self.h, bufs, validities, with_minmax, col_of_chunk, col_dtypes, out_device_ptr, None)
+
+    def reduce_stats_batch(self, bufs, validities, with_minmax: bool, col_of_chunk, col_dtypes) -> list:
+        aggs = (_lib.Agg * len(col_dtypes))()
+        _batch_exchange(self.ctx, self.h, bufs, validities, with_minmax, col_of_chunk, col_dtypes, None, aggs)
+        return [_agg_dict(dt, a, self.ctx.lib) for dt, a in zip(col_dtypes, aggs)]
+
+    def status(self, clear: bool = True) -> bool:
+        """True if an exchange on this handle timed out since the last clear (`mnr_xchg_status`)."""
+        r = C.c_int()
+        check(self.ctx.lib.mnr_xchg_status(self.h, int(clear), C.byref(r)))
+        return bool(r.value)
+
     def close(self) -> None:
         if getattr(self, "h", None) and self.ctx.h:
             self.ctx.lib.mnr_xchg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def _agg_dict(dtype, agg, lib) -> dict:
+    f = {"i": "i64", "u": "u64", "f": "f64"}[np.dtype(dtype).kind]
+    return {"sum": getattr(agg.sum, f), "min": getattr(agg.min, f), "max": getattr(agg.max, f), "count": int(agg.count),
+            "mean": float(lib.mnr_agg_mean(dtype_code(dtype), C.byref(agg)))}
+
+
+def _handles(items):
+    arr = (C.c_void_p * max(1, len(items)))()
+    for i, x in enumerate(items):
+        arr[i] = None if x is None else x.h
+    return arr
+
+
+def _batch_exchange(ctx, xh, bufs, validities, with_minmax, col_of_chunk, col_dtypes, out_device_ptr, out_aggs):
+    n, n_cols = len(bufs), len(col_dtypes)
+    cols = (C.c_uint32 * max(1, n))(*[int(c) for c in col_of_chunk])
+    dts = (C.c_int * n_cols)(*[dtype_code(d) for d in col_dtypes])
+    vals = None if validities is None else _handles(list(validities))
+    if out_aggs is None:
+        check(ctx.lib.mnr_reduce_stats_batch_exchange(ctx.h, xh, n, _handles(list(bufs)), vals, int(with_minmax), n_cols, cols, dts,
+                                                      C.c_void_p(out_device_ptr)))
+    else:
+        check(ctx.lib.mnr_reduce_stats_batch_exchange_sync(ctx.h, xh, n, _handles(list(bufs)), vals, int(with_minmax), n_cols, cols,
+                                                           dts, out_aggs))
+
+
+def sharded_stats(columns: Sequence["ShardedColumn"], with_minmax: bool = True, group=None,
+                  exchange: "FusedExchange" = None) -> List[dict]:
+    """Global {sum, min, max, count, mean} of every column of a sharded SuperArray / SuperTable (`columns[c]` = this
+    rank's chunks of column c; a rank may own none).  ONE call per rank on the device:
+      * `exchange` given (FusedExchange): batched reduction + per-column fold + NVLink mailbox exchange + rank-order
+        combine inside the kernels (`mnr_reduce_stats_batch_exchange`) — no NCCL call, no host round trip;
+      * otherwise: the same batched reduction + on-device per-column fold, then ONE all-gather of 32 bytes per column
+        and rank over the process group (NCCL on the box, gloo in the CPU tests) and the rank-order combine on the host.
+    Integer sums wrap (order-free); float sums fold chunks in chunk order, then ranks in rank order."""
+    import torch
+    import torch.distributed as dist
+    if not columns:
+        return []
+    ctx = columns[0].ctx
+    bufs, vals, cols = [], [], []
+    for c, col in enumerate(columns):
+        bufs += col.chunks
+        vals += col.validities
+        cols += [c] * len(col.chunks)
+    dts = [col.dtype for col in columns]
+    if exchange is not None:
+        return exchange.reduce_stats_batch(bufs, vals, with_minmax, cols, dts)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        aggs = (_lib.Agg * len(dts))()
+        _batch_exchange(ctx, None, bufs, vals, with_minmax, cols, dts, None, aggs)
+        return [_agg_dict(dt, a, ctx.lib) for dt, a in zip(dts, aggs)]
+    dev_ = torch.device("cuda", ctx.device)
+    local = torch.zeros(len(dts) * 4, dtype=torch.int64, device=dev_)
+    torch.cuda.current_stream(dev_).synchronize()       # torch zero-filled it on ITS stream; the context has its own
+    _batch_exchange(ctx, None, bufs, vals, with_minmax, cols, dts, local.data_ptr(), None)
+    ctx.synchronize()
+    allp = torch.empty(world * len(dts) * 4, dtype=torch.int64, device=dev_)
+    dist.all_gather_into_tensor(allp, local, group=group)
+    allp = allp.cpu().numpy().reshape(world, len(dts), 4)
+    return [combine_partials(dt, allp[:, c, :]) for c, dt in enumerate(dts)]
+
+
+class Group:
+    """All GPUs of the box driven from ONE process (`mnr_group`): one context + mailbox per device, peer access instead
+    of CUDA IPC.  `devices` may repeat a device ("virtual ranks"), which runs the whole exchange path on one GPU."""
+
+    def __init__(self, world: Optional[int] = None, devices: Optional[Sequence[int]] = None):
+        from .core import Context
+        self.lib = _lib.load()
+        if devices is not None:
+            world = len(devices)
+        elif world is None:
+            world = max(1, int(self.lib.mnr_device_count()))
+        dv = None if devices is None else (C.c_int * world)(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(self.lib.mnr_group_create(world, dv, C.byref(h)))
+        self.h, self.world = h, world
+        self.ctxs = [Context.borrow(self.lib.mnr_group_ctx(h, r)) for r in range(world)]
+
+    def ctx(self, rank: int):
+        return self.ctxs[rank]
+
+    def synchronize(self) -> None:
+        check(self.lib.mnr_group_synchronize(self.h))
+
+    def upload(self, chunks: Sequence) -> Tuple[list, list]:
+        """Host SuperArray chunks (IntegerArray / FloatArray / numpy) -> device chunks on their owning ranks."""
+        from .core import DeviceBitmask, DeviceBuffer
+        n = len(chunks)
+        data = [np.ascontiguousarray(getattr(c, "data", c)) for c in chunks]
+        masks = [getattr(c, "null_mask", None) for c in chunks]
+        dt = data[0].dtype
+        hp = (C.c_void_p * n)(*[d.ctypes.data for d in data])
+        lens = (C.c_size_t * n)(*[d.size for d in data])
+        mkeep = [None if m is None else np.ascontiguousarray(m.bits, dtype=np.uint8) for m in masks]
+        for m, d, k in zip(masks, data, mkeep):
+            if m is not None and (m.len < d.size or k.size < (d.size + 7) // 8):
+                raise KernelError("InvalidArguments", f"mask has {m.len} bits / {k.size} bytes, need {d.size} bits")
+        mp = (C.c_void_p * n)(*[None if k is None else k.ctypes.data for k in mkeep])
+        ob, om = (C.c_void_p * n)(), (C.c_void_p * n)()
+        check(self.lib.mnr_group_upload(self.h, dtype_code(dt), n, hp, lens, mp, ob, om))
+        bufs = [DeviceBuffer(self.ctxs[chunk_owner(i, n, self.world)], C.c_void_p(ob[i])) for i in range(n)]
+        vals = [DeviceBitmask(self.ctxs[chunk_owner(i, n, self.world)], C.c_void_p(om[i])) if om[i] else None for i in range(n)]
+        return bufs, vals
+
+    def _wrap_outs(self, like, ob, om):
+        from .core import DeviceBitmask, DeviceBuffer
+        return ([DeviceBuffer(x.ctx, C.c_void_p(ob[i])) for i, x in enumerate(like)],
+                [DeviceBitmask(x.ctx, C.c_void_p(om[i])) if om[i] else None for i, x in enumerate(like)])
+
+    def ew_binary(self, op: int, lhs, rhs, lhs_masks=None, rhs_masks=None, mode: int = 0):
+        """Shard-local `lhs[i] op rhs[i]` on the owning devices (no communication), one batched launch per device."""
+        n = len(lhs)
+        ob, om = (C.c_void_p * max(1, n))(), (C.c_void_p * max(1, n))()
+        check(self.lib.mnr_group_ew_binary(self.h, int(op), n, _handles(lhs), _handles(rhs),
+                                           None if lhs_masks is None else _handles(lhs_masks),
+                                           None if rhs_masks is None else _handles(rhs_masks), int(mode), ob, om))
+        return self._wrap_outs(lhs, ob, om)
+
+    def ew_scalar(self, op: int, arrs, scalars, scalar_is_lhs: bool = False, masks=None):
+        n = len(arrs)
+        keep = [np.array([s], dtype=a.dtype) for a, s in zip(arrs, scalars)]
+        sp = (C.c_void_p * max(1, n))(*[k.ctypes.data for k in keep])
+        ob, om = (C.c_void_p * max(1, n))(), (C.c_void_p * max(1, n))()
+        check(self.lib.mnr_group_ew_scalar(self.h, int(op), n, _handles(arrs), sp, int(scalar_is_lhs),
+                                           None if masks is None else _handles(masks), ob, om))
+        return self._wrap_outs(arrs, ob, om)
+
+    def reduce_stats(self, bufs, validities, with_minmax: bool, col_of_chunk, col_dtypes) -> list:
+        n, n_cols = len(bufs), len(col_dtypes)
+        cols = (C.c_uint32 * max(1, n))(*[int(c) for c in col_of_chunk])
+        dts = (C.c_int * n_cols)(*[dtype_code(d) for d in col_dtypes])
+        aggs = (_lib.Agg * n_cols)()
+        check(self.lib.mnr_group_reduce_stats(self.h, n, _handles(bufs), None if validities is None else _handles(validities),
+                                              int(with_minmax), n_cols, cols, dts, aggs))
+        return [_agg_dict(dt, a, self.lib) for dt, a in zip(col_dtypes, aggs)]
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            for c in self.ctxs:
+                c.h = None
+            self.lib.mnr_group_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Tests that put several "virtual ranks" on one GPU (tests/test_gpu_group.py) keep one kernel per rank spinning on its
+# peers' flags; every stream needs its own hardware queue so a queued successor never blocks a peer's launch.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

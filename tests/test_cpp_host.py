@@ -11,6 +11,8 @@ SRC = os.path.join(ROOT, "tests", "cpp", "test_reference_kats.cpp")
 EXE = os.path.join(ROOT, "tests", "cpp", "test_reference_kats")
 ROUTES_SRC = os.path.join(ROOT, "tests", "cpp", "test_container_routes.cpp")
 ROUTES_EXE = os.path.join(ROOT, "tests", "cpp", "test_container_routes")
+GROUP_SRC = os.path.join(ROOT, "tests", "cpp", "test_shard_group.cpp")
+GROUP_EXE = os.path.join(ROOT, "tests", "cpp", "test_shard_group")
 
 
 def _build(src, exe):
@@ -26,6 +28,7 @@ def _build(src, exe):
 
 def build_cpp():
     _build(ROUTES_SRC, ROUTES_EXE)
+    _build(GROUP_SRC, GROUP_EXE)
     return _build(SRC, EXE)
 
 
@@ -39,6 +42,24 @@ def test_cpp_container_routes_compile_link_and_load():
     build_cpp()
     r = subprocess.run([ROUTES_EXE, "--link"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.startswith("abi 1"), r.stdout + r.stderr
+
+
+def test_cpp_shard_group_compiles_links_and_loads():
+    build_cpp()
+    r = subprocess.run([GROUP_EXE, "--link"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.startswith("abi 1"), r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [0, 1, 2, 5])
+def test_shard_group_single_process_multi_rank(gpu_ctx, world):
+    """mnr_shard_* / mnr_group_* from one process (tests/cpp/test_shard_group.cpp): SuperTable stats through the batched
+    fused exchange + shard-local element-wise fan-out.  world 0 = one rank per GPU of the box (3 virtual ranks on a
+    1-GPU box); explicit worlds map rank r to device r % n_devices, so the mailbox protocol runs on any box."""
+    build_cpp()
+    r = subprocess.run([GROUP_EXE] + ([str(world)] if world else []), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " 0 failed" in r.stdout and "kernel launches" in r.stdout, r.stdout[-500:]
 
 
 @pytest.mark.gpu
