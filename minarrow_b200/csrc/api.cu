@@ -982,11 +982,15 @@ static int ensure_batch_scratch(mnr_ctx* c, size_t nseg_total, size_t nseg_launc
     return MNR_OK;
 }
 
-// Batched launch(es) over validated chunks.  `f` / `x`: optional second stage (per-column fold + cross-GPU exchange) run
-// by the block that writes the last chunk aggregate of the call.
-static int reduce_batch_launch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
-                               bool minmax, AggRaw* outs, const FoldArgs& f, const XchgDev& x) {
-    // Group the segments by kernel instantiation; order inside a group is the caller's order.
+// Launch plan of a batched reduction: the segments grouped by kernel instantiation (order inside a group is the caller's
+// order), flattened in launch order with gridDim.y <= 65535 per launch.
+struct ReduceLaunch { int dtype, tier, masked; size_t cnt; uint32_t max_blk; size_t seg0; };
+struct ReducePlan {
+    std::vector<ReduceLaunch> launches;
+    std::vector<ReduceSeg> flat;
+    size_t max_cnt = 0, max_pblk = 0;
+};
+static ReducePlan plan_reduce_batch(size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities, bool minmax) {
     struct Key { int dtype, tier, masked; };
     std::vector<Key> keys;
     std::vector<std::vector<ReduceSeg>> groups;
@@ -1002,32 +1006,34 @@ static int reduce_batch_launch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs,
         s.nblk = reduce_nblk(b->dtype, b->len, k.tier, minmax); s.out_index = (uint32_t)i;
         groups[g].push_back(s);
     }
-    // One descriptor upload for the whole call (launch order = group order, gridDim.y <= 65535 per launch), so the
-    // launches sit back to back on the stream.  The area is double-buffered; a pageable-source cudaMemcpyAsync stages the
-    // bytes before it returns, so the host vector may die right after; stream order protects the device copy.
-    struct Launch { size_t g, off, cnt; uint32_t max_blk; size_t seg0; };
-    std::vector<Launch> launches;
-    std::vector<ReduceSeg> flat;
-    size_t max_cnt = 0, max_pblk = 0;
+    ReducePlan p;
     for (size_t g = 0; g < groups.size(); ++g)
         for (size_t off = 0; off < groups[g].size(); off += 65535) {
             const size_t cnt = std::min<size_t>(65535, groups[g].size() - off);
             uint32_t max_blk = 1;
             for (size_t i = 0; i < cnt; ++i) max_blk = std::max(max_blk, groups[g][off + i].nblk);
-            launches.push_back(Launch{g, off, cnt, max_blk, flat.size()});
-            flat.insert(flat.end(), groups[g].begin() + off, groups[g].begin() + off + cnt);
-            max_cnt = std::max(max_cnt, cnt);
-            max_pblk = std::max<size_t>(max_pblk, cnt * max_blk);
+            p.launches.push_back(ReduceLaunch{keys[g].dtype, keys[g].tier, keys[g].masked, cnt, max_blk, p.flat.size()});
+            p.flat.insert(p.flat.end(), groups[g].begin() + off, groups[g].begin() + off + cnt);
+            p.max_cnt = std::max(p.max_cnt, cnt);
+            p.max_pblk = std::max<size_t>(p.max_pblk, cnt * max_blk);
         }
-    // Launches of one call run one after the other on the stream, so they share the partials area; tickets are per
-    // segment of a launch and re-arm themselves.
-    int rc = ensure_batch_scratch(c, n, max_cnt, max_pblk);
+    return p;
+}
+
+// Batched launch(es) over validated chunks.  `f` / `x`: optional second stage (per-column fold + cross-GPU exchange) run
+// by the block that writes the last chunk aggregate of the call.  One descriptor upload for the whole call, so the
+// launches sit back to back on the stream.  The descriptor area is double-buffered; a pageable-source cudaMemcpyAsync
+// stages the bytes before it returns, so the host vector may die right after; stream order protects the device copy.
+// Launches of one call run one after the other on the stream, so they share the partials area; tickets are per segment
+// of a launch and re-arm themselves.
+static int reduce_batch_launch(mnr_ctx* c, const ReducePlan& p, bool minmax, AggRaw* outs, const FoldArgs& f, const XchgDev& x) {
+    int rc = ensure_batch_scratch(c, p.flat.size(), p.max_cnt, p.max_pblk);
     if (rc) return rc;
     char* dst = static_cast<char*>(c->batch_segs) + (c->batch_flip ? c->batch_segs_bytes / 2 : 0);
     c->batch_flip ^= 1;
-    CU(cudaMemcpyAsync(dst, flat.data(), flat.size() * sizeof(ReduceSeg), cudaMemcpyHostToDevice, c->stream));
-    for (const Launch& L : launches) {
-        CU(launch_reduce_stats_batch((mnr_dtype)keys[L.g].dtype, keys[L.g].tier, keys[L.g].masked != 0, minmax,
+    CU(cudaMemcpyAsync(dst, p.flat.data(), p.flat.size() * sizeof(ReduceSeg), cudaMemcpyHostToDevice, c->stream));
+    for (const ReduceLaunch& L : p.launches) {
+        CU(launch_reduce_stats_batch((mnr_dtype)L.dtype, L.tier, L.masked != 0, minmax,
                                      reinterpret_cast<const ReduceSeg*>(dst) + L.seg0, (uint32_t)L.cnt, L.max_blk,
                                      static_cast<AggRaw*>(c->batch_partials), static_cast<unsigned int*>(c->batch_tickets),
                                      outs, f, x, c->stream));
@@ -1046,7 +1052,8 @@ int mnr_reduce_stats_batch_async(mnr_ctx* c, size_t n, const mnr_buf* const* buf
         if (rc) return rc;
     }
     CU(cudaSetDevice(c->device));
-    return reduce_batch_launch(c, n, bufs, validities, with_minmax != 0, static_cast<AggRaw*>(out_device), FoldArgs{}, XchgDev{});
+    return reduce_batch_launch(c, plan_reduce_batch(n, bufs, validities, with_minmax != 0), with_minmax != 0,
+                               static_cast<AggRaw*>(out_device), FoldArgs{}, XchgDev{});
 }
 
 int mnr_reduce_stats_batch(mnr_ctx* c, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
@@ -1241,12 +1248,43 @@ static void agg_identity(mnr_dtype dt, AggRaw* a) {
 }
 static int dtype_kind(mnr_dtype dt);
 
-int mnr_reduce_stats_batch_exchange(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr_buf* const* bufs,
-                                    const mnr_bits* const* validities, int with_minmax, size_t n_cols,
-                                    const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes, void* out_device) {
-    REQUIRE(c && (bufs || n == 0) && (col_of_chunk || n == 0) && col_dtypes && out_device, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
+static size_t fold_desc_bytes(size_t n, size_t n_cols, size_t* off_idx, size_t* off_id, size_t* off_kind) {
+    // fold descriptor: [grp_off (n_cols+1) u32][grp_idx n u32][pad to 16][identity n_cols x 32 B][kind n_cols u8]
+    *off_idx = (n_cols + 1) * 4;
+    *off_id = (*off_idx + n * 4 + 15) & ~(size_t)15;
+    *off_kind = *off_id + n_cols * 32;
+    return (*off_kind + n_cols + 15) & ~(size_t)15;
+}
+
+// Every allocation a sharded reduction of this shape needs, made up front.  cudaMalloc / cudaFree synchronise the
+// device: a rank that allocated lazily after a co-located peer's kernel started spinning on its flag would deadlock
+// against it, so mnr_group_reduce_stats reserves on ALL ranks before the first launch.
+static int reduce_exchange_reserve(mnr_ctx* c, const ReducePlan& p, size_t n, size_t n_cols) {
+    CU(cudaSetDevice(c->device));
+    int rc = ensure_batch_scratch(c, p.flat.size(), p.max_cnt, p.max_pblk);
+    if (rc) return rc;
+    const size_t need_aggs = n ? n : 1;
+    if (c->chunk_aggs_cap < need_aggs) {
+        if (c->chunk_aggs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->chunk_aggs)); }
+        c->chunk_aggs = nullptr; c->chunk_aggs_cap = 0;
+        CU(cudaMalloc(&c->chunk_aggs, sizeof(AggRaw) * need_aggs));
+        c->chunk_aggs_cap = need_aggs;
+    }
+    size_t o1, o2, o3;
+    const size_t desc_bytes = fold_desc_bytes(n, n_cols, &o1, &o2, &o3);
+    if (c->fold_desc_bytes < desc_bytes * 2) {
+        if (c->fold_desc) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->fold_desc)); }
+        c->fold_desc = nullptr; c->fold_desc_bytes = 0;
+        CU(cudaMalloc(&c->fold_desc, desc_bytes * 2));
+        c->fold_desc_bytes = desc_bytes * 2;
+    }
+    return MNR_OK;
+}
+
+static int check_batch_exchange(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities,
+                                size_t n_cols, const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes) {
+    REQUIRE(c && (bufs || n == 0) && (col_of_chunk || n == 0) && col_dtypes, MNR_ERR_INVALID_ARGUMENTS, "NULL argument");
     REQUIRE(n_cols >= 1 && n_cols <= MNR_XCHG_MAX_AGGS, MNR_ERR_INVALID_ARGUMENTS, "n_cols %zu out of range (1..%d)", n_cols, MNR_XCHG_MAX_AGGS);
-    REQUIRE((reinterpret_cast<uintptr_t>(out_device) & 15u) == 0, MNR_ERR_INVALID_ARGUMENTS, "out_device must be 16-byte aligned");
     REQUIRE(n <= 0xffffffffull, MNR_ERR_INVALID_ARGUMENTS, "too many chunks");
     if (x) { int rc = check_xchg(c, x); if (rc) return rc; }
     for (size_t g = 0; g < n_cols; ++g) REQUIRE(valid_dtype(col_dtypes[g]), MNR_ERR_UNSUPPORTED_TYPE, "column %zu: unknown dtype %d", g, (int)col_dtypes[g]);
@@ -1257,10 +1295,33 @@ int mnr_reduce_stats_batch_exchange(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr
         REQUIRE(bufs[i]->dtype == col_dtypes[col_of_chunk[i]], MNR_ERR_TYPE_MISMATCH, "chunk %zu has dtype %d, its column %u has %d", i,
                 (int)bufs[i]->dtype, col_of_chunk[i], (int)col_dtypes[col_of_chunk[i]]);
     }
-    CU(cudaSetDevice(c->device));
-    // fold descriptor: [grp_off (n_cols+1) u32][grp_idx n u32][pad to 16][identity n_cols x 32 B][kind n_cols u8]
-    const size_t off_idx = (n_cols + 1) * 4, off_id = (off_idx + n * 4 + 15) & ~(size_t)15, off_kind = off_id + n_cols * 32;
-    const size_t desc_bytes = (off_kind + n_cols + 15) & ~(size_t)15;
+    return MNR_OK;
+}
+
+}  // extern "C"
+namespace mnr {
+int reduce_stats_batch_exchange_reserve(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr_buf* const* bufs,
+                                        const mnr_bits* const* validities, int with_minmax, size_t n_cols,
+                                        const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes) {
+    int rc = check_batch_exchange(c, x, n, bufs, validities, n_cols, col_of_chunk, col_dtypes);
+    if (rc) return rc;
+    return reduce_exchange_reserve(c, plan_reduce_batch(n, bufs, validities, with_minmax != 0), n, n_cols);
+}
+}  // namespace mnr
+extern "C" {
+
+int mnr_reduce_stats_batch_exchange(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr_buf* const* bufs,
+                                    const mnr_bits* const* validities, int with_minmax, size_t n_cols,
+                                    const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes, void* out_device) {
+    int rc = check_batch_exchange(c, x, n, bufs, validities, n_cols, col_of_chunk, col_dtypes);
+    if (rc) return rc;
+    REQUIRE(out_device && (reinterpret_cast<uintptr_t>(out_device) & 15u) == 0, MNR_ERR_INVALID_ARGUMENTS,
+            "out_device must be a 16-byte aligned device pointer");
+    const ReducePlan plan = plan_reduce_batch(n, bufs, validities, with_minmax != 0);
+    rc = reduce_exchange_reserve(c, plan, n, n_cols);
+    if (rc) return rc;
+    size_t off_idx, off_id, off_kind;
+    const size_t desc_bytes = fold_desc_bytes(n, n_cols, &off_idx, &off_id, &off_kind);
     std::vector<unsigned char> desc(desc_bytes, 0);
     uint32_t* grp_off = reinterpret_cast<uint32_t*>(desc.data());
     uint32_t* grp_idx = reinterpret_cast<uint32_t*>(desc.data() + off_idx);
@@ -1273,19 +1334,6 @@ int mnr_reduce_stats_batch_exchange(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr
     for (size_t g = 0; g < n_cols; ++g) {
         agg_identity(col_dtypes[g], reinterpret_cast<AggRaw*>(desc.data() + off_id) + g);
         desc[off_kind + g] = (unsigned char)dtype_kind(col_dtypes[g]);
-    }
-    const size_t need_aggs = n ? n : 1;
-    if (c->chunk_aggs_cap < need_aggs) {
-        if (c->chunk_aggs) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->chunk_aggs)); }
-        c->chunk_aggs = nullptr; c->chunk_aggs_cap = 0;
-        CU(cudaMalloc(&c->chunk_aggs, sizeof(AggRaw) * need_aggs));
-        c->chunk_aggs_cap = need_aggs;
-    }
-    if (c->fold_desc_bytes < desc_bytes * 2) {
-        if (c->fold_desc) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->fold_desc)); }
-        c->fold_desc = nullptr; c->fold_desc_bytes = 0;
-        CU(cudaMalloc(&c->fold_desc, desc_bytes * 2));
-        c->fold_desc_bytes = desc_bytes * 2;
     }
     char* dd = static_cast<char*>(c->fold_desc) + (c->fold_flip ? c->fold_desc_bytes / 2 : 0);
     c->fold_flip ^= 1;
@@ -1305,7 +1353,7 @@ int mnr_reduce_stats_batch_exchange(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr
         CU(launch_fold_exchange(c->chunk_aggs, f, xd, c->stream));
         c->launches++;
     } else {
-        int rc = reduce_batch_launch(c, n, bufs, validities, with_minmax != 0, c->chunk_aggs, f, xd);
+        rc = reduce_batch_launch(c, plan, with_minmax != 0, c->chunk_aggs, f, xd);
         if (rc) { cudaMemsetAsync(f.gticket, 0, 4, c->stream); return rc; }   // the fold only fires after the LAST launch: no epoch was consumed
     }
     if (x) x->epoch++;

@@ -13,6 +13,10 @@
 
 namespace mnr {
 int fail_public(int code, const char* msg);
+// api.cu: validation + every allocation of mnr_reduce_stats_batch_exchange, without launching anything
+int reduce_stats_batch_exchange_reserve(mnr_ctx* c, mnr_xchg* x, size_t n, const mnr_buf* const* bufs,
+                                        const mnr_bits* const* validities, int with_minmax, size_t n_cols,
+                                        const uint32_t* col_of_chunk, const mnr_dtype* col_dtypes);
 }
 
 static int failf(int code, const char* fmt, ...) {
@@ -230,20 +234,25 @@ int mnr_group_reduce_stats(mnr_group* g, size_t n, const mnr_buf* const* bufs, c
         REQUIRE(!v || v->len >= bufs[i]->len, MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: validity has %zu bits, need %zu", i, v->len, bufs[i]->len);
     }
     REQUIRE(n_cols >= 1 && n_cols <= MNR_XCHG_MAX_AGGS, MNR_ERR_INVALID_ARGUMENTS, "n_cols %zu out of range (1..%d)", n_cols, MNR_XCHG_MAX_AGGS);
-    for (size_t r = 0; r < world; ++r) {
-        const size_t m = idx[r].size();
-        std::vector<const mnr_buf*> b(m);
-        std::vector<const mnr_bits*> v(m, nullptr);
-        std::vector<uint32_t> col(m);
-        for (size_t k = 0; k < m; ++k) {
-            const size_t i = idx[r][k];
-            b[k] = bufs[i]; col[k] = col_of_chunk[i];
-            if (validities) v[k] = validities[i];
+    // Pass 0 validates and allocates on every rank, pass 1 launches: cudaMalloc synchronises its device, so a rank that
+    // allocated lazily after a co-located peer (virtual ranks) had started spinning on its flag would deadlock against it;
+    // and a rank failing validation after its peers launched would leave them waiting until the timeout.
+    for (int pass = 0; pass < 2; ++pass)
+        for (size_t r = 0; r < world; ++r) {
+            const size_t m = idx[r].size();
+            std::vector<const mnr_buf*> b(m);
+            std::vector<const mnr_bits*> v(m, nullptr);
+            std::vector<uint32_t> col(m);
+            for (size_t k = 0; k < m; ++k) {
+                const size_t i = idx[r][k];
+                b[k] = bufs[i]; col[k] = col_of_chunk[i];
+                if (validities) v[k] = validities[i];
+            }
+            mnr_ctx* c = g->ctx[r];
+            rc = pass == 0 ? mnr::reduce_stats_batch_exchange_reserve(c, g->xchg[r], m, b.data(), v.data(), with_minmax, n_cols, col.data(), col_dtypes)
+                           : mnr_reduce_stats_batch_exchange(c, g->xchg[r], m, b.data(), v.data(), with_minmax, n_cols, col.data(), col_dtypes, c->fold_result);
+            if (rc) return rc;
         }
-        mnr_ctx* c = g->ctx[r];
-        rc = mnr_reduce_stats_batch_exchange(c, g->xchg[r], m, b.data(), v.data(), with_minmax, n_cols, col.data(), col_dtypes, c->fold_result);
-        if (rc) return rc;
-    }
     // Every rank holds the same bits; rank 0's copy goes to the caller.  All ranks are drained so the group is idle on return.
     mnr_ctx* c0 = g->ctx[0];
     cudaSetDevice(c0->device);

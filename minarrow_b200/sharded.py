@@ -298,11 +298,12 @@ class FusedExchange:
         return {"sum": getattr(agg.sum, f), "min": getattr(agg.min, f), "max": getattr(agg.max, f), "count": int(agg.count),
                 "mean": float(self.ctx.lib.mnr_agg_mean(dtype_code(buf.dtype), C.byref(agg)))}
 
-    def reduce_stats_batch_async(self, bufs, validities, with_minmax: bool, col_of_chunk, col_dtypes, out_device_ptr: int):
+    def reduce_stats_batch_async(self, bufs, validities, with_minmax: bool, col_of_chunk, col_dtypes, out_device_ptr: int,
+                                 plan: "BatchExchangePlan" = None):
         """Sharded SuperArray / SuperTable reduction, asynchronous: this rank's chunks (chunk i belongs to column
         col_of_chunk[i]) -> len(col_dtypes) global aggregates at `out_device_ptr` on every rank.  One batched launch
         per (dtype, alignment, masked) class; the fold and the cross-GPU exchange ride in the last block."""
-        _batch_exchange(self.ctx, self.h, bufs, validities, with_minmax, col_of_chunk, col_dtypes, out_device_ptr, None)
+        _batch_exchange(self.ctx, self.h, bufs, validities, with_minmax, col_of_chunk, col_dtypes, out_device_ptr, None, plan)
 
     def reduce_stats_batch(self, bufs, validities, with_minmax: bool, col_of_chunk, col_dtypes) -> list:
         aggs = (_lib.Agg * len(col_dtypes))()
@@ -340,17 +341,26 @@ def _handles(items):
     return arr
 
 
-def _batch_exchange(ctx, xh, bufs, validities, with_minmax, col_of_chunk, col_dtypes, out_device_ptr, out_aggs):
-    n, n_cols = len(bufs), len(col_dtypes)
-    cols = (C.c_uint32 * max(1, n))(*[int(c) for c in col_of_chunk])
-    dts = (C.c_int * n_cols)(*[dtype_code(d) for d in col_dtypes])
-    vals = None if validities is None else _handles(list(validities))
+class BatchExchangePlan:
+    """Pre-marshalled argument arrays of a repeated sharded reduction (the ctypes arrays are built once)."""
+
+    def __init__(self, bufs, validities, col_of_chunk, col_dtypes):
+        self.n, self.n_cols = len(bufs), len(col_dtypes)
+        self.bufs = _handles(list(bufs))
+        self.vals = None if validities is None else _handles(list(validities))
+        self.cols = (C.c_uint32 * max(1, self.n))(*[int(c) for c in col_of_chunk])
+        self.dts = (C.c_int * self.n_cols)(*[dtype_code(d) for d in col_dtypes])
+        self.keep = (bufs, validities)
+
+
+def _batch_exchange(ctx, xh, bufs, validities, with_minmax, col_of_chunk, col_dtypes, out_device_ptr, out_aggs, plan=None):
+    p = plan or BatchExchangePlan(bufs, validities, col_of_chunk, col_dtypes)
     if out_aggs is None:
-        check(ctx.lib.mnr_reduce_stats_batch_exchange(ctx.h, xh, n, _handles(list(bufs)), vals, int(with_minmax), n_cols, cols, dts,
+        check(ctx.lib.mnr_reduce_stats_batch_exchange(ctx.h, xh, p.n, p.bufs, p.vals, int(with_minmax), p.n_cols, p.cols, p.dts,
                                                       C.c_void_p(out_device_ptr)))
     else:
-        check(ctx.lib.mnr_reduce_stats_batch_exchange_sync(ctx.h, xh, n, _handles(list(bufs)), vals, int(with_minmax), n_cols, cols,
-                                                           dts, out_aggs))
+        check(ctx.lib.mnr_reduce_stats_batch_exchange_sync(ctx.h, xh, p.n, p.bufs, p.vals, int(with_minmax), p.n_cols, p.cols,
+                                                           p.dts, out_aggs))
 
 
 def sharded_stats(columns: Sequence["ShardedColumn"], with_minmax: bool = True, group=None,

@@ -65,10 +65,15 @@ def test_group_supertable_stats_and_elementwise(gpu_ctx, oracle, world):
             assert abs(got[c]["sum"] - exp["sum"]) <= 1e-12 * np.abs(whole[valid].astype(np.float64)).sum()
         else:
             assert got[c]["sum"] == exp["sum"]
-    # sum + count only (the cheaper kernel) gives the same sums
+    # sum + count only (the cheaper kernel): same counts and integer sums; float sums take another vector tier = another
+    # (documented) summation order, so they agree to the tolerance only
     got2 = g.reduce_stats(flat_b, flat_v, False, cols, dts)
-    for c in range(4):
-        assert got2[c]["count"] == got[c]["count"] and got2[c]["sum"] == got[c]["sum"]
+    for c, dt in enumerate(dts):
+        assert got2[c]["count"] == got[c]["count"]
+        if np.dtype(dt).kind == "f":
+            assert abs(got2[c]["sum"] - got[c]["sum"]) <= 1e-12 * np.abs(np.concatenate([x.data for x in lt[c]]).astype(np.float64)).sum()
+        else:
+            assert got2[c]["sum"] == got[c]["sum"]
     # table * table: chunk pairs on their owning ranks, OR-union validity like route_super_array_broadcast
     for c, dt in enumerate(dts):
         ob, om = g.ew_binary(mnr.ArithmeticOperator.Multiply, lb[c], rb[c], lv[c], rv[c], mnr.MaskMode.Or)
