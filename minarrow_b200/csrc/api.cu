@@ -1084,6 +1084,8 @@ int mnr_xchg_create(mnr_ctx* c, int world, int rank, mnr_xchg** out) {
     REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, MNR_ERR_INVALID_ARGUMENTS,
             "world %d / rank %d out of range (max %d peers)", world, rank, kMaxPeers);
     CU(cudaSetDevice(c->device));
+    // Kernels of an exchange wait on their peers: everything they may need must be resident before the first one runs.
+    CU(reduce_preload_all());
     mnr_xchg* x = new mnr_xchg();
     x->ctx = c; x->world = world; x->rank = rank;
     cudaError_t e = cudaMalloc(&x->mailbox, kMailboxBytes);

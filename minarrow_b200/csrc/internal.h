@@ -32,6 +32,8 @@ cudaError_t launch_reduce_stats_batch(mnr_dtype dt, int tier, bool masked, bool 
                                       uint32_t nseg, uint32_t max_blk, AggRaw* partials, unsigned int* tickets,
                                       AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s);
 cudaError_t launch_fold_exchange(const AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s);
+// Load every reduction kernel on the current device now (see reduce.cu: lazy loading vs. kernels that wait on peers).
+cudaError_t reduce_preload_all();
 
 // Element-wise binary op.  lhs/rhs: device pointers, or NULL for the side held in `scalar_bits`
 // (at most one).  lmask/rmask: NULL or validity bytes indexed from bit 0.  out_mask: required iff a mask is

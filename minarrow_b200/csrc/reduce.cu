@@ -95,6 +95,27 @@ static cudaError_t batch_t(int tier, bool masked, bool minmax, const ReduceSeg* 
 #undef CALLB
 }
 
+// Force-load every instantiation of this element type (CUDA loads kernels lazily, and loading one needs the device to
+// be idle: a first launch issued while a peer's kernel is already spinning on this rank's flag would deadlock against
+// it on a shared device).  cudaFuncGetAttributes loads the function.
+template <typename T, typename VecT, bool MASKED, bool MINMAX>
+static cudaError_t preload_one() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, reduce_stats_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>);
+    if (e != cudaSuccess) return e;
+    return cudaFuncGetAttributes(&a, reduce_stats_batch_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>);
+}
+template <typename T>
+static cudaError_t preload_t() {
+    cudaError_t e = cudaSuccess;
+#define PL(V, M, X) if (e == cudaSuccess) e = preload_one<T, V, M, X>()
+    PL(V32, true, true); PL(V32, false, true);
+    PL(V16, true, true); PL(V16, false, true); PL(V16, true, false); PL(V16, false, false);
+    PL(T, true, true); PL(T, false, true); PL(T, true, false); PL(T, false, false);
+#undef PL
+    return e;
+}
+
 // This file is compiled once per element type (-DMNR_RED_DTYPE=<mnr_dtype code>) plus a front (-DMNR_RED_DTYPE=100)
 // that switches on the runtime dtype; see the Makefile.
 #define MNR_RED_DECL(NAME)                                                                                                   \
@@ -102,7 +123,8 @@ static cudaError_t batch_t(int tier, bool masked, bool minmax, const ReduceSeg* 
                                      const XchgDev&, int, cudaStream_t);                                                     \
     uint32_t reduce_nblk_##NAME(uint64_t, int, bool);                                                                        \
     cudaError_t reduce_batch_##NAME(int, bool, bool, const ReduceSeg*, uint32_t, uint32_t, AggRaw*, unsigned int*, AggRaw*,  \
-                                    const FoldArgs&, const XchgDev&, cudaStream_t);
+                                    const FoldArgs&, const XchgDev&, cudaStream_t);                                          \
+    cudaError_t reduce_preload_##NAME();
 #define MNR_RED_DEF(NAME, T)                                                                                                  \
     cudaError_t reduce_single_##NAME(const void* data, const uint8_t* mask, uint64_t n, bool minmax, AggRaw* partials,       \
                                      unsigned int* ticket, AggRaw* out, AggRaw* out_host, const XchgDev& x, int flags,       \
@@ -114,7 +136,8 @@ static cudaError_t batch_t(int tier, bool masked, bool minmax, const ReduceSeg* 
                                     uint32_t max_blk, AggRaw* partials, unsigned int* tickets, AggRaw* outs,                 \
                                     const FoldArgs& f, const XchgDev& x, cudaStream_t s) {                                   \
         return batch_t<T>(tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, f, x, s);                      \
-    }
+    }                                                                                                                         \
+    cudaError_t reduce_preload_##NAME() { return preload_t<T>(); }
 
 #if MNR_RED_DTYPE == 0
 MNR_RED_DEF(i32, int32_t)
@@ -188,6 +211,15 @@ cudaError_t launch_reduce_stats_batch(mnr_dtype dt, int tier, bool masked, bool 
                                       AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s) {
     MNR_DTYPE_SWITCH(dt, reduce_batch, tier, masked, minmax, segs, nseg, max_blk, partials, tickets, outs, f, x, s);
     return cudaErrorInvalidValue;
+}
+
+cudaError_t reduce_preload_all() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, fold_exchange_kernel<kRBlock>);
+#define PLD(NAME) if (e == cudaSuccess) e = reduce_preload_##NAME()
+    PLD(i8); PLD(u8); PLD(i16); PLD(u16); PLD(i32); PLD(u32); PLD(i64); PLD(u64); PLD(f32); PLD(f64);
+#undef PLD
+    return e;
 }
 
 cudaError_t launch_fold_exchange(const AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s) {

@@ -1,19 +1,19 @@
-"""Container fan-out of the broadcast layer that feeds the leaf kernels: the SuperArray route
-(src/kernels/broadcast/super_array.rs:180-249), the Table route (table.rs:31-62) and the SuperTable route
-(super_table.rs:38-73).  Only the decomposition semantics live here — per chunk / per column, operand order,
-chunk-length checks, and which validity merge each route uses; the arithmetic is one fused kernel per chunk.
+"""Container fan-out of the broadcast layer that feeds the leaf kernels, on HOST containers: the SuperArray route
+(src/kernels/broadcast/super_array.rs:180-249), the Table route (table.rs:31-62), the SuperTable route
+(super_table.rs:38-73), the Array <-> SuperArray re-chunk arms (mod.rs:1351-1375 + utils.rs:367-481) and the view
+variants (ArrayV / SuperArrayV / TableV).  Each route uploads its operands once, runs the device-resident route of
+`minarrow_b200.containers` — every leaf call of the operation in batched launches — and downloads the result.  Callers
+that keep their data in HBM use `minarrow_b200.containers` directly and skip both copies.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import numpy as np
 
-from .. import device_ops as dev
-from ..core import (ArithmeticOperator, Bitmask, Context, DeviceBitmask, DeviceBuffer, KernelError, MaskMode, ShapeError,
-                    default_context, make_array)
-from .routing import resolve_binary_arithmetic
+from .. import containers as dc
+from ..core import (ArithmeticOperator, Bitmask, Context, DeviceBitmask, KernelError, ShapeError, default_context)
 
 
 @dataclass
@@ -31,46 +31,37 @@ class SuperArray:
         return [len(c) for c in self.chunks]
 
 
-def route_super_array_broadcast(op: ArithmeticOperator, lhs: SuperArray, rhs: SuperArray,
-                                null_mask_override: Optional[Bitmask] = None, ctx: Optional[Context] = None) -> SuperArray:
-    """Per-chunk arithmetic.  Validity per chunk: override if given, else the OR-union of the two chunks'
-    masks, else the one present mask (super_array.rs:214-230) — fused into the kernel (MaskMode.Or)."""
-    ctx = ctx or default_context()
-    out = SuperArray()
-    # Chunk pairs that can share one batched launch (same dtype and length, at least one mask, no override):
-    # upload them all, one mnr_ew_binary_batch call, download.  Everything else takes the per-chunk router.
-    slots, bl, br, blm, brm = [], [], [], [], []
-    for i, lc in enumerate(lhs.chunks):
-        rc = rhs.chunks[i]
-        if len(lc) != len(rc):
-            raise ShapeError(f"Super Array broadcasting error for {op!r} - Chunk: LHS {len(lc)} RHS {len(rc)}, "
-                             f"Shape: LHS {lhs.shape_1d()} RHS {rhs.shape_1d()}")
-        if null_mask_override is not None:
-            out.chunks.append(resolve_binary_arithmetic(op, lc, rc, null_mask_override, ctx))
-            continue
-        lm, rm = getattr(lc, "null_mask", None), getattr(rc, "null_mask", None)
-        if lm is None and rm is None:
-            out.chunks.append(resolve_binary_arithmetic(op, lc, rc, None, ctx))
-            continue
-        ld, rd = np.ascontiguousarray(lc.data), np.ascontiguousarray(rc.data)
-        if ld.dtype != rd.dtype or ld.size != rd.size:
-            merged = lm if rm is None else rm if lm is None else None
-            if merged is None:
-                from .bitmask import union
-                merged = union(lm, rm, ctx)
-            out.chunks.append(resolve_binary_arithmetic(op, lc, rc, merged, ctx))
-            continue
-        slots.append(len(out.chunks))
-        out.chunks.append(None)
-        bl.append(DeviceBuffer.upload(ctx, ld))
-        br.append(DeviceBuffer.upload(ctx, rd))
-        blm.append(None if lm is None else DeviceBitmask.upload(ctx, lm))
-        brm.append(None if rm is None else DeviceBitmask.upload(ctx, rm))
-    if slots:
-        obs, oms = dev.ew_binary_batch(ctx, op, bl, br, blm, brm, MaskMode.Or)
-        for slot, ob, om in zip(slots, obs, oms):
-            out.chunks[slot] = make_array(ob.download(), om.download())
-    return out
+@dataclass
+class ArrayV:
+    """`ArrayV = (Array, offset, len)` window (src/structs/views/array_view.rs:79-94)."""
+    array: object
+    offset: int = 0
+    len: int = -1
+
+    def __post_init__(self):
+        n = len(self.array)
+        if self.len < 0:
+            self.len = n - self.offset
+        if self.offset < 0 or self.offset + self.len > n:
+            raise KernelError("OutOfBounds", f"ArrayV window [{self.offset}, {self.offset + self.len}) of an array of {n}")
+
+    def __len__(self) -> int:
+        return self.len
+
+    def slice(self, offset: int, length: int) -> "ArrayV":
+        """`ArrayV::slice` — a window of the window."""
+        if offset + length > self.len:
+            raise KernelError("OutOfBounds", "ArrayV::slice out of bounds")
+        return ArrayV(self.array, self.offset + offset, length)
+
+
+@dataclass
+class SuperArrayV:
+    """`SuperArrayV {slices: Vec<ArrayV>, len}` (src/structs/views/chunked/super_array_view.rs)."""
+    slices: List[ArrayV] = field(default_factory=list)
+
+    def __len__(self) -> int:
+        return sum(len(s) for s in self.slices)
 
 
 @dataclass
@@ -84,6 +75,23 @@ class Table:
 
     def n_rows(self) -> int:
         return len(self.cols[0]) if self.cols else 0
+
+
+@dataclass
+class TableV:
+    """`TableV {cols: Vec<ArrayV>, offset, len}` (src/structs/views/table_view.rs): the same row window of every column."""
+    table: Table
+    offset: int = 0
+    len: int = -1
+
+    def __post_init__(self):
+        if self.len < 0:
+            self.len = self.table.n_rows() - self.offset
+        if self.offset < 0 or self.offset + self.len > self.table.n_rows():
+            raise KernelError("OutOfBounds", "TableV window exceeds the table")
+
+    def n_cols(self) -> int:
+        return self.table.n_cols()
 
 
 @dataclass
@@ -102,90 +110,149 @@ class SuperTable:
         return self.batches[0].n_cols() if self.batches else 0
 
 
-def _cols(t):
-    return t.cols if isinstance(t, Table) else list(t)
+def _is_scalar(x) -> bool:
+    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
+
+
+def _window(arr, offset: int, length: int):
+    """Host copy of rows [offset, offset + len) of a typed array: values slice + validity bits re-based to bit 0
+    (`slice_clone`)."""
+    from ..core import make_array
+    data = np.ascontiguousarray(getattr(arr, "data", arr))[offset:offset + length]
+    m = getattr(arr, "null_mask", None)
+    if m is not None:
+        m = Bitmask.from_bools(m.to_bools()[offset:offset + length])
+    return make_array(data, m)
+
+
+def to_device(ctx: Context, v):
+    """Host Value -> device-resident Value (scalars stay on the host)."""
+    if _is_scalar(v) or isinstance(v, (dc.DeviceArray, dc.DeviceSuperArray, dc.DeviceTable, dc.DeviceSuperTable)):
+        return v
+    if isinstance(v, SuperTable):
+        return dc.DeviceSuperTable.from_host(ctx, v)
+    if isinstance(v, Table):
+        return dc.DeviceTable.from_host(ctx, v)
+    if isinstance(v, TableV):
+        return dc.DeviceTable(v.table.name, [dc.DeviceArray.from_host(ctx, _window(c, v.offset, v.len)) for c in v.table.cols])
+    if isinstance(v, SuperArray):
+        return dc.DeviceSuperArray.from_host(ctx, v)
+    if isinstance(v, SuperArrayV):
+        return dc.DeviceSuperArray([dc.DeviceArray.from_host(ctx, _window(s.array, s.offset, s.len)) for s in v.slices])
+    if isinstance(v, ArrayV):
+        return dc.DeviceArray.from_host(ctx, _window(v.array, v.offset, v.len))
+    return dc.DeviceArray.from_host(ctx, v)
+
+
+def _run(op, lhs, rhs, ctx, fn=dc.broadcast_value):
+    ctx = ctx or default_context()
+    return fn(op, to_device(ctx, lhs), to_device(ctx, rhs), ctx).to_host()
+
+
+def route_super_array_broadcast(op: ArithmeticOperator, lhs: SuperArray, rhs: SuperArray,
+                                null_mask_override: Optional[Bitmask] = None, ctx: Optional[Context] = None) -> SuperArray:
+    """Per-chunk arithmetic.  Validity per chunk: override if given, else the OR-union of the two chunks'
+    masks, else the one present mask (super_array.rs:214-230) — fused into the kernel (MaskMode.Or); one batched call."""
+    ctx = ctx or default_context()
+    ov = None if null_mask_override is None else DeviceBitmask.upload(ctx, null_mask_override)
+    return dc.route_super_array_broadcast(op, to_device(ctx, lhs), to_device(ctx, rhs), ov, ctx).to_host()
+
+
+def create_aligned_chunks_from_array(array, super_array: SuperArray, ctx: Optional[Context] = None) -> SuperArray:
+    """src/utils.rs:417-481: `array` split to the SuperArray's chunk lengths, each chunk carrying its window of the union
+    of the array's mask and the concatenated chunk masks (computed on the device)."""
+    ctx = ctx or default_context()
+    return dc.create_aligned_chunks_from_array(to_device(ctx, array), to_device(ctx, super_array)).to_host()
 
 
 def broadcast_table_with_operator(op: ArithmeticOperator, lhs, rhs, ctx=None):
     """Table route (table.rs:31-62): column i of lhs against column i of rhs through the router with NO mask (so the
     result columns carry no validity and a dense integer zero divisor is the reference's panic).  Returns a `Table`
     named after the left one (or a list when plain column lists were passed)."""
-    lc, rc = _cols(lhs), _cols(rhs)
-    if len(lc) != len(rc):
-        raise ShapeError(f"Table column count mismatch: {len(lc)} vs {len(rc)}")
-    out = [resolve_binary_arithmetic(op, l, r, None, ctx) for l, r in zip(lc, rc)]
-    return Table(lhs.name, out) if isinstance(lhs, Table) else out
+    as_list = not isinstance(lhs, Table)
+    lt = lhs if isinstance(lhs, Table) else Table("", list(lhs))
+    rt = rhs if isinstance(rhs, Table) else Table("", list(rhs))
+    if lt.n_cols() != rt.n_cols():
+        raise ShapeError(f"Table column count mismatch: {lt.n_cols()} vs {rt.n_cols()}")
+    out = _run(op, lt, rt, ctx, dc.broadcast_table_with_operator)
+    return out.cols if as_list else out
 
 
 def broadcast_table_to_array(op: ArithmeticOperator, table: Table, arr, ctx=None) -> Table:
-    """`table op array`: every column against the same array (table.rs broadcast_table_to_array)."""
-    return Table(table.name, [resolve_binary_arithmetic(op, c, arr, None, ctx) for c in table.cols])
+    """`table op array`: every column against the same array (table.rs:179-228)."""
+    return _run(op, table, arr, ctx)
 
 
 def broadcast_array_to_table(op: ArithmeticOperator, arr, table: Table, ctx=None) -> Table:
-    """`array op table`: operand order is significant (array.rs broadcast_array_to_table)."""
-    return Table(table.name, [resolve_binary_arithmetic(op, arr, c, None, ctx) for c in table.cols])
-
-
-def _scalar_array(scalar, like):
-    """Scalar -> length-1 array of the column's dtype (scalar.rs:169-210, array.rs:139-184)."""
-    return np.array([scalar], dtype=np.asarray(getattr(like, "data", like)).dtype)
+    """`array op table`: operand order is significant (array.rs:187-236)."""
+    return _run(op, arr, table, ctx)
 
 
 def broadcast_table_to_scalar(op: ArithmeticOperator, table: Table, scalar, ctx=None) -> Table:
     """`table op scalar`: the same scalar against every column (table.rs:230-261)."""
-    return Table(table.name, [resolve_binary_arithmetic(op, c, _scalar_array(scalar, c), None, ctx) for c in table.cols])
+    return _run(op, table, scalar, ctx)
 
 
 def broadcast_scalar_to_table(op: ArithmeticOperator, scalar, table: Table, ctx=None) -> Table:
-    return Table(table.name, [resolve_binary_arithmetic(op, _scalar_array(scalar, c), c, None, ctx) for c in table.cols])
+    return _run(op, scalar, table, ctx)
 
 
 def broadcast_super_table_with_operator(op: ArithmeticOperator, lhs, rhs, ctx=None):
-    """SuperTable route (super_table.rs:38-73): batch by batch through the Table route."""
-    lb = lhs.batches if isinstance(lhs, SuperTable) else list(lhs)
-    rb = rhs.batches if isinstance(rhs, SuperTable) else list(rhs)
-    if len(lb) != len(rb):
-        raise ShapeError(f"SuperTable chunk count mismatch: {len(lb)} vs {len(rb)}")
-    out = [broadcast_table_with_operator(op, l, r, ctx) for l, r in zip(lb, rb)]
-    return SuperTable(out, getattr(lhs, "name", "")) if isinstance(lhs, SuperTable) else out
+    """SuperTable route (super_table.rs:38-73): batch by batch through the Table route; all batches x columns go out in one
+    batched call (one launch per column dtype)."""
+    as_list = not isinstance(lhs, SuperTable)
+    ls = lhs if isinstance(lhs, SuperTable) else SuperTable([b if isinstance(b, Table) else Table("", list(b)) for b in lhs])
+    rs = rhs if isinstance(rhs, SuperTable) else SuperTable([b if isinstance(b, Table) else Table("", list(b)) for b in rhs])
+    if ls.n_batches() != rs.n_batches():
+        raise ShapeError(f"SuperTable chunk count mismatch: {ls.n_batches()} vs {rs.n_batches()}")
+    out = _run(op, ls, rs, ctx, dc.broadcast_super_table_with_operator)
+    return [b.cols for b in out.batches] if as_list else out
 
 
-def _is_scalar(x) -> bool:
-    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
+def broadcast_arrayview_to_superarray(op: ArithmeticOperator, view: ArrayV, sa, ctx=None) -> SuperArray:
+    """ArrayView (op) SuperArray / SuperArrayView (super_array.rs:255-309, 367-419): NO mask, chunk by chunk."""
+    ctx = ctx or default_context()
+    return dc.broadcast_arrayview_to_superarray(op, to_device(ctx, view), to_device(ctx, sa), True, ctx).to_host()
+
+
+def broadcast_superarray_to_arrayview(op: ArithmeticOperator, sa, view: ArrayV, ctx=None) -> SuperArray:
+    """SuperArray / SuperArrayView (op) ArrayView (super_array.rs:311-365, 421-470)."""
+    ctx = ctx or default_context()
+    return dc.broadcast_arrayview_to_superarray(op, to_device(ctx, view), to_device(ctx, sa), False, ctx).to_host()
+
+
+def broadcast_tableview_to_tableview(op: ArithmeticOperator, lhs: TableV, rhs: TableV, ctx=None) -> Table:
+    """table_view.rs:25-60: the windows of column i against each other, no mask; the result Table is unnamed."""
+    if lhs.n_cols() != rhs.n_cols():
+        raise ShapeError(f"TableView column count mismatch: {lhs.n_cols()} vs {rhs.n_cols()}")
+    out = _run(op, lhs, rhs, ctx, dc.broadcast_table_with_operator)
+    out.name = ""
+    return out
 
 
 def broadcast_value(op: ArithmeticOperator, lhs, rhs, ctx=None):
     """`broadcast_value(op, Value, Value)` (src/kernels/broadcast/mod.rs:152-...) for the Value variants on this path:
-    Scalar (python / numpy number), Array (numpy, IntegerArray, FloatArray), SuperArray, Table, SuperTable.
-    Array-level routes pass no mask (mod.rs:166-209); the SuperArray route merges chunk masks by OR-union."""
-    if isinstance(lhs, SuperTable) and isinstance(rhs, SuperTable):
-        return broadcast_super_table_with_operator(op, lhs, rhs, ctx)
-    if isinstance(lhs, SuperTable) and _is_scalar(rhs):
-        return SuperTable([broadcast_table_to_scalar(op, b, rhs, ctx) for b in lhs.batches], lhs.name)
-    if _is_scalar(lhs) and isinstance(rhs, SuperTable):
-        return SuperTable([broadcast_scalar_to_table(op, lhs, b, ctx) for b in rhs.batches], rhs.name)
-    if isinstance(lhs, Table) and isinstance(rhs, Table):
-        return broadcast_table_with_operator(op, lhs, rhs, ctx)
-    if isinstance(lhs, Table):
-        return broadcast_table_to_scalar(op, lhs, rhs, ctx) if _is_scalar(rhs) else broadcast_table_to_array(op, lhs, rhs, ctx)
-    if isinstance(rhs, Table):
-        return broadcast_scalar_to_table(op, lhs, rhs, ctx) if _is_scalar(lhs) else broadcast_array_to_table(op, lhs, rhs, ctx)
-    if isinstance(lhs, SuperArray) and isinstance(rhs, SuperArray):
-        return route_super_array_broadcast(op, lhs, rhs, None, ctx)
-    if isinstance(lhs, SuperArray):
-        rr = (lambda c: _scalar_array(rhs, c)) if _is_scalar(rhs) else (lambda c: rhs)
-        return SuperArray([resolve_binary_arithmetic(op, c, rr(c), None, ctx) for c in lhs.chunks])
-    if isinstance(rhs, SuperArray):
-        ll = (lambda c: _scalar_array(lhs, c)) if _is_scalar(lhs) else (lambda c: lhs)
-        return SuperArray([resolve_binary_arithmetic(op, ll(c), c, None, ctx) for c in rhs.chunks])
+    Scalar (python / numpy number), Array (numpy, IntegerArray, FloatArray), ArrayV, SuperArray, SuperArrayV, Table, TableV,
+    SuperTable.  Array-level routes pass no mask (mod.rs:166-209); the SuperArray route merges chunk masks by OR-union;
+    Array (op) SuperArray / SuperArrayV re-chunks the array to the chunk lengths with the union mask (mod.rs:1351-1375);
+    ArrayV (op) SuperArray goes chunk by chunk with no mask (super_array.rs:255-365); Array (op) TableV takes the table
+    view's window of the array (mod.rs:1386-1393)."""
     if _is_scalar(lhs) and _is_scalar(rhs):
         raise KernelError("UnsupportedType", "Scalar op Scalar is host arithmetic, not a kernel route")
-    if _is_scalar(lhs):
-        return resolve_binary_arithmetic(op, _scalar_array(lhs, rhs), rhs, None, ctx)
-    if _is_scalar(rhs):
-        return resolve_binary_arithmetic(op, lhs, _scalar_array(rhs, lhs), None, ctx)
-    return resolve_binary_arithmetic(op, lhs, rhs, None, ctx)
+    ctx = ctx or default_context()
+    L, R = lhs, rhs
+    chunked = (SuperArray, SuperArrayV)
+    if isinstance(L, ArrayV) and isinstance(R, chunked):
+        return broadcast_arrayview_to_superarray(op, L, R, ctx)
+    if isinstance(L, chunked) and isinstance(R, ArrayV):
+        return broadcast_superarray_to_arrayview(op, L, R, ctx)
+    if isinstance(R, TableV) and not isinstance(L, (Table, TableV, SuperTable, ArrayV)) and not _is_scalar(L) and not isinstance(L, chunked):
+        L = ArrayV(L, R.offset, R.len)          # Array (op) TableView: ArrayV::new(array, tv.offset, tv.len)
+    if isinstance(L, TableV) and not isinstance(R, (Table, TableV, SuperTable, ArrayV)) and not _is_scalar(R) and not isinstance(R, chunked):
+        R = ArrayV(R, L.offset, L.len)
+    if isinstance(L, TableV) and isinstance(R, TableV):
+        return broadcast_tableview_to_tableview(op, L, R, ctx)
+    return _run(op, L, R, ctx)
 
 
 def value_add(lhs, rhs, ctx=None):

@@ -190,6 +190,66 @@ def resolve_binary_arithmetic(op: int, lhs, rhs, null_mask=None):
     raise KernelError("UnsupportedType", "Unsupported array type combination for arithmetic operations")
 
 
+# ---- container routes: SuperArray fan-out and the Array <-> SuperArray re-chunk --------------------
+# Chunks are (data: np.ndarray, mask: Optional[Bits]) pairs.
+
+def route_super_array_broadcast(op: int, lhs_chunks, rhs_chunks, null_mask_override: Optional[Bits] = None):
+    """route_super_array_broadcast — src/kernels/broadcast/super_array.rs:180-249: chunk i of lhs against chunk i of rhs
+    through resolve_binary_arithmetic; the chunk's mask is the override if given, else the UNION of the two chunks'
+    masks, else the one present mask, else None (:214-230).  Chunk lengths must match pairwise (:203-213)."""
+    out = []
+    for i, ((ld, lm), (rd, rm)) in enumerate(zip(lhs_chunks, rhs_chunks)):
+        if len(ld) != len(rd):
+            raise KernelError("ShapeError", f"Super Array broadcasting error - Chunk: LHS {len(ld)} RHS {len(rd)}")
+        if null_mask_override is not None:
+            mask = null_mask_override
+        elif lm is not None and rm is not None:
+            mask = union(lm, rm)
+        else:
+            mask = lm if lm is not None else rm
+        out.append(resolve_binary_arithmetic(op, ld, rd, mask))
+    return out
+
+
+def union_array_superarray_masks(arr_mask: Optional[Bits], sa_chunks) -> Optional[Bits]:
+    """union_array_superarray_masks — src/utils.rs:367-413: the SuperArray's chunk masks concatenated bit by bit (a chunk
+    without a mask counts as all valid, but only if SOME chunk has one), OR-ed with the array's mask; lengths must match."""
+    if any(m is not None for _, m in sa_chunks):
+        bools = np.concatenate([np.unpackbits(m.bits, bitorder="little")[:m.len].astype(bool) if m is not None
+                                else np.ones(len(d), dtype=bool) for d, m in sa_chunks])
+        sa_mask = Bits.from_bools(bools)
+    else:
+        sa_mask = None
+    if arr_mask is not None and sa_mask is not None:
+        if arr_mask.len != sa_mask.len:
+            raise KernelError("ShapeError", f"Mask lengths must match for union: {arr_mask.len} vs {sa_mask.len}")
+        return union(arr_mask, sa_mask)
+    return arr_mask if arr_mask is not None else sa_mask
+
+
+def create_aligned_chunks_from_array(arr, arr_mask: Optional[Bits], sa_chunks):
+    """create_aligned_chunks_from_array — src/utils.rs:417-481: split `arr` to the SuperArray's chunk lengths
+    (slice_clone of the values) and give every produced chunk its window of the FULL union mask (bit by bit, :463-469)."""
+    arr = np.asarray(arr)
+    total = sum(len(d) for d, _ in sa_chunks)
+    if arr.size != total:
+        raise KernelError("ShapeError", f"Array and SuperArray must have same total length for broadcasting: {arr.size} vs {total}")
+    full = union_array_superarray_masks(arr_mask, sa_chunks)
+    fb = None if full is None else np.unpackbits(full.bits, bitorder="little")[:full.len].astype(bool)
+    out, start = [], 0
+    for d, _ in sa_chunks:
+        n = len(d)
+        out.append((arr[start:start + n].copy(), None if fb is None else Bits.from_bools(fb[start:start + n])))
+        start += n
+    return out
+
+
+def broadcast_array_superarray(op: int, arr, arr_mask, sa_chunks, array_is_lhs: bool):
+    """`Value::Array (op) Value::SuperArray` and the mirrored arm — src/kernels/broadcast/mod.rs:1351-1361."""
+    aligned = create_aligned_chunks_from_array(arr, arr_mask, sa_chunks)
+    return route_super_array_broadcast(op, aligned, sa_chunks) if array_is_lhs else route_super_array_broadcast(op, sa_chunks, aligned)
+
+
 # ---- bitmask kernels ----------------------------------------------------------------------------
 
 def _win(m):
