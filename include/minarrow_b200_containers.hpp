@@ -394,4 +394,212 @@ template <class S> SuperTable broadcast_super_table_to_scalar(ArithmeticOperator
     return SuperTable::from_batches(std::move(out), t.name);
 }
 
+
+// ---- device-resident containers: operands stay in HBM between calls --------------------------------------------------------
+// The same containers holding mnr_buf / mnr_bits handles.  A route gathers every (chunk, column) leaf call and issues them
+// through mnr_ew_binary_batch (one launch per (dtype, alignment, masked) class); results are device-resident again, so
+// `table * table + table` never visits the host.  Views are free: DeviceArray::view is the ArrayV window (a pointer offset
+// for the values, mnr_bits_slice for the validity), so SuperArrayV = DeviceSuperArray of views, TableV = DeviceTable::view.
+struct DeviceArray {
+    std::shared_ptr<mnr_buf> buf;
+    std::shared_ptr<mnr_bits> mask;   // null = no validity
+    static std::shared_ptr<mnr_buf> own(mnr_buf* b) { return std::shared_ptr<mnr_buf>(b, [](mnr_buf* p) { mnr_buf_free(p); }); }
+    static std::shared_ptr<mnr_bits> own(mnr_bits* b) { return b ? std::shared_ptr<mnr_bits>(b, [](mnr_bits* p) { mnr_bits_free(p); }) : nullptr; }
+    static DeviceArray from_host(Context& ctx, const Array& a) {
+        DeviceArray d;
+        detail::BufH b = detail::upload_window(ctx, ArrayV(a));
+        d.buf = own(b.h); b.h = nullptr;
+        detail::BitsH m = detail::upload_mask(ctx, a.null_mask(), a.len());
+        d.mask = own(m.h); m.h = nullptr;
+        return d;
+    }
+    Array to_host(Context& ctx) const {
+        // detail::download takes ownership of the handles it is given: hand it fresh non-owning views
+        mnr_buf* b = nullptr;
+        check(mnr_buf_slice(buf.get(), 0, len(), &b));
+        mnr_bits* m = nullptr;
+        if (mask) check(mnr_bits_wrap(ctx.get(), mnr_bits_device_ptr(mask.get()), len(), &m));
+        return detail::download(ctx, dtype(), b, m);
+    }
+    size_t len() const { return mnr_buf_len(buf.get()); }
+    mnr_dtype dtype() const { return static_cast<mnr_dtype>(mnr_buf_dtype(buf.get())); }
+    // ArrayV::new(array, offset, len): zero-copy values window (the parent stays alive through the deleter), validity
+    // re-based to bit 0 at its exact bit offset (Bitmask::slice_clone on the device).
+    DeviceArray view(Context& ctx, size_t offset, size_t n) const {
+        if (offset + n > len()) throw KernelError(MNR_ERR_OUT_OF_BOUNDS, "OutOfBounds", "DeviceArray::view exceeds the array");
+        DeviceArray v;
+        mnr_buf* b = nullptr;
+        check(mnr_buf_slice(buf.get(), offset, n, &b));
+        std::shared_ptr<mnr_buf> parent = buf;
+        v.buf = std::shared_ptr<mnr_buf>(b, [parent](mnr_buf* p) { mnr_buf_free(p); });
+        if (mask) { mnr_bits* m = nullptr; check(mnr_bits_slice(ctx.get(), mask.get(), offset, n, &m)); v.mask = own(m); }
+        return v;
+    }
+};
+struct DeviceSuperArray {
+    std::vector<DeviceArray> chunks;
+    static DeviceSuperArray from_host(Context& ctx, const SuperArray& s) { DeviceSuperArray d; for (const auto& c : s.chunks()) d.chunks.push_back(DeviceArray::from_host(ctx, c)); return d; }
+    SuperArray to_host(Context& ctx) const { SuperArray s; for (const auto& c : chunks) s.push(c.to_host(ctx)); return s; }
+    size_t len() const { size_t n = 0; for (const auto& c : chunks) n += c.len(); return n; }
+    size_t n_chunks() const { return chunks.size(); }
+};
+struct DeviceTable {
+    std::string name;
+    std::vector<DeviceArray> cols;
+    static DeviceTable from_host(Context& ctx, const Table& t) { DeviceTable d; d.name = t.name; for (const auto& c : t.cols) d.cols.push_back(DeviceArray::from_host(ctx, c)); return d; }
+    Table to_host(Context& ctx) const { Table t; t.name = name; for (const auto& c : cols) t.cols.push_back(c.to_host(ctx)); return t; }
+    size_t n_cols() const { return cols.size(); }
+    size_t n_rows() const { return cols.empty() ? 0 : cols[0].len(); }
+    DeviceTable view(Context& ctx, size_t offset, size_t n) const { DeviceTable v; v.name = name; for (const auto& c : cols) v.cols.push_back(c.view(ctx, offset, n)); return v; }   // TableV
+};
+struct DeviceSuperTable {
+    std::vector<DeviceTable> batches;
+    std::string name;
+    static DeviceSuperTable from_host(Context& ctx, const SuperTable& s) { DeviceSuperTable d; d.name = s.name; for (const auto& b : s.batches) d.batches.push_back(DeviceTable::from_host(ctx, *b)); return d; }
+    SuperTable to_host(Context& ctx) const { std::vector<Table> b; for (const auto& t : batches) b.push_back(t.to_host(ctx)); return SuperTable::from_batches(std::move(b), name); }
+    size_t n_batches() const { return batches.size(); }
+    size_t n_cols() const { return batches.empty() ? 0 : batches[0].n_cols(); }
+};
+
+namespace detail {
+struct Leaf { const DeviceArray* l; const DeviceArray* r; const mnr_bits* lm; const mnr_bits* rm; };
+// All leaves of one container operation in ONE mnr_ew_binary_batch call.  Operands of a leaf must agree in dtype and length
+// (the length-1 / promotion corners of the router stay on the host layer above: resolve_binary_arithmetic).
+inline std::vector<DeviceArray> route_leaves(Context& ctx, ArithmeticOperator op, const std::vector<Leaf>& leaves, mnr_mask_mode mode) {
+    const size_t n = leaves.size();
+    std::vector<const mnr_buf*> l(n), r(n);
+    std::vector<const mnr_bits*> lm(n), rm(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (leaves[i].l->len() != leaves[i].r->len())
+            throw KernelError(MNR_ERR_LENGTH_MISMATCH, "LengthMismatch", "cannot broadcast arrays of length " + std::to_string(leaves[i].l->len()) + " and " + std::to_string(leaves[i].r->len()));
+        if (leaves[i].l->dtype() != leaves[i].r->dtype() || !routed_dtype(leaves[i].l->dtype()))
+            throw KernelError(MNR_ERR_UNSUPPORTED_TYPE, "UnsupportedType", "Unsupported array type combination for arithmetic operations");
+        l[i] = leaves[i].l->buf.get(); r[i] = leaves[i].r->buf.get(); lm[i] = leaves[i].lm; rm[i] = leaves[i].rm;
+    }
+    std::vector<mnr_buf*> ob(n, nullptr);
+    std::vector<mnr_bits*> om(n, nullptr);
+    if (n) check(mnr_ew_binary_batch(ctx.get(), static_cast<mnr_op>(op), n, l.data(), r.data(), lm.data(), rm.data(), mode, ob.data(), om.data()));
+    std::vector<DeviceArray> out(n);
+    for (size_t i = 0; i < n; ++i) { out[i].buf = DeviceArray::own(ob[i]); out[i].mask = DeviceArray::own(om[i]); }
+    return out;
+}
+}  // namespace detail
+
+// route_super_array_broadcast on the device: chunk i against chunk i, validity = union of the chunks' masks or the one present.
+inline DeviceSuperArray route_super_array_broadcast(ArithmeticOperator op, const DeviceSuperArray& lhs, const DeviceSuperArray& rhs, Context& ctx = Context::thread_default()) {
+    if (rhs.n_chunks() < lhs.n_chunks()) throw KernelError(MNR_ERR_SHAPE, "ShapeError", "Super Array broadcasting error - chunk count");
+    std::vector<detail::Leaf> leaves;
+    for (size_t i = 0; i < lhs.n_chunks(); ++i) {
+        if (lhs.chunks[i].len() != rhs.chunks[i].len())
+            throw KernelError(MNR_ERR_SHAPE, "ShapeError", "Super Array broadcasting error - Chunk: LHS " + std::to_string(lhs.chunks[i].len()) + " RHS " + std::to_string(rhs.chunks[i].len()));
+        leaves.push_back({&lhs.chunks[i], &rhs.chunks[i], lhs.chunks[i].mask.get(), rhs.chunks[i].mask.get()});
+    }
+    DeviceSuperArray out;
+    out.chunks = detail::route_leaves(ctx, op, leaves, MNR_MASK_OR);
+    return out;
+}
+
+// union_array_superarray_masks (src/utils.rs:367-413) on the device: the chunk masks concatenated at bit granularity
+// (mnr_concat's validity gather; a chunk without a mask counts as all valid once ANY chunk has one) OR-ed with the array's.
+inline std::shared_ptr<mnr_bits> union_array_superarray_masks(const DeviceArray& array, const DeviceSuperArray& sa, Context& ctx = Context::thread_default()) {
+    std::shared_ptr<mnr_bits> sa_mask;
+    bool any = false;
+    for (const auto& c : sa.chunks) any = any || c.mask;
+    if (any) {
+        std::vector<const mnr_buf*> b;
+        std::vector<const mnr_bits*> m;
+        for (const auto& c : sa.chunks) { b.push_back(c.buf.get()); m.push_back(c.mask.get()); }
+        mnr_buf* ob = nullptr; mnr_bits* om = nullptr;
+        check(mnr_concat(ctx.get(), b.size(), b.data(), m.data(), &ob, &om));
+        mnr_buf_free(ob);
+        sa_mask = DeviceArray::own(om);
+    }
+    if (array.mask && sa_mask) {
+        if (mnr_bits_len(array.mask.get()) != mnr_bits_len(sa_mask.get()))
+            throw KernelError(MNR_ERR_SHAPE, "ShapeError", "Mask lengths must match for union");
+        mnr_bits* u = nullptr;
+        check(mnr_bits_merge(ctx.get(), array.mask.get(), sa_mask.get(), array.len(), MNR_MASK_OR, &u));
+        return DeviceArray::own(u);
+    }
+    return array.mask ? array.mask : sa_mask;
+}
+
+// create_aligned_chunks_from_array (src/utils.rs:417-481) on the device: `array` re-chunked to the SuperArray's chunk
+// lengths; value chunks are zero-copy windows, every chunk carries its window of the FULL union mask.
+inline DeviceSuperArray create_aligned_chunks_from_array(const DeviceArray& array, const DeviceSuperArray& sa, Context& ctx = Context::thread_default()) {
+    if (array.len() != sa.len())
+        throw KernelError(MNR_ERR_SHAPE, "ShapeError", "Array and SuperArray must have same total length for broadcasting: " + std::to_string(array.len()) + " vs " + std::to_string(sa.len()));
+    DeviceArray carrier;
+    carrier.buf = array.buf;
+    carrier.mask = union_array_superarray_masks(array, sa, ctx);
+    DeviceSuperArray out;
+    size_t start = 0;
+    for (const auto& c : sa.chunks) { out.chunks.push_back(carrier.view(ctx, start, c.len())); start += c.len(); }
+    return out;
+}
+
+// Value::Array (op) Value::SuperArray and the mirrored arm (broadcast/mod.rs:1351-1361): re-chunk, then the SuperArray route.
+inline DeviceSuperArray broadcast_array_to_superarray(ArithmeticOperator op, const DeviceArray& array, const DeviceSuperArray& sa, bool array_is_lhs = true,
+                                                      Context& ctx = Context::thread_default()) {
+    DeviceSuperArray aligned = create_aligned_chunks_from_array(array, sa, ctx);
+    return array_is_lhs ? route_super_array_broadcast(op, aligned, sa, ctx) : route_super_array_broadcast(op, sa, aligned, ctx);
+}
+inline SuperArray create_aligned_chunks_from_array(const Array& array, const SuperArray& sa, Context& ctx = Context::thread_default()) {
+    return create_aligned_chunks_from_array(DeviceArray::from_host(ctx, array), DeviceSuperArray::from_host(ctx, sa), ctx).to_host(ctx);
+}
+inline SuperArray broadcast_array_to_superarray(ArithmeticOperator op, const Array& array, const SuperArray& sa, Context& ctx = Context::thread_default()) {
+    return broadcast_array_to_superarray(op, DeviceArray::from_host(ctx, array), DeviceSuperArray::from_host(ctx, sa), true, ctx).to_host(ctx);
+}
+inline SuperArray broadcast_superarray_to_array(ArithmeticOperator op, const SuperArray& sa, const Array& array, Context& ctx = Context::thread_default()) {
+    return broadcast_array_to_superarray(op, DeviceArray::from_host(ctx, array), DeviceSuperArray::from_host(ctx, sa), false, ctx).to_host(ctx);
+}
+
+// Table / SuperTable routes on the device: NO mask (table.rs:54), every batch x column of the operation in one batched call.
+inline DeviceTable broadcast_table_with_operator(ArithmeticOperator op, const DeviceTable& l, const DeviceTable& r, Context& ctx = Context::thread_default()) {
+    if (l.n_cols() != r.n_cols())
+        throw KernelError(MNR_ERR_SHAPE, "ShapeError", "Table column count mismatch: " + std::to_string(l.n_cols()) + " vs " + std::to_string(r.n_cols()));
+    std::vector<detail::Leaf> leaves;
+    for (size_t i = 0; i < l.n_cols(); ++i) leaves.push_back({&l.cols[i], &r.cols[i], nullptr, nullptr});
+    DeviceTable out;
+    out.name = l.name;
+    out.cols = detail::route_leaves(ctx, op, leaves, MNR_MASK_AND);
+    return out;
+}
+inline DeviceSuperTable broadcast_super_table_with_operator(ArithmeticOperator op, const DeviceSuperTable& l, const DeviceSuperTable& r, Context& ctx = Context::thread_default()) {
+    if (l.n_batches() != r.n_batches())
+        throw KernelError(MNR_ERR_SHAPE, "ShapeError", "SuperTable chunk count mismatch: " + std::to_string(l.n_batches()) + " vs " + std::to_string(r.n_batches()));
+    std::vector<detail::Leaf> leaves;
+    for (size_t b = 0; b < l.n_batches(); ++b) {
+        if (l.batches[b].n_cols() != r.batches[b].n_cols())
+            throw KernelError(MNR_ERR_SHAPE, "ShapeError", "Table column count mismatch: " + std::to_string(l.batches[b].n_cols()) + " vs " + std::to_string(r.batches[b].n_cols()));
+        for (size_t i = 0; i < l.batches[b].n_cols(); ++i) leaves.push_back({&l.batches[b].cols[i], &r.batches[b].cols[i], nullptr, nullptr});
+    }
+    std::vector<DeviceArray> res = detail::route_leaves(ctx, op, leaves, MNR_MASK_AND);
+    DeviceSuperTable out;
+    out.name = l.name;
+    size_t k = 0;
+    for (const auto& b : l.batches) {
+        DeviceTable t;
+        t.name = b.name;
+        for (size_t i = 0; i < b.n_cols(); ++i) t.cols.push_back(std::move(res[k++]));
+        out.batches.push_back(std::move(t));
+    }
+    return out;
+}
+
+// Per-column {sum, min, max, count} over all batches of a device-resident SuperTable (BASELINE configs[4]): every chunk of
+// every column in one batched call, folded per column in chunk order on the device.
+inline std::vector<mnr_agg> super_table_stats(const DeviceSuperTable& st, bool with_minmax = true, Context& ctx = Context::thread_default()) {
+    const size_t nc = st.n_cols();
+    std::vector<const mnr_buf*> b;
+    std::vector<const mnr_bits*> m;
+    std::vector<uint32_t> col;
+    std::vector<mnr_dtype> dts(nc);
+    for (size_t c = 0; c < nc; ++c)
+        for (const auto& t : st.batches) { b.push_back(t.cols[c].buf.get()); m.push_back(t.cols[c].mask.get()); col.push_back((uint32_t)c); dts[c] = t.cols[c].dtype(); }
+    std::vector<mnr_agg> out(nc);
+    check(mnr_reduce_stats_batch_exchange_sync(ctx.get(), nullptr, b.size(), b.data(), m.data(), with_minmax ? 1 : 0, nc, col.data(), dts.data(), out.data()));
+    return out;
+}
+
 }  // namespace minarrow_b200

@@ -189,6 +189,72 @@ int main(int argc, char** argv) {
             o = broadcast_super_table_to_scalar<int32_t>(Op::Add, l3, 100);
             CHECK(is<int32_t>(o.batches[2]->cols[1], {170, 180, 190}));
         }
+        {   // Array (op) SuperArray with re-chunking and the union mask (broadcast/mod.rs:1351-1361, utils.rs:367-481).  The
+            // reference has no test with null masks for these arms; expectations are the route's definition worked by hand:
+            // chunk i is valid where array_mask[window i] | chunk_mask[i]; a chunk WITHOUT a mask next to one with a mask is
+            // all valid in the union; with no chunk masks at all the array's window is used as is.
+            Bitmask am = Bitmask::from_bools({true, false, true, true, false, false, true});
+            Array arr = Array::from_slice<int32_t>({1, 2, 3, 4, 5, 6, 7}, &am);
+            Bitmask c0m = Bitmask::from_bools({false, false, true});
+            SuperArray sa = SuperArray::from_chunks({Array::from_slice<int32_t>({10, 20, 30}, &c0m), i32({40, 50, 60, 70})});
+            SuperArray o = broadcast_array_to_superarray(Op::Add, arr, sa);
+            CHECK(o.n_chunks() == 2 && is<int32_t>(o.chunks()[0], {11, 0, 33}) && is<int32_t>(o.chunks()[1], {44, 55, 66, 77}));
+            CHECK(o.chunks()[0].null_mask() && o.chunks()[0].null_mask()->to_bools() == std::vector<bool>({true, false, true}));
+            CHECK(o.chunks()[1].null_mask() && o.chunks()[1].null_mask()->count_ones() == 4);
+            o = broadcast_superarray_to_array(Op::Subtract, sa, arr);
+            CHECK(is<int32_t>(o.chunks()[0], {9, 0, 27}) && is<int32_t>(o.chunks()[1], {36, 45, 54, 63}));
+            SuperArray plain = SuperArray::from_chunks({i32({10, 20, 30}), i32({40, 50, 60, 70})});
+            o = broadcast_array_to_superarray(Op::Multiply, arr, plain);      // no chunk masks: the array's windows
+            CHECK(is<int32_t>(o.chunks()[0], {10, 0, 90}) && is<int32_t>(o.chunks()[1], {160, 0, 0, 490}));
+            CHECK(o.chunks()[1].null_mask() && o.chunks()[1].null_mask()->to_bools() == std::vector<bool>({true, false, false, true}));
+            o = broadcast_array_to_superarray(Op::Add, i32({1, 2, 3, 4, 5, 6, 7}), plain);   // no masks anywhere: dense
+            CHECK(is<int32_t>(o.chunks()[1], {44, 55, 66, 77}) && !o.chunks()[1].null_mask());
+            SuperArray al = create_aligned_chunks_from_array(arr, sa);
+            CHECK(al.shape_1d() == std::vector<size_t>({3, 4}) && is<int32_t>(al.chunks()[1], {4, 5, 6, 7}));
+            CHECK(al.chunks()[0].null_mask()->to_bools() == std::vector<bool>({true, false, true}) && al.chunks()[1].null_mask()->count_ones() == 4);
+            std::string msg;
+            CHECK(error_kind([&] { broadcast_array_to_superarray(Op::Add, i32({1, 2, 3}), sa); }, &msg) == "ShapeError" && msg.find("same total length") != std::string::npos);
+        }
+        {   // device-resident SuperTable: (A * B) + A chains in HBM, at most one launch per column dtype and operation
+            auto mk = [&](int k) {
+                IntegerArray<int32_t> a; FloatArray<double> b; IntegerArray<int64_t> c; FloatArray<float> d;
+                for (int i = 0; i < 2048; ++i) { a.data.push_back(i % 97 - 40 + k); b.data.push_back(0.5 * i - k); c.data.push_back((int64_t)i * 1000003 + k); d.data.push_back(0.25f * (float)(i % 31) + (float)k); }
+                return Table("b" + std::to_string(k), {Array(std::move(a)), Array(std::move(b)), Array(std::move(c)), Array(std::move(d))});
+            };
+            SuperTable ha = SuperTable::from_batches({mk(0), mk(1), mk(2), mk(3), mk(4)}, "A"), hb = SuperTable::from_batches({mk(7), mk(8), mk(9), mk(10), mk(11)}, "B");
+            DeviceSuperTable da = DeviceSuperTable::from_host(ctx, ha), db = DeviceSuperTable::from_host(ctx, hb);
+            ctx.synchronize();
+            const uint64_t l0 = ctx.launch_count();
+            DeviceSuperTable prod = broadcast_super_table_with_operator(Op::Multiply, da, db);
+            const uint64_t l1 = ctx.launch_count();
+            DeviceSuperTable res = broadcast_super_table_with_operator(Op::Add, prod, da);
+            const uint64_t l2 = ctx.launch_count();
+            CHECK(l1 - l0 <= 4 && l2 - l1 <= 4);
+            std::vector<mnr_agg> st = super_table_stats(res);
+            CHECK(ctx.launch_count() - l2 <= 4);
+            SuperTable out = res.to_host(ctx);
+            CHECK(out.name == "A" && out.n_batches() == 5 && out.batches[3]->name == "b3");
+            int64_t sum0 = 0; uint64_t sum2 = 0; bool same = true;
+            for (size_t k = 0; k < 5; ++k) {
+                const auto& A0 = *ha.batches[k]->cols[0].values<int32_t>(); const auto& B0 = *hb.batches[k]->cols[0].values<int32_t>();
+                const auto& A1 = *ha.batches[k]->cols[1].values<double>(); const auto& B1 = *hb.batches[k]->cols[1].values<double>();
+                const auto& A2 = *ha.batches[k]->cols[2].values<int64_t>(); const auto& B2 = *hb.batches[k]->cols[2].values<int64_t>();
+                for (size_t i = 0; i < 2048; ++i) {
+                    const int32_t e0 = (int32_t)((uint32_t)A0[i] * (uint32_t)B0[i] + (uint32_t)A0[i]);
+                    const double p1 = A1[i] * B1[i]; const double e1 = p1 + A1[i];
+                    const int64_t e2 = (int64_t)((uint64_t)A2[i] * (uint64_t)B2[i] + (uint64_t)A2[i]);
+                    same = same && (*out.batches[k]->cols[0].values<int32_t>())[i] == e0 && (*out.batches[k]->cols[1].values<double>())[i] == e1 &&
+                           (*out.batches[k]->cols[2].values<int64_t>())[i] == e2;
+                    sum0 += e0; sum2 += (uint64_t)e2;
+                }
+            }
+            CHECK(same);
+            CHECK(st.size() == 4 && st[0].sum.i64 == sum0 && st[0].count == 5 * 2048 && st[2].sum.u64 == sum2);
+            DeviceTable tv = da.batches[0].view(ctx, 100, 500);          // TableV window, still on the device
+            DeviceTable tw = broadcast_table_with_operator(Op::Subtract, tv, db.batches[0].view(ctx, 0, 500));
+            Table th = tw.to_host(ctx);
+            CHECK((*th.cols[0].values<int32_t>())[7] == (*ha.batches[0]->cols[0].values<int32_t>())[107] - (*hb.batches[0]->cols[0].values<int32_t>())[7]);
+        }
         std::printf("%d checks, %d failed, %llu kernel launches\n", g_checks, g_failed, (unsigned long long)ctx.launch_count());
     } catch (const std::exception& e) {
         std::printf("EXCEPTION %s\n", e.what());

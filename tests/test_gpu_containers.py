@@ -76,8 +76,8 @@ def test_array_superarray_rechunk_route_matches_oracle(gpu_ctx, oracle, dt, arra
         _same(g, ed, em, "create_aligned_chunks_from_array")
     # SuperArrayView arm (mod.rs:1362-1375): slices of a bigger array materialise to the same chunks
     big = _chunks(rng, dt, [sum(LENS) + 11], [True])[0]
-    sav = B.SuperArrayV([B.ArrayV(big, 5, 100), B.ArrayV(big, 300, sum(LENS) - 100)])
-    sub = [B._window(big, 5, 100), B._window(big, 300, sum(LENS) - 100)]
+    sav = B.SuperArrayV([B.ArrayV(big, 5, 100), B.ArrayV(big, 108, sum(LENS) - 100)])
+    sub = [B._window(big, 5, 100), B._window(big, 108, sum(LENS) - 100)]
     exp = oracle.broadcast_array_superarray(oracle.ADD, arr.data, am, _orc_chunks(oracle, sub), True)
     got = B.broadcast_value(A.Add, arr, sav, gpu_ctx)
     for g, (ed, em) in zip(got.chunks, exp):
