@@ -21,8 +21,10 @@ def main():
     from minarrow_b200 import sharded as sh
     from oracle import oracle as orc
     ctx = mnr.Context(local)
+    fx = sh.FusedExchange(ctx)                           # mailboxes over CUDA IPC, once
     rng = np.random.default_rng(123)                     # every rank builds the same SuperArray, uploads only its shard
     n_chunks, rows = 13, 250_007
+    table_cols, table_exp = [], []
     for dt in (np.int64, np.int32, np.uint64, np.float64, np.float32):
         chunks = []
         for _ in range(n_chunks):
@@ -32,10 +34,16 @@ def main():
                 d = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, rows, dtype=dt, endpoint=True)
             chunks.append(mnr.core.make_array(d, mnr.Bitmask.from_bools(rng.random(rows) < 0.9)))
         col = sh.ShardedColumn.from_host_chunks(ctx, chunks, rank, world)
-        got = col.stats(True)
         whole = np.concatenate([c.data for c in chunks])
         valid = np.concatenate([c.null_mask.to_bools() for c in chunks])
         exp = orc.stats(whole, orc.Bits.from_bools(valid))
+        table_cols.append(col)
+        table_exp.append((dt, whole, valid, exp))
+        # both finishes: the fused one (batched kernels + per-column fold + NVLink mailbox exchange, no NCCL) and the
+        # NCCL one (same kernels + on-device fold, one all-gather of 32 bytes per rank); they must agree bit for bit
+        got = col.stats(True, exchange=fx)
+        got_nccl = col.stats(True)
+        assert got == got_nccl or (got["sum"] != got["sum"]), (dt, got, got_nccl)
         assert got["count"] == exp["count"], (dt, got, exp)
         assert got["min"] == exp["min"] and got["max"] == exp["max"], (dt, got, exp)
         if np.dtype(dt).kind == "f":
@@ -57,6 +65,22 @@ def main():
             m = orc.Bits(chunks[i].null_mask.bits, rows)
             ed, em = orc.apply(chunks[i].data, chunks[i].data, orc.MUL, m)
             assert ob.download().tobytes() == ed.tobytes() and np.array_equal(om.download().bits, em.bits), (dt, i)
+    # the whole 5-column "SuperTable" in ONE exchange epoch (configs[4] shape): 5 aggregates per rank through the mailbox
+    for rep in range(3):
+        allg = sh.sharded_stats(table_cols, True, exchange=fx)
+    for got, (dt, whole, valid, exp) in zip(allg, table_exp):
+        assert (got["count"], got["min"], got["max"]) == (exp["count"], exp["min"], exp["max"]), (dt, got, exp)
+        if np.dtype(dt).kind == "f":
+            assert abs(got["sum"] - exp["sum"]) <= 1e-12 * np.abs(whole[valid].astype(np.float64)).sum(), (dt, got, exp)
+        else:
+            assert got["sum"] == exp["sum"], (dt, got, exp)
+    # fewer chunks than ranks: ranks that own nothing join the exchange with identity aggregates
+    few = [mnr.core.make_array(np.arange(1000, dtype=np.int64) + 7 * k, None) for k in range(max(1, world - 1))]
+    fcol = sh.ShardedColumn.from_host_chunks(ctx, few, rank, world)
+    g = fcol.stats(True, exchange=fx)
+    fw = np.concatenate([c.data for c in few])
+    assert (g["sum"], g["min"], g["max"], g["count"]) == (int(fw.sum()), int(fw.min()), int(fw.max()), fw.size), g
+    del table_cols, fcol
     # rebalance (multi-GPU rechunk): deliberately uneven shards -> even 64-row-aligned windows; rows move between GPUs
     # with one all-to-all of value bytes + one of validity bytes, stitched by the device consolidate
     for dt in (np.int64, np.int8, np.float32):
@@ -85,7 +109,6 @@ def main():
         assert after["sum"] == before["sum"] or np.dtype(dt).kind == "f"
     # fused reduction + exchange kernel (P2P mailboxes): every rank reduces its window of one big column and must end
     # with the oracle's aggregate of the WHOLE column, bit-identical on all ranks, over many back-to-back epochs.
-    fx = sh.FusedExchange(ctx)
     n = 3_000_017
     for dt in (np.int64, np.int32, np.float64, np.float32):
         if np.dtype(dt).kind == "f":
@@ -113,14 +136,21 @@ def main():
         g = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(g, t)
         assert all(int(x) == int(t) for x in g), "fused exchange: ranks disagree"
-        # asynchronous form, 200 epochs back to back without host synchronisation
+        # asynchronous form, 200 epochs back to back without host synchronisation — first serialised, then with
+        # consecutive reductions overlapped (programmatic dependent launch + late dependency wait, as bench.py runs it)
         outd = torch.zeros(4, dtype=torch.int64, device="cuda")
         torch.cuda.synchronize()
-        ctx.synchronize()
-        for _ in range(200):
-            fx.reduce_stats_async(B, V, False, outd.data_ptr())
-        ctx.synchronize()
-        assert int(outd[3]) == exp["count"]
+        for overlap in (0, 1):
+            ctx.set_option("reduce_overlap", overlap)
+            ctx.synchronize()
+            for k in range(200):
+                fx.reduce_stats_async(B, V, k % 3 == 0, outd.data_ptr())
+            ctx.synchronize()
+            assert int(outd[3]) == exp["count"], (dt, overlap)
+            if np.dtype(dt).kind != "f":
+                assert int(outd[0]) == exp["sum"], (dt, overlap)
+            assert not fx.status()
+        ctx.set_option("reduce_overlap", 0)
     fx.close()
     dist.barrier()
     if rank == 0:
