@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=1_000_000_000)
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="strong (default, BASELINE configs[1]): ONE --rows-row column sharded over the GPUs; weak: --rows rows per GPU")
+    ap.add_argument("--no-overlap", action="store_true", help="do not overlap consecutive reductions (reduce_overlap = 0)")
     ap.add_argument("--no-other-scaling", action="store_true", help="N > 1: skip the secondary measurement of the other scaling mode")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
@@ -692,7 +693,7 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = mnr.Context(local, stream=stream.cuda_stream)   # kernels launch on torch's current stream
-    ctx.set_option("reduce_overlap", 1)                   # the columns are at rest: consecutive reductions may overlap
+    ctx.set_option("reduce_overlap", 0 if args.no_overlap else 1)   # the columns are at rest: consecutive reductions may overlap
     peak, peak_src = peaks()
     strong = args.scaling == "strong"
 
@@ -742,15 +743,24 @@ def run_b200(args):
     for _ in range(W):
         step()
     barrier()
-    # Clocks: an untimed load phase of >= 150 ms right before the timed region gives the sampler something to see (the
-    # timed region itself can be a few ms at 8 GPUs); sampling continues through the timed region.
+    # Clocks: an untimed load phase of ~150 ms right before the timed region gives the sampler something to see (the timed
+    # region itself can be a few ms at 8 GPUs); sampling continues through the timed region.  The step is a collective:
+    # every rank must run the SAME number of load steps, so the count is fixed from a probe and agreed over the ranks.
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(8):
+        step()
+    p1.record()
+    p1.synchronize()
+    n_load = torch.tensor([max(8, min(4000, int(150.0 / max(p0.elapsed_time(p1) / 8, 1e-3))))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_load, op=dist.ReduceOp.MAX)
     clocks = ClockSampler(local)
+    barrier()
     clocks.start()
-    t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.15:
-        for _ in range(8):
-            step()
-        torch.cuda.synchronize()
+    for _ in range(int(n_load)):
+        step()
+    torch.cuda.synchronize()
     K = args.steps
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -767,8 +777,12 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total = float(tmax[0])
-    if fused and fx.status():
-        raise SystemExit("bench.py: the fused exchange timed out waiting for a peer")
+    if fused:   # agreed over the ranks: a rank that left alone would strand its peers in the next collective
+        bad = torch.tensor([1 if fx.status() else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad):
+            raise SystemExit("bench.py: the fused exchange timed out waiting for a peer")
 
     # result of the last step: per-GPU partials combined in rank order (integer sums wrap; order-free)
     parts = (total.view(1, 4) if fused else gathered if world > 1 else partial.view(1, 4)).cpu().numpy()
@@ -926,8 +940,8 @@ def run_b200(args):
             "config": {"workload": "configs[1]: 1B-row IntegerArray<i64> null-aware sum/avg, 10% nulls, ONE column sharded "
                                    "over the GPUs as a SuperArray (64-row-aligned windows)" if strong else
                                    "configs[1] shape, weak scaling: one 1B-row i64 shard per GPU",
-                       "exchange": ("fused kernel: reduce + P2P mailbox all-gather over NVLink + rank-order combine, consecutive "
-                                    "reductions overlapped by programmatic dependent launch" if fused
+                       "exchange": (("fused kernel: reduce + P2P mailbox all-gather over NVLink + rank-order combine" +
+                                     ("" if args.no_overlap else ", consecutive reductions overlapped by programmatic dependent launch")) if fused
                                     else ("NCCL all-gather of 32-byte partials" + (f" (fused exchange unavailable: {fused_note})" if fused_note else ""))),
                        "api": "minarrow_b200.sharded.FusedExchange.reduce_stats_async -> mnr_reduce_stats_exchange (C ABI)",
                        "rows_per_gpu": rows, "total_rows": total_rows, "bytes_per_row": BYTES_PER_ROW,

@@ -159,7 +159,10 @@ void mnr_bits_free(mnr_bits* bits);
  * `mode` matters only when both masks are given.  lhs/rhs must share dtype and length. */
 int mnr_ew_binary(mnr_ctx* ctx, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lhs_mask,
                   const mnr_bits* rhs_mask, mnr_mask_mode mode, mnr_buf** out, mnr_bits** out_mask);
-/* Same, into caller-provided outputs (out_mask required iff a mask is given). */
+/* Same, into caller-provided outputs (out_mask required iff a mask is given).  For every *_into entry point: an
+ * output (values or mask) must not overlap any input of the same call — the kernels read inputs through the read-only
+ * path — and an overlapping call is refused with MNR_ERR_INVALID_ARGUMENTS.  In-place `x = x op y` therefore takes a
+ * fresh output (the allocating forms draw from a stream-ordered pool: no cudaMalloc per call). */
 int mnr_ew_binary_into(mnr_ctx* ctx, mnr_op op, const mnr_buf* lhs, const mnr_buf* rhs, const mnr_bits* lhs_mask,
                        const mnr_bits* rhs_mask, mnr_mask_mode mode, mnr_buf* out, mnr_bits* out_mask);
 /* Scalar broadcast without materialising the length-1 operand (replaces broadcast_length_1_array +

@@ -249,6 +249,10 @@ inline Bitmask binop(Context& ctx, LogicalOperator op, BitmaskVT l, BitmaskVT r)
     const auto& [lm, lo, ll] = l;
     const auto& [rm, ro, rl] = r;
     if (ll != rl) throw KernelError(MNR_ERR_LENGTH_MISMATCH, "LengthMismatch", "bitmask_binop: window lengths differ");
+    // raw host pointers cross the C ABI below: the windows must lie inside their masks' own storage (the reference would
+    // panic on the slice, bitmask/mod.rs:124-139)
+    auto inside = [](const Bitmask& m, size_t off, size_t len) { return len == 0 || (off / 8 + (len + 7) / 8 <= m.bits.size() && off + len <= m.bits.size() * 8); };
+    if (!inside(lm, lo, ll) || !inside(rm, ro, rl)) throw KernelError(MNR_ERR_OUT_OF_BOUNDS, "OutOfBounds", "bitmask_binop: window leaves the mask");
     Bitmask out = Bitmask::new_set_all(ll, false);
     check(mnr_bitmask_binop_host(ctx.get(), static_cast<mnr_logical_op>(op), lm.bits.data(), lo, rm.bits.data(), ro, ll, out.bits.data()));
     return out;

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <limits>
 #include <string>
 #include <algorithm>
@@ -367,6 +368,33 @@ static int run_ew(mnr_ctx* c, EwArgs& a, cudaStream_t s, bool promote, mnr_dtype
     return MNR_OK;
 }
 
+// The kernels read their inputs through the read-only (non-coherent) path and declare every pointer __restrict__: an
+// output that overlaps an input is undefined behaviour, so the *_into entry points refuse it (in-place `x = x op y` needs
+// a fresh output; the stream-ordered pool makes that allocation cheap).
+static bool overlaps(const void* a, size_t abytes, const void* b, size_t bbytes) {
+    if (!a || !b || !abytes || !bbytes) return false;
+    const uintptr_t pa = reinterpret_cast<uintptr_t>(a), pb = reinterpret_cast<uintptr_t>(b);
+    return pa < pb + bbytes && pb < pa + abytes;
+}
+static int check_no_alias(const mnr_buf* out, const mnr_bits* out_mask, std::initializer_list<const mnr_buf*> ins,
+                          std::initializer_list<const mnr_bits*> in_masks) {
+    const size_t ob = out ? out->len * dtype_size(out->dtype) : 0, omb = out_mask ? mask_bytes(out_mask->len) : 0;
+    for (const mnr_buf* b : ins) {
+        if (!b) continue;
+        const size_t bb = b->len * dtype_size(b->dtype);
+        REQUIRE(!(out && overlaps(out->ptr, ob, b->ptr, bb)) && !(out_mask && overlaps(out_mask->ptr, omb, b->ptr, bb)),
+                MNR_ERR_INVALID_ARGUMENTS, "an output overlaps an input buffer (in-place operation is not supported: pass a fresh output)");
+    }
+    for (const mnr_bits* m : in_masks) {
+        if (!m) continue;
+        const size_t mb = mask_bytes(m->len);
+        REQUIRE(!(out && overlaps(out->ptr, ob, m->ptr, mb)) && !(out_mask && overlaps(out_mask->ptr, omb, m->ptr, mb)),
+                MNR_ERR_INVALID_ARGUMENTS, "an output overlaps an input mask (in-place operation is not supported: pass a fresh output)");
+    }
+    REQUIRE(!(out && out_mask && overlaps(out->ptr, ob, out_mask->ptr, omb)), MNR_ERR_INVALID_ARGUMENTS, "output values and output mask overlap");
+    return MNR_OK;
+}
+
 static int check_masks(const mnr_bits* lm, const mnr_bits* rm, size_t n) {
     REQUIRE(!lm || lm->len >= n, MNR_ERR_INVALID_ARGUMENTS, "lhs mask has %zu bits, need %zu", lm->len, n);
     REQUIRE(!rm || rm->len >= n, MNR_ERR_INVALID_ARGUMENTS, "rhs mask has %zu bits, need %zu", rm->len, n);
@@ -387,6 +415,8 @@ int mnr_ew_binary_into(mnr_ctx* c, mnr_op op, const mnr_buf* lhs, const mnr_buf*
     REQUIRE(!masked || (out_mask && out_mask->len == lhs->len), MNR_ERR_INVALID_ARGUMENTS,
             "masked call needs an output mask of %zu bits", lhs->len);
     int rc = check_masks(lm, rm, lhs->len);
+    if (rc) return rc;
+    rc = check_no_alias(out, masked ? out_mask : nullptr, {lhs, rhs}, {lm, rm});
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     EwArgs a{};
@@ -431,6 +461,8 @@ int mnr_ew_scalar_into(mnr_ctx* c, mnr_op op, const mnr_buf* arr, const void* sc
             "masked call needs an output mask of %zu bits", arr->len);
     int rc = check_masks(mask, nullptr, arr->len);
     if (rc) return rc;
+    rc = check_no_alias(out, mask ? out_mask : nullptr, {arr}, {mask});
+    if (rc) return rc;
     CU(cudaSetDevice(c->device));
     EwArgs a{};
     a.dtype = arr->dtype; a.op = op;
@@ -461,6 +493,8 @@ int mnr_ew_fma_into(mnr_ctx* c, const mnr_buf* a, const mnr_buf* b, const mnr_bu
     REQUIRE(!mask || (out_mask && out_mask->len == a->len), MNR_ERR_INVALID_ARGUMENTS,
             "masked call needs an output mask of %zu bits", a->len);
     int rc = check_masks(mask, nullptr, a->len);
+    if (rc) return rc;
+    rc = check_no_alias(out, mask ? out_mask : nullptr, {a, b, acc}, {mask});
     if (rc) return rc;
     if (a->len == 0) return MNR_OK;
     CU(cudaSetDevice(c->device));
@@ -594,6 +628,8 @@ int mnr_ew_binary_batch_into(mnr_ctx* c, mnr_op op, size_t n, const mnr_buf* con
         REQUIRE(!masked || (om && om->len == l->len), MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: masked call needs an output mask of %zu bits", i, l->len);
         int rc = check_masks(lm, rm, l->len);
         if (rc) return rc;
+        rc = check_no_alias(out[i], masked ? om : nullptr, {l, r}, {lm, rm});   // chunk i's outputs against chunk i's inputs
+        if (rc) return rc;
         EwArgs& a = items[i];
         a = EwArgs{};
         a.dtype = l->dtype; a.op = op; a.lhs = l->ptr; a.rhs = r->ptr;
@@ -616,6 +652,8 @@ int mnr_ew_scalar_batch_into(mnr_ctx* c, mnr_op op, size_t n, const mnr_buf* con
         REQUIRE(out[i]->dtype == arr->dtype && out[i]->len == arr->len, MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: output shape/dtype mismatch", i);
         REQUIRE(!m || (om && om->len == arr->len), MNR_ERR_INVALID_ARGUMENTS, "chunk %zu: masked call needs an output mask of %zu bits", i, arr->len);
         int rc = check_masks(m, nullptr, arr->len);
+        if (rc) return rc;
+        rc = check_no_alias(out[i], m ? om : nullptr, {arr}, {m});
         if (rc) return rc;
         EwArgs& a = items[i];
         a = EwArgs{};
@@ -666,6 +704,8 @@ int mnr_bits_binop_into(mnr_ctx* c, mnr_logical_op op, const mnr_bits* lhs, size
     if (rc) return rc;
     rc = check_window(rhs, rp, len, "bitmask_binop rhs");
     if (rc) return rc;
+    rc = check_no_alias(nullptr, out, {}, {lhs, rhs});
+    if (rc) return rc;
     if (len == 0) return MNR_OK;
     CU(cudaSetDevice(c->device));
     CU(launch_bits_op((int)op, lhs->ptr, lp, lhs->len, rhs->ptr, rp, rhs->len, len, out->ptr, c->stream));
@@ -689,6 +729,8 @@ int mnr_bits_not_into(mnr_ctx* c, const mnr_bits* src, size_t off, size_t len, m
     REQUIRE(out->len == len, MNR_ERR_INVALID_ARGUMENTS, "output mask has %zu bits, need %zu", out->len, len);
     const uint64_t sp = (uint64_t)(off / 8) * 8;
     int rc = check_window(src, sp, len, "bitmask_unop");
+    if (rc) return rc;
+    rc = check_no_alias(nullptr, out, {}, {src});
     if (rc) return rc;
     if (len == 0) return MNR_OK;
     CU(cudaSetDevice(c->device));
@@ -831,7 +873,9 @@ int mnr_bits_in(mnr_ctx* c, const mnr_bits* lhs, size_t lo, const mnr_bits* rhs,
     mnr_bits* r = nullptr;
     if (has_true && has_false) rc = mnr_bits_new_set_all(c, len, 1, &r);
     else if (has_true) {   // lhs.slice_clone(lhs_off, len): exact bit offset (bitmask.rs:604-626)
-        rc = check_window(lhs, lo, len, "in_mask lhs");
+        // exact bit offset here (not floored): the window must end inside the mask bit-exactly
+        rc = (lo <= lhs->len && len <= lhs->len - lo) ? MNR_OK
+                 : fail(MNR_ERR_OUT_OF_BOUNDS, "in_mask lhs: window [%zu, +%zu) leaves the %zu-bit mask", lo, len, lhs->len);
         if (!rc) rc = mnr_bits_alloc(c, len, &r);
         if (!rc) {
             CU(launch_bits_op(5, lhs->ptr, lo, lhs->len, nullptr, 0, 0, len, r->ptr, c->stream));

@@ -64,6 +64,9 @@ int upload_bits_window(mnr_ctx* c, const uint8_t* host, int64_t bit_offset, int6
     if (rc || len == 0) return rc;
     const size_t first = (size_t)bit_offset >> 3, shift = (size_t)bit_offset & 7;
     const size_t nbytes = (shift + (size_t)len + 7) >> 3;
+    void* tmp = nullptr;
+    const char* err = nullptr;
+    int code = MNR_ERR_CUDA;
     if (shift == 0) {
         // byte-aligned window: plain copy; the slack bits of the last byte (Bitmask::mask_trailing_bits, bitmask.rs:83-90) are
         // cleared on the host copy of that one byte — a foreign producer may leave anything there
@@ -73,18 +76,25 @@ int upload_bits_window(mnr_ctx* c, const uint8_t* host, int64_t bit_offset, int6
         bool ok = true;
         if (nb > 1) ok &= cudaMemcpyAsync((*out)->ptr, host + first, nb - 1, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
         ok &= cudaMemcpyAsync((*out)->ptr + nb - 1, &last, 1, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
-        if (!ok) AFAIL(MNR_ERR_CUDA, "arrow import: validity upload failed");
+        if (!ok) err = "arrow import: validity upload failed";
+    } else if (cudaMallocAsync(&tmp, nbytes + 16, c->stream) != cudaSuccess) {
+        tmp = nullptr;
+        code = MNR_ERR_OUT_OF_MEMORY;
+        err = "arrow import: staging allocation failed";
+    } else if (cudaMemcpyAsync(tmp, host + first, nbytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+        err = "arrow import: validity upload failed";
+    } else if (launch_bits_op(5, static_cast<const uint8_t*>(tmp), shift, nbytes * 8, nullptr, 0, 0, (uint64_t)len, (*out)->ptr, c->stream) != cudaSuccess) {
+        err = "arrow import: bit shift failed";
     } else {
-        void* tmp = nullptr;
-        if (cudaMallocAsync(&tmp, nbytes + 16, c->stream) != cudaSuccess) AFAIL(MNR_ERR_OUT_OF_MEMORY, "arrow import: staging allocation failed");
-        if (cudaMemcpyAsync(tmp, host + first, nbytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
-            AFAIL(MNR_ERR_CUDA, "arrow import: validity upload failed");
-        if (launch_bits_op(5, static_cast<const uint8_t*>(tmp), shift, nbytes * 8, nullptr, 0, 0, (uint64_t)len, (*out)->ptr, c->stream) != cudaSuccess)
-            AFAIL(MNR_ERR_CUDA, "arrow import: bit shift failed");
         c->launches++;
-        cudaFreeAsync(tmp, c->stream);
     }
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) AFAIL(MNR_ERR_CUDA, "arrow import: synchronize failed");
+    if (tmp) cudaFreeAsync(tmp, c->stream);
+    if (!err && cudaStreamSynchronize(c->stream) != cudaSuccess) err = "arrow import: synchronize failed";
+    if (err) {   // nothing leaks on a failure path: the staging buffer above, the fresh mask here
+        mnr_bits_free(*out);
+        *out = nullptr;
+        AFAIL(code, err);
+    }
     return MNR_OK;
 }
 
@@ -142,8 +152,11 @@ static int export_common(mnr_ctx* c, const char* fmt, size_t len, const void* de
     ok &= cudaStreamSynchronize(c->stream) == cudaSuccess;
     if (!ok) { free(p->values); free(p->validity); delete p; AFAIL(MNR_ERR_CUDA, "arrow export: download failed"); }
     if (validity && len) {
+        // `validity` may be longer than the values (a wrapped mask, or one taken before a slice): bits past `len` in the
+        // last byte are not part of this array — clear them in the exported bitmap and keep them out of null_count
+        uint8_t* vb = static_cast<uint8_t*>(p->validity);
+        if (len & 7) vb[(len - 1) >> 3] &= (uint8_t)((1u << (len & 7)) - 1u);
         ones = 0;
-        const uint8_t* vb = static_cast<const uint8_t*>(p->validity);
         for (size_t i = 0; i < (len + 7) / 8; ++i) ones += (uint64_t)__builtin_popcount(vb[i]);
     }
     p->buffers[0] = p->validity;

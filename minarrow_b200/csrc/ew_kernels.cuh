@@ -179,6 +179,108 @@ __device__ __forceinline__ void packed_cheap_vec(const uint32_t (&a)[NW], bool h
     }
 }
 
+// ---- 8/16-bit integer Div / Rem / FloorDiv of two columns, SIMD-in-register --------------------------------------------
+// The per-element path costs ~35 instructions per row (ncu r01zz: ALU pipe 72 %, issue slots 70 %): a byte extract and a
+// sign extension per operand, the quotient, `q * r`, three selects for the operator, the zero-divisor test, the validity
+// select, the validity bit and a byte insert.  Only the quotient has to be per row.  Here a 32-bit word (4 or 2 lanes) is
+// the unit for everything else:
+//   * signed lanes become magnitudes with one packed subtract ((x ^ s) - s, s = 0xFF.. in negative lanes); |MIN| stays
+//     0x80.. and is read as the unsigned 2^(bits-1), so MIN / -1 comes out as 2^(bits-1) = MIN after the sign is restored
+//     (the wrapped quotient every other width produces);
+//   * one PRMT per operand both extracts lane k and plants it in the mantissa of 2^23 (the exponent constant is PRMT's second
+//     source), one FADD removes the bias: the exact float |l| + 0.5 or |r|.  MUFU.RCP, FMUL and FADD.RZ(2^23) then leave
+//     floor(|l| / |r|) in the low mantissa bits — bit for bit the arithmetic of narrow_quot<false>, whose exactness is
+//     enumerated over all 2^32 (dividend, divisor) pairs of u16 (tests/sweep_div16.py).  A zero divisor gives Inf -> bits 0;
+//   * the quotient lanes are packed back with 0.75 PRMT per lane; remainder = |l| - q * |r| with the packed multiply of
+//     packed_cheap_word; signs are restored per word (quotient: sign(l) ^ sign(r); remainder: sign(l); FloorDiv: q - 1 where
+//     the remainder is non-zero and the signs differ, std.rs:72-75);
+//   * zero divisors and input validity are lane masks; the output word is ANDed once and the output validity bits are
+//     squeezed out of the mask with one multiply.
+// ~10 (unsigned Div) to ~15 (signed Rem / FloorDiv) instructions per row.
+template <int ESZ> __device__ __forceinline__ uint32_t lane_neg_mask(uint32_t x) {
+    if constexpr (ESZ == 1) return ((x >> 7) & 0x01010101u) * 0xFFu;
+    else return ((x >> 15) & 0x00010001u) * 0xFFFFu;
+}
+template <int ESZ> __device__ __forceinline__ uint32_t lane_nonzero_mask(uint32_t x) {   // 0xFF.. in lanes that are != 0
+    if constexpr (ESZ == 1) return (((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7) & 0x01010101u) * 0xFFu;
+    else return (((((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) >> 15) & 0x00010001u) * 0xFFFFu;
+}
+template <int ESZ> __device__ __forceinline__ uint32_t lane_sub(uint32_t a, uint32_t b) {
+    if constexpr (ESZ == 1) return __vsub4(a, b);
+    else return __vsub2(a, b);
+}
+// lane k of `w` as the float bits of 2^23 + lane (PRMT with the exponent constant as second source)
+template <int ESZ, int K> __device__ __forceinline__ float lane_biased(uint32_t w) {
+    constexpr uint32_t sel = ESZ == 1 ? (0x7540u | (uint32_t)K) : (K == 0 ? 0x7510u : 0x7532u);
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel));
+}
+template <int ESZ> __device__ __forceinline__ uint32_t lane_valid_to_bits(uint32_t m) {   // lane mask -> EPW validity bits
+    if constexpr (ESZ == 1) return ((m & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
+    else { const uint32_t x = m & 0x00010001u; return (x | (x >> 15)) & 3u; }
+}
+
+// One 32-bit word of lanes.  `vm` (in/out): lanes that are valid on input -> lanes valid on output (zero divisors removed).
+template <int ESZ, bool SIGNED, int OP>
+__device__ __forceinline__ uint32_t packed_div_word(uint32_t lw, uint32_t rw, uint32_t& vm) {
+    constexpr int EPW = 4 / ESZ;
+    uint32_t sl = 0, sq = 0, la = lw, ra = rw;
+    if constexpr (SIGNED) {
+        sl = lane_neg_mask<ESZ>(lw);
+        const uint32_t sr = lane_neg_mask<ESZ>(rw);
+        sq = sl ^ sr;
+        la = lane_sub<ESZ>(lw ^ sl, sl);
+        ra = lane_sub<ESZ>(rw ^ sr, sr);
+    }
+    uint32_t t[EPW];
+#pragma unroll
+    for (int k = 0; k < EPW; ++k) {
+        float fa, fb;
+        if (k == 0) { fa = lane_biased<ESZ, 0>(la); fb = lane_biased<ESZ, 0>(ra); }
+        else if (k == 1) { fa = lane_biased<ESZ, 1>(la); fb = lane_biased<ESZ, 1>(ra); }
+        else if (k == 2) { fa = lane_biased<ESZ, (EPW > 2 ? 2 : 0)>(la); fb = lane_biased<ESZ, (EPW > 2 ? 2 : 0)>(ra); }
+        else { fa = lane_biased<ESZ, (EPW > 2 ? 3 : 0)>(la); fb = lane_biased<ESZ, (EPW > 2 ? 3 : 0)>(ra); }
+        fa = __fsub_rn(fa, 8388607.5f);   // |l| + 0.5, exact
+        fb = __fsub_rn(fb, 8388608.0f);   // |r|, exact
+        float rc;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fb));
+        t[k] = __float_as_uint(__fadd_rz(__fmul_rn(fa, rc), 8388608.0f));
+    }
+    uint32_t uq;
+    if constexpr (ESZ == 1) uq = __byte_perm(__byte_perm(t[0], t[1], 0x0040), __byte_perm(t[2], t[3], 0x0040), 0x5410);
+    else uq = __byte_perm(t[0], t[1], 0x5410);
+    vm &= lane_nonzero_mask<ESZ>(rw);
+    if constexpr (OP == MNR_DIV && !SIGNED) return uq;
+    if constexpr (OP == MNR_FLOORDIV && !SIGNED) return uq;
+    if constexpr (OP == MNR_DIV) return lane_sub<ESZ>(uq ^ sq, sq);
+    const uint32_t um = lane_sub<ESZ>(la, packed_cheap_word<ESZ, MNR_MUL>(uq, ra));   // |l| - q |r|
+    if constexpr (OP == MNR_REM) return SIGNED ? lane_sub<ESZ>(um ^ sl, sl) : um;
+    // FloorDiv, signed: truncated quotient, minus one where the remainder is non-zero and the signs differ
+    const uint32_t q = lane_sub<ESZ>(uq ^ sq, sq);
+    const uint32_t adj = lane_nonzero_mask<ESZ>(um) & sq & (ESZ == 1 ? 0x01010101u : 0x00010001u);
+    return lane_sub<ESZ>(q, adj);
+}
+
+// One vector (NW words); returns the output validity bits of its lanes (MASKED) / whether a zero divisor was met (dense).
+template <int ESZ, bool SIGNED, int OP, bool MASKED, int NW>
+__device__ __forceinline__ uint32_t packed_div_vec(const uint32_t (&a)[NW], bool has_a, const uint32_t (&b)[NW], bool has_b, uint32_t sword,
+                                                   uint32_t bits, uint32_t (&o)[NW]) {
+    constexpr int EPW = 4 / ESZ;
+    uint32_t even = 0, odd = 0, ob = 0;
+    if constexpr (MASKED && ESZ == 1) { even = bits & 0x0F0F0F0Fu; odd = (bits >> 4) & 0x0F0F0F0Fu; }
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        uint32_t vm = 0xFFFFFFFFu;
+        if constexpr (MASKED) {
+            if constexpr (ESZ == 1) vm = ((__byte_perm((j & 1) ? odd : even, 0u, 0x4440u | (uint32_t)(j >> 1)) * 0x00204081u) & 0x01010101u) * 0xFFu;
+            else vm = expand_valid_word<ESZ>(bits >> (j * EPW));
+        }
+        const uint32_t r = packed_div_word<ESZ, SIGNED, OP>(has_a ? a[j] : sword, has_b ? b[j] : sword, vm);
+        if constexpr (MASKED) { o[j] = r & vm; ob |= lane_valid_to_bits<ESZ>(vm) << (j * EPW); }
+        else { o[j] = r; ob |= ~vm; }   // dense: any zero divisor raises the flag (the reference panics)
+    }
+    return ob;
+}
+
 template <typename T, int CLS>
 __device__ __forceinline__ T elem(int op, T l, T r, bool& ok, const DivMagic& dm) {
     if constexpr (Traits<T>::is_float) { ok = true; return float_elem<T, CLS>(op, l, r); }
@@ -298,6 +400,9 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
     // and the packed one is slower, 5.5 TB/s, because expanding 2 validity bits costs as much as the two selects it saves.)
     constexpr bool PACKED = CLS == CLS_CHEAP && !Traits<T>::is_float && sizeof(T) == 1 && std::is_same<TL, T>::value &&
                             std::is_same<TR, T>::value && sizeof(VecT) >= 16;
+    // ... and the division family of 8/16-bit columns (packed_div_vec above).
+    constexpr bool PACKED_DIV = CLS == CLS_DIV && !Traits<T>::is_float && sizeof(T) <= 2 && std::is_same<TL, T>::value &&
+                                std::is_same<TR, T>::value && sizeof(VecT) >= 16;
     const uint32_t sword = sizeof(T) == 1 ? (uint32_t)(uint8_t)a.scalar_bits * 0x01010101u : (uint32_t)(uint16_t)a.scalar_bits * 0x00010001u;
     const DivMagic dm = a.magic;
     bool div0 = false;
@@ -333,6 +438,22 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
                 else packed_cheap_vec<sizeof(T), MNR_MUL, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
                 O.v = PO.v;
                 if constexpr (MASKED) ob = mb[u];
+            } else if constexpr (PACKED_DIV) {
+                constexpr int NW = sizeof(VecT) / 4;
+                constexpr int ESZ = sizeof(T) <= 2 ? (int)sizeof(T) : 1;
+                constexpr bool SG = Traits<T>::is_signed;
+                union { VecT v; uint32_t w[NW]; } PL, PR, PO;
+                memcpy(&PL.v, &L[u].v, sizeof(VecT));
+                memcpy(&PR.v, &R[u].v, sizeof(VecT));
+                const bool ha = lp != nullptr, hb = rp != nullptr;
+                const uint32_t vb = MASKED ? mb[u] : 0u;
+                uint32_t r;
+                if (op == MNR_DIV) r = packed_div_vec<ESZ, SG, MNR_DIV, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
+                else if (op == MNR_REM) r = packed_div_vec<ESZ, SG, MNR_REM, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
+                else r = packed_div_vec<ESZ, SG, MNR_FLOORDIV, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
+                O.v = PO.v;
+                if constexpr (MASKED) ob = r;
+                else div0 |= r != 0;
             } else
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {

@@ -10,10 +10,10 @@ from test_gpu_parity import same_float
 pytestmark = pytest.mark.gpu
 
 
-def _same(got, exp, op=None):
+def _same(got, exp, op=None, a=None, b=None):
     """Bit-exact (NaN by position) except float Power, which has the reference's own tolerance (tests/test_gpu_parity.py)."""
     if exp.dtype.kind == "f":
-        return same_float(got, exp, orc.POW if op == "pow" else orc.DIV, exp.dtype.type)
+        return same_float(got, exp, orc.POW if op == "pow" else orc.DIV, exp.dtype.type, a, b)
     return got.tobytes() == exp.tobytes()
 
 
@@ -76,14 +76,14 @@ def test_every_geometry_matches_the_oracle(gpu_ctx, knob, values, dtypes, ops):
                     rhs, R = (e, E) if op == "pow" else (b, B)
                     exp, em = apply(lhs, rhs, code[op], orc.Bits(V.bits, n))
                     ob, om = dev.ew_binary(gpu_ctx, code[op], L, R, DV, None, mnr.MaskMode.And)
-                    assert _same(ob.download(), exp, op) and np.array_equal(om.download().bits, em.bits), (knob, v, dt, op, "masked")
+                    assert _same(ob.download(), exp, op, lhs, rhs) and np.array_equal(om.download().bits, em.bits), (knob, v, dt, op, "masked")
                     # dense (non-zero divisors for the integer kernels: a zero there is DivideByZero) + an unaligned window
                     rhs2, R2 = (e, E) if op == "pow" else ((b, B) if is_f else (bnz, BNZ))
                     exp, _ = apply(lhs, rhs2, code[op], None)
                     ob, om = dev.ew_binary(gpu_ctx, code[op], L, R2, None, None, mnr.MaskMode.And)
-                    assert om is None and _same(ob.download(), exp, op), (knob, v, dt, op, "dense")
+                    assert om is None and _same(ob.download(), exp, op, lhs, rhs2), (knob, v, dt, op, "dense")
                     exp, _ = apply(lhs[3:n - 2], rhs2[3:n - 2], code[op], None)
                     ob, _ = dev.ew_binary(gpu_ctx, code[op], L.slice(3, n - 5), R2.slice(3, n - 5), None, None, mnr.MaskMode.And)
-                    assert _same(ob.download(), exp, op), (knob, v, dt, op, "unaligned")
+                    assert _same(ob.download(), exp, op, lhs[3:n - 2], rhs2[3:n - 2]), (knob, v, dt, op, "unaligned")
     finally:
         gpu_ctx.set_option(knob, 0)

@@ -1,7 +1,7 @@
 """Tuning experiment: launch geometry of the heavy element-wise classes — integer Div / Rem / FloorDiv of two columns,
 float Rem, Power — (ctx option ew_heavy_cfg: 1 = CfgHeavy 256 thr x 2 x 128-bit <= 64 regs resident; 2 = 128 thr x 2 x
 256-bit <= 85 regs covering; 3 = 256 thr x 2 x 256-bit <= 85 regs resident; 0 = the library's choice.  The r01zz run
-still numbered CfgHeavy 0).  Usage: python tools/heavy_exp.py"""
+still numbered CfgHeavy 0).  Usage: python tools/heavy_exp.py [dtype,dtype,...]"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 import minarrow_b200 as mnr
@@ -10,7 +10,8 @@ dev = torch.device("cuda:0"); ctx = mnr.Context(0, torch.cuda.current_stream().c
 A = mnr.ArithmeticOperator
 g = torch.Generator(device=dev); g.manual_seed(1)
 carrier = {1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}
-for name in ("int8", "int16", "uint16", "int32", "uint32", "int64", "uint64", "float32", "float64"):
+NAMES = sys.argv[1].split(",") if len(sys.argv) > 1 else ("int8", "uint8", "int16", "uint16", "int32", "uint32", "int64", "uint64", "float32", "float64")
+for name in NAMES:
     nd = np.dtype(name); sz = nd.itemsize
     n = (1 << 30) // sz
     if nd.kind == "f":
