@@ -281,6 +281,52 @@ __device__ __forceinline__ uint32_t packed_div_vec(const uint32_t (&a)[NW], bool
     return ob;
 }
 
+// ---- 8-bit integer Power through a shared-memory table ---------------------------------------------------------------------
+// base^e mod 256 by repeated squaring is ~35 instructions per row for general exponents (and data-dependent).  In Z/256 the
+// whole function is tiny: an ODD base has multiplicative order dividing 64, so b^e = b^(e mod 64); an EVEN base gives 0 as
+// soon as e >= 8 (2^8 | b^8).  Table: 128 half-bases x (64 odd-exponent entries + 16 even-exponent entries) = 10 KB of
+// shared memory, built by the block once (resident grid), then ONE byte load per row.  Signed columns use the same bits
+// (wrapping multiply); a negative exponent is `rhs.to_u32().unwrap_or(0)` = 0 (std.rs:67) -> 1.
+constexpr int kPowLutRow = 80;   // per half-base: [0, 64) odd base, exponent mod 64; [64, 80) even base, exponent min(e, 8) (+ padding)
+__device__ __forceinline__ uint32_t pow8_mod256(uint32_t b, uint32_t e) {
+    uint32_t acc = 1;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {   // e < 64
+        if (e & 1u) acc = (acc * b) & 0xFFu;
+        b = (b * b) & 0xFFu;
+        e >>= 1;
+    }
+    return acc;
+}
+template <int BLOCK> __device__ __forceinline__ void build_pow8_lut(uint8_t* lut) {
+    for (int i = threadIdx.x; i < 128 * kPowLutRow; i += BLOCK) {
+        const uint32_t x = (uint32_t)i / kPowLutRow, t = (uint32_t)i % kPowLutRow;
+        lut[i] = t < 64 ? (uint8_t)pow8_mod256(2 * x + 1, t) : (uint8_t)((t - 64) >= 8 ? 0u : pow8_mod256(2 * x, t - 64));
+    }
+    __syncthreads();
+}
+template <bool SIGNED, bool MASKED, int NW>
+__device__ __forceinline__ void packed_pow8_vec(const uint8_t* __restrict__ lut, const uint32_t (&a)[NW], bool has_a, const uint32_t (&b)[NW], bool has_b,
+                                                uint32_t sword, uint32_t bits, uint32_t (&o)[NW]) {
+    uint32_t even = 0, odd = 0;
+    if constexpr (MASKED) { even = bits & 0x0F0F0F0Fu; odd = (bits >> 4) & 0x0F0F0F0Fu; }
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        const uint32_t lw = has_a ? a[j] : sword;
+        uint32_t ew = has_b ? b[j] : sword;
+        if constexpr (SIGNED) ew &= ~lane_neg_mask<1>(ew);                       // negative exponent -> 0
+        const uint32_t oddm = (lw & 0x01010101u) * 0xFFu;                         // lanes with an odd base
+        const uint32_t tw = ((ew & 0x3F3F3F3Fu) & oddm) | ((0x40404040u + __vminu4(ew, 0x08080808u)) & ~oddm);
+        const uint32_t xw = (lw >> 1) & 0x7F7F7F7Fu;                              // half-base
+        uint32_t r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = lut[((xw >> (8 * k)) & 0xFFu) * kPowLutRow + ((tw >> (8 * k)) & 0xFFu)];
+        uint32_t w = __byte_perm(__byte_perm(r[0], r[1], 0x0040), __byte_perm(r[2], r[3], 0x0040), 0x5410);
+        if constexpr (MASKED) w &= ((__byte_perm((j & 1) ? odd : even, 0u, 0x4440u | (uint32_t)(j >> 1)) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        o[j] = w;
+    }
+}
+
 template <typename T, int CLS>
 __device__ __forceinline__ T elem(int op, T l, T r, bool& ok, const DivMagic& dm) {
     if constexpr (Traits<T>::is_float) { ok = true; return float_elem<T, CLS>(op, l, r); }
@@ -403,6 +449,11 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
     // ... and the division family of 8/16-bit columns (packed_div_vec above).
     constexpr bool PACKED_DIV = CLS == CLS_DIV && !Traits<T>::is_float && sizeof(T) <= 2 && std::is_same<TL, T>::value &&
                                 std::is_same<TR, T>::value && sizeof(VecT) >= 16;
+    // ... and Power of 1-byte columns (packed_pow8_vec above: one shared-memory table lookup per row).
+    constexpr bool PACKED_POW = CLS == CLS_POW && !Traits<T>::is_float && sizeof(T) == 1 && std::is_same<TL, T>::value &&
+                                std::is_same<TR, T>::value && sizeof(VecT) >= 16;
+    __shared__ uint8_t pow_lut[PACKED_POW ? 128 * kPowLutRow : 1];
+    if constexpr (PACKED_POW) build_pow8_lut<BLOCK>(pow_lut);
     const uint32_t sword = sizeof(T) == 1 ? (uint32_t)(uint8_t)a.scalar_bits * 0x01010101u : (uint32_t)(uint16_t)a.scalar_bits * 0x00010001u;
     const DivMagic dm = a.magic;
     bool div0 = false;
@@ -454,6 +505,14 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
                 O.v = PO.v;
                 if constexpr (MASKED) ob = r;
                 else div0 |= r != 0;
+            } else if constexpr (PACKED_POW) {
+                constexpr int NW = sizeof(VecT) / 4;
+                union { VecT v; uint32_t w[NW]; } PL, PR, PO;
+                memcpy(&PL.v, &L[u].v, sizeof(VecT));
+                memcpy(&PR.v, &R[u].v, sizeof(VecT));
+                packed_pow8_vec<Traits<T>::is_signed, MASKED, NW>(pow_lut, PL.w, lp != nullptr, PR.w, rp != nullptr, sword, MASKED ? mb[u] : 0u, PO.w);
+                O.v = PO.v;
+                if constexpr (MASKED) ob = mb[u];      // Power never nulls a row: output validity = merged input validity
             } else
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
