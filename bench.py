@@ -350,6 +350,14 @@ def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows):
     for _ in range(1000):
         devops.reduce_sum(ctx, S)
     dev_us = (time.perf_counter() - t0) * 1e3
+    # the same call with the ctypes arguments marshalled once: what the C ABI itself costs (launch + stream sync)
+    s64, c64 = mnr._lib.Scalar64(), C.c_uint64()
+    fn, a1, a2, a3, a4 = ctx.lib.mnr_reduce_sum, ctx.h, S.h, C.byref(s64), C.byref(c64)
+    t0 = time.perf_counter()
+    for _ in range(1000):
+        fn(a1, a2, None, a3, a4)
+    abi_us = (time.perf_counter() - t0) * 1e3
+    assert s64.i64 == 499500
     t0 = time.perf_counter()
     for _ in range(1000):
         mnr.kernels.reduce.stats(small, None, False, ctx)
@@ -363,7 +371,8 @@ def secondary(torch, mnr, ctx, dev, peak, data_buf, n_rows):
         mnr.core.check(ctx.lib.mnr_reduce_stats_batch(ctx.h, 1000, harr, None, 0, aggs))     # one C ABI call, one launch
     batch_us = (time.perf_counter() - t0) / 20 * 1e6
     assert all(a.sum.i64 == 499500 and a.count == 1000 for a in aggs)
-    out["c1_i64_1000_sum"] = {"device_resident_us_per_call": round(dev_us, 2), "host_slice_us_per_call": round(host_us, 2),
+    out["c1_i64_1000_sum"] = {"device_resident_us_per_call": round(dev_us, 2), "c_abi_us_per_call": round(abi_us, 2),
+                              "host_slice_us_per_call": round(host_us, 2),
                               "batched_1000_arrays_us_per_array": round(batch_us / 1000, 3),
                               "published_cpu_ns": {"Vec64<i64>": 55, "IntegerArray direct": 88, "Array enum": 170},
                               "note": "roofline N/A (8 KB): one kernel launch + one stream sync per call; result 499500 checked"}

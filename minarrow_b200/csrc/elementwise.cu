@@ -136,8 +136,7 @@ static cudaError_t go_heavy(const EwArgs& a, cudaStream_t s) {
         else if (CLS == CLS_REM) cfg = sizeof(T) == 8 ? 2 : 1;                       // float remainder
         else if (sizeof(T) == 8) cfg = 2;
         else if (sizeof(T) == 4) cfg = (masked && Traits<T>::is_signed) ? 3 : 2;
-        else if (sizeof(T) == 2) cfg = 1;
-        else cfg = masked ? 2 : 1;
+        else cfg = 2;   // 8/16-bit columns: the packed division / table paths (r02d: 128 thr x 2 x 256-bit wins every shape)
     }
     if (cfg == 2) return go_align<T, T, T, CLS, CfgFdiv2>(a, s);
     if (cfg == 3) return go_align<T, T, T, CLS, CfgFdiv3>(a, s);

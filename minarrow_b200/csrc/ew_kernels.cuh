@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "divmagic.h"
 #include "fastmod.h"
+#include "fastpow.h"
 #include "internal.h"
 
 namespace mnr {
@@ -139,7 +140,8 @@ __device__ __forceinline__ T float_elem(int op, T a, T b) {
     } else if constexpr (CLS == CLS_REM) {
         return fast_fmod<T>(a, b);   // exact like fmod; the libm loop only for NaN / Inf / zero divisors / huge quotients
     } else {
-        return exp(b * log(a));
+        if constexpr (std::is_same<T, double>::value) return fast_pow_f64(a, b);   // same expression, ~45 instead of ~120 FP64 operations
+        else return exp(b * log(a));
     }
 }
 
@@ -228,8 +230,10 @@ __device__ __forceinline__ uint32_t packed_div_word(uint32_t lw, uint32_t rw, ui
         sl = lane_neg_mask<ESZ>(lw);
         const uint32_t sr = lane_neg_mask<ESZ>(rw);
         sq = sl ^ sr;
-        la = lane_sub<ESZ>(lw ^ sl, sl);
-        ra = lane_sub<ESZ>(rw ^ sr, sr);
+        // |x| = (x ^ s) + 1 in negative lanes: ~x <= 2^(bits-1) - 1 there, so the increment never carries into the next lane
+        constexpr uint32_t ONE = ESZ == 1 ? 0x01010101u : 0x00010001u;
+        la = (lw ^ sl) + (sl & ONE);
+        ra = (rw ^ sr) + (sr & ONE);
     }
     uint32_t t[EPW];
 #pragma unroll
@@ -252,7 +256,7 @@ __device__ __forceinline__ uint32_t packed_div_word(uint32_t lw, uint32_t rw, ui
     if constexpr (OP == MNR_DIV && !SIGNED) return uq;
     if constexpr (OP == MNR_FLOORDIV && !SIGNED) return uq;
     if constexpr (OP == MNR_DIV) return lane_sub<ESZ>(uq ^ sq, sq);
-    const uint32_t um = lane_sub<ESZ>(la, packed_cheap_word<ESZ, MNR_MUL>(uq, ra));   // |l| - q |r|
+    const uint32_t um = la - packed_cheap_word<ESZ, MNR_MUL>(uq, ra);   // |l| - q |r| >= 0 in every lane: a plain subtract never borrows across lanes
     if constexpr (OP == MNR_REM) return SIGNED ? lane_sub<ESZ>(um ^ sl, sl) : um;
     // FloorDiv, signed: truncated quotient, minus one where the remainder is non-zero and the signs differ
     const uint32_t q = lane_sub<ESZ>(uq ^ sq, sq);

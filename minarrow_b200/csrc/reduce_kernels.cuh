@@ -525,10 +525,8 @@ __device__ __forceinline__ bool reduce_stats_body(const T* __restrict__ data, co
         AggRaw r = q.raw();
         if (poisoned) r.count = kAggPoison;
         *out = r;
-        if (out_host) {   // optional second copy straight into mapped pinned host memory (synchronous APIs: no D2H memcpy)
-            *out_host = r;
-            __threadfence_system();
-        }
+        if (out_host) *out_host = r;   // second copy straight into mapped pinned host memory (synchronous APIs: no D2H memcpy); kernel
+                                       // completion makes it visible to the host — no system fence on the latency path
         if (nblk > 1) *ticket = 0;   // re-arm for the next launch on this stream
     }
     return true;
@@ -599,7 +597,6 @@ __device__ __forceinline__ void fold_and_exchange(const FoldArgs& f, const AggRa
         f.result[g] = acc;
         if (f.result_host) f.result_host[g] = acc;
     }
-    if (f.result_host) __threadfence_system();
     if (threadIdx.x == 0) *f.gticket = 0;   // re-arm
 }
 

@@ -105,3 +105,16 @@ def test_float_remainder_fast_path_is_exact():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:]
     assert r.stdout.count(", 0 failed") == 2, r.stdout
+
+
+def test_float64_power_fast_path_stays_inside_the_reference_tolerance():
+    """minarrow_b200/csrc/fastpow.h (f64 Power = exp(b ln a) in ~45 FP64 operations instead of two libm calls) against
+    glibc's exp(b * log(a)) — the oracle's arithmetic — over 1.4e7 random pairs up to |b ln a| = 699, plus the special
+    values that must fall through to libm.  Host-only, ~4 s."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_fastpow.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_fastpow")
+    deps = [src, os.path.join(ROOT, "minarrow_b200", "csrc", "fastpow.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", src, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.rstrip().endswith("0 failed"), r.stdout[-2000:]
