@@ -329,6 +329,7 @@ static uint64_t scalar_to_bits(mnr_dtype dt, const void* scalar) {
 // which nulls every row (masked) or raises the divide-by-zero flag (dense).
 static void prepare_scalar_division(EwArgs& a) {
     a.sdiv = 0;
+    a.nonzero_divisor = 0;
     if (is_float_dtype(a.dtype) || a.rhs != nullptr || a.lhs == nullptr) return;
     if (a.op != MNR_DIV && a.op != MNR_REM && a.op != MNR_FLOORDIV) return;
     const size_t sz = dtype_size(a.dtype);
@@ -336,6 +337,10 @@ static void prepare_scalar_division(EwArgs& a) {
     uint64_t u = a.scalar_bits;
     if (sz < 8) u &= (1ull << (8 * sz)) - 1ull;
     if (u == 0) return;
+    a.nonzero_divisor = 1;
+    // 8/16-bit columns: the packed division path of the generic kernel takes the scalar as a broadcast word (its reciprocal
+    // is loop-invariant) and beats the widened multiplicative inverse (r02e: i8 0.25 -> the two-column rate).
+    if (sz <= 2) return;
     const int nbits = sz == 8 ? 64 : 32;   // 8/16-bit columns are widened to 32 bits in the kernel
     DivMagic k;
     if (is_signed) {
@@ -352,7 +357,7 @@ static void prepare_scalar_division(EwArgs& a) {
 static int run_ew(mnr_ctx* c, EwArgs& a, cudaStream_t s, bool promote, mnr_dtype lt, mnr_dtype rt) {
     if (a.n == 0) return MNR_OK;
     if (!promote) prepare_scalar_division(a);
-    const bool dense_int_div = !a.lmask && !a.rmask && !is_float_dtype(a.dtype) && !a.sdiv &&
+    const bool dense_int_div = !a.lmask && !a.rmask && !is_float_dtype(a.dtype) && !a.sdiv && !a.nonzero_divisor &&
                                (a.op == MNR_DIV || a.op == MNR_REM || a.op == MNR_FLOORDIV);
     a.div0_flag = c->ticket[0] + 8;
     if (dense_int_div) CU(cudaMemsetAsync(a.div0_flag, 0, 4, s));
@@ -558,7 +563,8 @@ static int run_ew_batch(mnr_ctx* c, std::vector<EwArgs>& items) {
     for (auto& a : items) {
         a.div0_flag = flag;
         prepare_scalar_division(a);
-        if (!a.lmask && !a.rmask && !is_float_dtype(a.dtype) && !a.sdiv && (a.op == MNR_DIV || a.op == MNR_REM || a.op == MNR_FLOORDIV))
+        if (!a.lmask && !a.rmask && !is_float_dtype(a.dtype) && !a.sdiv && !a.nonzero_divisor &&
+            (a.op == MNR_DIV || a.op == MNR_REM || a.op == MNR_FLOORDIV))
             any_dense_int_div = true;
     }
     if (any_dense_int_div) CU(cudaMemsetAsync(flag, 0, 4, c->stream));

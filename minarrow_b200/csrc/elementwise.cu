@@ -132,11 +132,12 @@ static cudaError_t go_heavy(const EwArgs& a, cudaStream_t s) {
     int cfg = a.k.heavy_cfg;
     if (cfg == 0) {
         const bool masked = a.lmask || a.rmask;
-        if (CLS == CLS_POW) cfg = 2;
+        if (CLS == CLS_POW && sizeof(T) > 1) cfg = 2;
         else if (CLS == CLS_REM) cfg = sizeof(T) == 8 ? 2 : 1;                       // float remainder
         else if (sizeof(T) == 8) cfg = 2;
         else if (sizeof(T) == 4) cfg = (masked && Traits<T>::is_signed) ? 3 : 2;
-        else cfg = 2;   // 8/16-bit columns: the packed division / table paths (r02d: 128 thr x 2 x 256-bit wins every shape)
+        else if (CLS == CLS_POW && sizeof(T) == 1) cfg = 3;   // table in shared memory, built once per block: resident grid
+        else cfg = 2;   // 8/16-bit columns: the packed division path (r02d: 128 thr x 2 x 256-bit wins every shape)
     }
     if (cfg == 2) return go_align<T, T, T, CLS, CfgFdiv2>(a, s);
     if (cfg == 3) return go_align<T, T, T, CLS, CfgFdiv3>(a, s);

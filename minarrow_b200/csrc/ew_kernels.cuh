@@ -292,20 +292,17 @@ __device__ __forceinline__ uint32_t packed_div_vec(const uint32_t (&a)[NW], bool
 // shared memory, built by the block once (resident grid), then ONE byte load per row.  Signed columns use the same bits
 // (wrapping multiply); a negative exponent is `rhs.to_u32().unwrap_or(0)` = 0 (std.rs:67) -> 1.
 constexpr int kPowLutRow = 80;   // per half-base: [0, 64) odd base, exponent mod 64; [64, 80) even base, exponent min(e, 8) (+ padding)
-__device__ __forceinline__ uint32_t pow8_mod256(uint32_t b, uint32_t e) {
-    uint32_t acc = 1;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {   // e < 64
-        if (e & 1u) acc = (acc * b) & 0xFFu;
-        b = (b * b) & 0xFFu;
-        e >>= 1;
-    }
-    return acc;
-}
 template <int BLOCK> __device__ __forceinline__ void build_pow8_lut(uint8_t* lut) {
-    for (int i = threadIdx.x; i < 128 * kPowLutRow; i += BLOCK) {
-        const uint32_t x = (uint32_t)i / kPowLutRow, t = (uint32_t)i % kPowLutRow;
-        lut[i] = t < 64 ? (uint8_t)pow8_mod256(2 * x + 1, t) : (uint8_t)((t - 64) >= 8 ? 0u : pow8_mod256(2 * x, t - 64));
+    // one thread per (half-base, parity): the powers of one base by running product, 64 (odd) or 16 (even) multiplies
+    for (int i = threadIdx.x; i < 256; i += BLOCK) {
+        const uint32_t x = (uint32_t)i >> 1, odd = (uint32_t)i & 1u, base = 2 * x + odd;
+        uint8_t* row = lut + x * kPowLutRow + (odd ? 0 : 64);
+        uint32_t acc = 1;
+        const int cnt = odd ? 64 : 16;
+        for (int t = 0; t < cnt; ++t) {
+            row[t] = (uint8_t)((!odd && t >= 8) ? 0u : acc);
+            acc = (acc * base) & 0xFFu;
+        }
     }
     __syncthreads();
 }

@@ -64,6 +64,7 @@ struct EwArgs {
     int sdiv;
     uint64_t magic_m;
     uint32_t magic_s1, magic_s2;
+    int nonzero_divisor;    // host-side: the divisor is a broadcast scalar known to be non-zero (no divide-by-zero check needed)
     EwKnobs k;
 };
 cudaError_t launch_ew_binary(const EwArgs& a, cudaStream_t s);
