@@ -38,6 +38,10 @@ struct CfgSdiv64 { static constexpr int BLOCK = 128, U = 2, MINB = 6; static con
 // (also measured: CfgCheap's 128 thr x 4 x 256-bit — never the best; CfgHeavy with a covering grid — always the worst.)
 struct CfgFdiv2 { static constexpr int BLOCK = 128, U = 2, MINB = 6; static constexpr bool RESIDENT = false; using Wide = V32; };
 struct CfgFdiv3 { static constexpr int BLOCK = 256, U = 2, MINB = 3; static constexpr bool RESIDENT = true; using Wide = V32; };
+// f64 Power (fastpow.h: ~55 FP64 operations per row, long dependent chains, 16-byte values): the 85-register geometries spill
+// (72 bytes of stack at U = 2 x 256-bit).  Candidates without spills: one vector in flight, or 128 registers.
+struct CfgPow4 { static constexpr int BLOCK = 128, U = 1, MINB = 6; static constexpr bool RESIDENT = false; using Wide = V32; };
+struct CfgPow5 { static constexpr int BLOCK = 128, U = 2, MINB = 4; static constexpr bool RESIDENT = false; using Wide = V32; };
 
 static EwDev to_dev(const EwArgs& a) {
     EwDev d;
@@ -141,6 +145,10 @@ static cudaError_t go_heavy(const EwArgs& a, cudaStream_t s) {
     }
     if (cfg == 2) return go_align<T, T, T, CLS, CfgFdiv2>(a, s);
     if (cfg == 3) return go_align<T, T, T, CLS, CfgFdiv3>(a, s);
+    if constexpr (CLS == CLS_POW && std::is_same<T, double>::value) {
+        if (cfg == 4) return go_align<T, T, T, CLS, CfgPow4>(a, s);
+        if (cfg == 5) return go_align<T, T, T, CLS, CfgPow5>(a, s);
+    }
     return go_align<T, T, T, CLS>(a, s);
 }
 

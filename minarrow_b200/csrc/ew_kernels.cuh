@@ -200,8 +200,11 @@ __device__ __forceinline__ void packed_cheap_vec(const uint32_t (&a)[NW], bool h
 //     squeezed out of the mask with one multiply.
 // ~10 (unsigned Div) to ~15 (signed Rem / FloorDiv) instructions per row.
 template <int ESZ> __device__ __forceinline__ uint32_t lane_neg_mask(uint32_t x) {
-    if constexpr (ESZ == 1) return ((x >> 7) & 0x01010101u) * 0xFFu;
-    else return ((x >> 15) & 0x00010001u) * 0xFFFFu;
+    // PRMT with selector bit 3 set replicates the sign bit of the selected byte: one instruction per word
+    uint32_t d;
+    if constexpr (ESZ == 1) asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(d) : "r"(x));
+    else asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(d) : "r"(x));
+    return d;
 }
 template <int ESZ> __device__ __forceinline__ uint32_t lane_nonzero_mask(uint32_t x) {   // 0xFF.. in lanes that are != 0
     if constexpr (ESZ == 1) return (((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7) & 0x01010101u) * 0xFFu;
@@ -210,6 +213,11 @@ template <int ESZ> __device__ __forceinline__ uint32_t lane_nonzero_mask(uint32_
 template <int ESZ> __device__ __forceinline__ uint32_t lane_sub(uint32_t a, uint32_t b) {
     if constexpr (ESZ == 1) return __vsub4(a, b);
     else return __vsub2(a, b);
+}
+// t + inc per lane for inc in {0, 1}, without carries between lanes (4 instructions; the emulated packed subtract costs more)
+template <int ESZ> __device__ __forceinline__ uint32_t lane_add01(uint32_t t, uint32_t inc) {
+    constexpr uint32_t L = ESZ == 1 ? 0x7F7F7F7Fu : 0x7FFF7FFFu;
+    return ((t & L) + inc) ^ (t & ~L);
 }
 // lane k of `w` as the float bits of 2^23 + lane (PRMT with the exponent constant as second source)
 template <int ESZ, int K> __device__ __forceinline__ float lane_biased(uint32_t w) {
@@ -255,13 +263,12 @@ __device__ __forceinline__ uint32_t packed_div_word(uint32_t lw, uint32_t rw, ui
     vm &= lane_nonzero_mask<ESZ>(rw);
     if constexpr (OP == MNR_DIV && !SIGNED) return uq;
     if constexpr (OP == MNR_FLOORDIV && !SIGNED) return uq;
-    if constexpr (OP == MNR_DIV) return lane_sub<ESZ>(uq ^ sq, sq);
+    constexpr uint32_t ONE = ESZ == 1 ? 0x01010101u : 0x00010001u;
+    if constexpr (OP == MNR_DIV) return lane_add01<ESZ>(uq ^ sq, sq & ONE);                 // -q = ~q + 1 in the lanes whose signs differ
     const uint32_t um = la - packed_cheap_word<ESZ, MNR_MUL>(uq, ra);   // |l| - q |r| >= 0 in every lane: a plain subtract never borrows across lanes
-    if constexpr (OP == MNR_REM) return SIGNED ? lane_sub<ESZ>(um ^ sl, sl) : um;
-    // FloorDiv, signed: truncated quotient, minus one where the remainder is non-zero and the signs differ
-    const uint32_t q = lane_sub<ESZ>(uq ^ sq, sq);
-    const uint32_t adj = lane_nonzero_mask<ESZ>(um) & sq & (ESZ == 1 ? 0x01010101u : 0x00010001u);
-    return lane_sub<ESZ>(q, adj);
+    if constexpr (OP == MNR_REM) return SIGNED ? lane_add01<ESZ>(um ^ sl, sl & ONE) : um;   // the remainder takes the dividend's sign
+    // FloorDiv, signed (std.rs:72-75): where the signs differ the result is -q - (remainder != 0) = ~q + (remainder == 0)
+    return lane_add01<ESZ>(uq ^ sq, sq & ~lane_nonzero_mask<ESZ>(um) & ONE);
 }
 
 // One vector (NW words); returns the output validity bits of its lanes (MASKED) / whether a zero divisor was met (dense).

@@ -37,7 +37,7 @@ for name in NAMES:
                  ("floordiv two masks", lambda: ops.ew_binary_into(ctx, A.FloorDiv, X, Y, M1, M2, mnr.MaskMode.And, O, OM), n * (3 * sz + 0.375)),
                  ("div dense", lambda: ops.ew_binary_into(ctx, A.Divide, X, Y, None, None, mnr.MaskMode.And, O, None), n * 3 * sz)] + cases
     ref = {}
-    for cfg in (1, 2, 3, 0):
+    for cfg in ((1, 2, 3, 4, 5, 0) if name == "float64" else (1, 2, 3, 0)):
         ctx.set_option("ew_heavy_cfg", cfg)
         for label, fn, nb in cases:
             med, _ = event_time_ms(torch, fn, 11)
