@@ -319,6 +319,12 @@ class BooleanArray:
     def __len__(self) -> int:
         return self.data.len
 
+    def __invert__(self) -> "BooleanArray":
+        """`impl Not for BooleanArray` (boolean.rs:853-866): the data bits are inverted on the device (`not_mask`, slack bits
+        stay zero), the validity is kept as is."""
+        from .kernels.bitmask import not_mask
+        return BooleanArray(not_mask((self.data, 0, self.data.len)), self.null_mask)
+
 
 def make_array(data: np.ndarray, null_mask: Optional[Bitmask]):
     return (FloatArray if data.dtype.kind == "f" else IntegerArray)(data, null_mask)

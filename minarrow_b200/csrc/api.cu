@@ -1034,11 +1034,11 @@ static int ensure_batch_scratch(mnr_ctx* c, size_t nseg_total, size_t nseg_launc
 
 // Launch plan of a batched reduction: the segments grouped by kernel instantiation (order inside a group is the caller's
 // order), flattened in launch order with gridDim.y <= 65535 per launch.
-struct ReduceLaunch { int dtype, tier, masked; size_t cnt; uint32_t max_blk; size_t seg0; };
+struct ReduceLaunch { int dtype, tier, masked; size_t cnt; uint32_t max_blk; size_t seg0; size_t part0; };
 struct ReducePlan {
     std::vector<ReduceLaunch> launches;
     std::vector<ReduceSeg> flat;
-    size_t max_cnt = 0, max_pblk = 0;
+    size_t pblk_total = 0;   // partial slots over all launches of the call (every launch has its own region: they overlap)
 };
 static ReducePlan plan_reduce_batch(size_t n, const mnr_buf* const* bufs, const mnr_bits* const* validities, bool minmax) {
     struct Key { int dtype, tier, masked; };
@@ -1062,10 +1062,9 @@ static ReducePlan plan_reduce_batch(size_t n, const mnr_buf* const* bufs, const 
             const size_t cnt = std::min<size_t>(65535, groups[g].size() - off);
             uint32_t max_blk = 1;
             for (size_t i = 0; i < cnt; ++i) max_blk = std::max(max_blk, groups[g][off + i].nblk);
-            p.launches.push_back(ReduceLaunch{keys[g].dtype, keys[g].tier, keys[g].masked, cnt, max_blk, p.flat.size()});
+            p.launches.push_back(ReduceLaunch{keys[g].dtype, keys[g].tier, keys[g].masked, cnt, max_blk, p.flat.size(), p.pblk_total});
             p.flat.insert(p.flat.end(), groups[g].begin() + off, groups[g].begin() + off + cnt);
-            p.max_cnt = std::max(p.max_cnt, cnt);
-            p.max_pblk = std::max<size_t>(p.max_pblk, cnt * max_blk);
+            p.pblk_total += cnt * max_blk;
         }
     return p;
 }
@@ -1074,10 +1073,11 @@ static ReducePlan plan_reduce_batch(size_t n, const mnr_buf* const* bufs, const 
 // by the block that writes the last chunk aggregate of the call.  One descriptor upload for the whole call, so the
 // launches sit back to back on the stream.  The descriptor area is double-buffered; a pageable-source cudaMemcpyAsync
 // stages the bytes before it returns, so the host vector may die right after; stream order protects the device copy.
-// Launches of one call run one after the other on the stream, so they share the partials area; tickets are per segment
-// of a launch and re-arm themselves.
+// The launches of one call carry the programmatic-launch attribute and are independent of each other (own partials region,
+// own tickets — one per segment of the call, self re-arming), so launch i+1 fills the SMs while launch i drains; the
+// descriptor copy in front keeps the call itself ordered after everything earlier on the stream.
 static int reduce_batch_launch(mnr_ctx* c, const ReducePlan& p, bool minmax, AggRaw* outs, const FoldArgs& f, const XchgDev& x) {
-    int rc = ensure_batch_scratch(c, p.flat.size(), p.max_cnt, p.max_pblk);
+    int rc = ensure_batch_scratch(c, p.flat.size(), p.flat.size(), p.pblk_total);
     if (rc) return rc;
     char* dst = static_cast<char*>(c->batch_segs) + (c->batch_flip ? c->batch_segs_bytes / 2 : 0);
     c->batch_flip ^= 1;
@@ -1085,7 +1085,7 @@ static int reduce_batch_launch(mnr_ctx* c, const ReducePlan& p, bool minmax, Agg
     for (const ReduceLaunch& L : p.launches) {
         CU(launch_reduce_stats_batch((mnr_dtype)L.dtype, L.tier, L.masked != 0, minmax,
                                      reinterpret_cast<const ReduceSeg*>(dst) + L.seg0, (uint32_t)L.cnt, L.max_blk,
-                                     static_cast<AggRaw*>(c->batch_partials), static_cast<unsigned int*>(c->batch_tickets),
+                                     static_cast<AggRaw*>(c->batch_partials) + L.part0, static_cast<unsigned int*>(c->batch_tickets) + L.seg0,
                                      outs, f, x, c->stream));
         c->launches++;
     }
@@ -1140,15 +1140,21 @@ int mnr_xchg_create(mnr_ctx* c, int world, int rank, mnr_xchg** out) {
     x->ctx = c; x->world = world; x->rank = rank;
     cudaError_t e = cudaMalloc(&x->mailbox, kMailboxBytes);
     if (e == cudaSuccess) e = cudaMemset(x->mailbox, 0, kMailboxBytes);
-    if (e == cudaSuccess) e = cudaMalloc(&x->err, 64);
-    if (e == cudaSuccess) e = cudaMemset(x->err, 0, 64);
+    if (e == cudaSuccess) e = cudaMalloc(&x->err, 128);          // [0] error word, [64] the `done` epoch
+    if (e == cudaSuccess) e = cudaMemset(x->err, 0, 128);
+    if (e == cudaSuccess) e = cudaMalloc(&x->partials, 2 * sizeof(AggRaw) * (size_t)reduce_max_grid());
+    if (e == cudaSuccess) e = cudaMalloc(&x->ticket, 128);
+    if (e == cudaSuccess) e = cudaMemset(x->ticket, 0, 128);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         if (x->mailbox) cudaFree(x->mailbox);
         if (x->err) cudaFree(x->err);
+        if (x->partials) cudaFree(x->partials);
+        if (x->ticket) cudaFree(x->ticket);
         delete x;
         return fail_cuda(e, "mnr_xchg_create");
     }
+    x->done = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x->err) + 64);
     x->peers[rank] = x->mailbox;
     x->connected = world == 1;
     *out = x;
@@ -1222,6 +1228,8 @@ void mnr_xchg_destroy(mnr_xchg* x) {
     for (int r = 0; r < x->world; ++r) if (x->opened[r]) cudaIpcCloseMemHandle(x->peers[r]);
     cudaFree(x->mailbox);
     cudaFree(x->err);
+    cudaFree(x->partials);
+    cudaFree(x->ticket);
     delete x;
 }
 
@@ -1232,7 +1240,7 @@ static int check_xchg(const mnr_ctx* c, const mnr_xchg* x) {
 }
 static XchgDev xchg_dev(const mnr_xchg* x, unsigned long long epoch) {
     XchgDev d{};
-    d.world = x->world; d.rank = x->rank; d.epoch = epoch; d.err = x->err; d.slot_bytes = kSlotBytes;
+    d.world = x->world; d.rank = x->rank; d.epoch = epoch; d.err = x->err; d.done = x->done; d.slot_bytes = kSlotBytes;
     for (int r = 0; r < x->world; ++r) d.mailbox[r] = x->peers[r];
     return d;
 }
@@ -1249,8 +1257,10 @@ int mnr_reduce_stats_exchange(mnr_ctx* c, mnr_xchg* x, const mnr_buf* b, const m
     // Overlap with the previous reduction (late dependency wait) only when the caller opted in AND nothing else of this
     // library was launched on the stream since that reduction — an element-wise kernel could be producing this column.
     const bool late = c->reduce_overlap && c->last_reduce_launch == c->launches && c->launches != 0;
-    CU(launch_reduce_stats_xchg(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, with_minmax != 0, c->partials[3], c->ticket[3],
-                                static_cast<AggRaw*>(out_device), nullptr, xchg_dev(x, x->epoch + 1), late, !x->shares_device,
+    const unsigned long long epoch = x->epoch + 1;   // partials / ticket alternate by epoch parity (overlapped launches)
+    CU(launch_reduce_stats_xchg(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, with_minmax != 0,
+                                x->partials + (epoch & 1) * (size_t)reduce_max_grid(), x->ticket + (epoch & 1) * 16,
+                                static_cast<AggRaw*>(out_device), nullptr, xchg_dev(x, epoch), late, !x->shares_device,
                                 c->stream));
     x->epoch++;   // only a launch that happened consumes an epoch (a failed one would leave this rank ahead of its peers)
     c->launches++;
@@ -1313,7 +1323,7 @@ static size_t fold_desc_bytes(size_t n, size_t n_cols, size_t* off_idx, size_t* 
 // against it, so mnr_group_reduce_stats reserves on ALL ranks before the first launch.
 static int reduce_exchange_reserve(mnr_ctx* c, const ReducePlan& p, size_t n, size_t n_cols) {
     CU(cudaSetDevice(c->device));
-    int rc = ensure_batch_scratch(c, p.flat.size(), p.max_cnt, p.max_pblk);
+    int rc = ensure_batch_scratch(c, p.flat.size(), p.flat.size(), p.pblk_total);
     if (rc) return rc;
     const size_t need_aggs = n ? n : 1;
     if (c->chunk_aggs_cap < need_aggs) {

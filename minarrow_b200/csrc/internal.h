@@ -157,6 +157,9 @@ struct mnr_xchg {
     char* peers[16] = {};                    // every rank's mailbox as mapped here (peers[rank] == mailbox)
     bool opened[16] = {};                    // mapped through CUDA IPC (to be closed)
     unsigned int* err = nullptr;             // device word: a peer's flag never arrived
+    unsigned long long* done = nullptr;      // device word: last epoch finished on this rank
+    mnr::AggRaw* partials = nullptr;         // 2 x reduce_max_grid(): block partials, alternating by epoch parity
+    unsigned int* ticket = nullptr;          // 2 x 16 words: finish tickets, alternating by epoch parity
     bool connected = false;
     // Another rank of this exchange lives on the SAME device (virtual ranks).  Then reductions are launched without the
     // programmatic-launch attribute: an early-scheduled successor kernel parks resident blocks at its dependency wait,

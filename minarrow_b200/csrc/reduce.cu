@@ -49,9 +49,17 @@ static cudaError_t launch_one(const void* data, const uint8_t* mask, uint64_t n,
 template <typename T, typename VecT, bool MASKED, bool MINMAX>
 static cudaError_t launch_batch_one(const ReduceSeg* segs, uint32_t nseg, uint32_t max_blk, AggRaw* partials,
                                     unsigned int* tickets, AggRaw* outs, const FoldArgs& f, const XchgDev& x, cudaStream_t s) {
-    reduce_stats_batch_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>
-        <<<dim3(max_blk, nseg, 1), kRBlock, 0, s>>>(segs, partials, tickets, outs, max_blk, f, x);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(max_blk, nseg, 1);
+    cfg.blockDim = dim3(kRBlock, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the launches of one batched call overlap (api.cu reduce_batch_launch)
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, reduce_stats_batch_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>,
+                              segs, partials, tickets, outs, max_blk, f, x);
 }
 
 // (tier, masked, minmax) -> instantiation.  The 256-bit tier exists only with min/max.

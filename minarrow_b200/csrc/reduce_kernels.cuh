@@ -307,6 +307,7 @@ struct XchgDev {
     int rank;
     unsigned long long epoch;  // 1, 2, 3, ... identical sequence on every rank
     unsigned int* err;         // device word, set to 1 if a peer's flag never arrives (bounded spin)
+    unsigned long long* done;  // device word: the last epoch whose exchange has finished on this rank (orders overlapped launches)
     unsigned int slot_bytes;   // kXchgHeader + 32 * max_aggs, rounded up to 64
     char* mailbox[kMaxPeers];  // mailbox[r]: rank r's mailbox as mapped in this process
 };
@@ -325,6 +326,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const void* p) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ AggRaw ld_sys_agg(const void* p) {
     AggRaw r;
     asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.sum), "=l"(r.mn) : "l"(p) : "memory");
@@ -341,6 +350,12 @@ __device__ __forceinline__ void st_sys_agg(void* p, const AggRaw& a) {
 // blocks take over SM slots as ours exit — the launch ramp, the ticket finish and the cross-GPU flag wait of reduction k
 // overlap the streaming phase of reduction k+1.  `pdl_wait` blocks until the previous kernel on the stream has completed
 // and its writes are visible; both instructions are no-ops for a kernel launched without the attribute.
+// In the overlapped ("late") form of the exchange reduction NO block takes that wait: streaming blocks never depend on the
+// previous launch, partials / tickets alternate between two buffers by epoch parity, and the launches are ordered through
+// the exchange's `done` word instead — a block checks `done >= epoch - 2` before it writes its partial (the buffer's previous
+// user has folded; practically never spins) and the finishing block alone waits for `done >= epoch - 1` before it posts to
+// the mailboxes and writes the result, then publishes `done = epoch`.  So a rank may run up to two reductions ahead of the
+// slowest peer, and the per-step max-over-ranks jitter of a lock-step collective is absorbed instead of added.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -480,13 +495,14 @@ __device__ __forceinline__ bool reduce_stats_body(const T* __restrict__ data, co
     }
 
     p = block_combine<P, BLOCK>(p, smem);
-    // Everything below touches memory shared with the previous launch on the stream (partials, ticket, out, mailboxes).
-    if (late_wait) pdl_wait();
+    // Everything below touches memory shared with earlier launches on the stream (partials, ticket, out, mailboxes); in the
+    // late form the order is kept through x.done (see pdl_* above), otherwise the kernel already waited for its predecessor.
     P q;
     if (nblk == 1) {
         q = p;   // small column: the only block is the finishing block — no partials, no ticket, no fences
     } else {
         if (threadIdx.x == 0) {
+            if (late_wait) while (ld_acquire_gpu(x.done) + 2 < x.epoch) {}   // this parity's buffer: its previous user has folded
             partials[bid] = p.raw();
             __threadfence();
             const unsigned int done = atomicAdd(ticket, 1u);
@@ -509,6 +525,7 @@ __device__ __forceinline__ bool reduce_stats_body(const T* __restrict__ data, co
         if (threadIdx.x == 0) {
             if constexpr (!MASKED) q.cnt = n;
             mine = q.raw();
+            if (late_wait) while (ld_acquire_gpu(x.done) + 1 < x.epoch) {}   // the previous reduction has left the mailboxes and `out`
         }
         const bool ok = xchg_exchange<BLOCK>(x, &mine, 1u);   // starts with a __syncthreads
         if (threadIdx.x == 0) {
@@ -528,6 +545,7 @@ __device__ __forceinline__ bool reduce_stats_body(const T* __restrict__ data, co
         if (out_host) *out_host = r;   // second copy straight into mapped pinned host memory (synchronous APIs: no D2H memcpy); kernel
                                        // completion makes it visible to the host — no system fence on the latency path
         if (nblk > 1) *ticket = 0;   // re-arm for the next launch on this stream
+        if (x.world > 0) { __threadfence(); st_release_gpu(x.done, x.epoch); }   // last: the successor may post / write now
     }
     return true;
 }
@@ -597,13 +615,17 @@ __device__ __forceinline__ void fold_and_exchange(const FoldArgs& f, const AggRa
         f.result[g] = acc;
         if (f.result_host) f.result_host[g] = acc;
     }
-    if (threadIdx.x == 0) *f.gticket = 0;   // re-arm
+    if (threadIdx.x == 0) {
+        *f.gticket = 0;   // re-arm
+        if (x.world > 0) { __threadfence(); st_release_gpu(x.done, x.epoch); }
+    }
 }
 
 template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MINB, int U>
 __global__ void __launch_bounds__(BLOCK, MINB)
 reduce_stats_batch_kernel(const ReduceSeg* __restrict__ segs, AggRaw* __restrict__ partials, unsigned int* __restrict__ tickets,
                           AggRaw* __restrict__ outs, uint32_t max_blk, const FoldArgs f, const XchgDev x) {
+    pdl_launch_dependents();   // the next launch of the same batched call may start filling the SMs (no data dependency)
     const ReduceSeg s = segs[blockIdx.y];
     if (blockIdx.x >= s.nblk) return;
     const bool fin = reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(static_cast<const T*>(s.data), s.mask, s.n,

@@ -211,3 +211,15 @@ def test_super_array_stats_and_masked_route_on_device(gpu_ctx, oracle):
         e = oracle.stats(whole, oracle.Bits.from_bools(valid))
         assert s["count"] == e["count"] and s["min"] == e["min"] and s["max"] == e["max"]
         assert s["sum"] == e["sum"] or abs(s["sum"] - e["sum"]) <= 1e-12 * np.abs(whole[valid].astype(np.float64)).sum()
+
+
+def test_boolean_array_not(gpu_ctx):
+    """BooleanArray `!` (boolean.rs:853-866): data inverted, validity unchanged, slack bits zero."""
+    import minarrow_b200 as mnr
+    rng = np.random.default_rng(9)
+    for n in (1, 7, 64, 1001):
+        d, v = rng.random(n) < 0.5, rng.random(n) < 0.8
+        b = mnr.BooleanArray(mnr.Bitmask.from_bools(d), mnr.Bitmask.from_bools(v))
+        r = ~b
+        assert np.array_equal(r.data.to_bools(), ~d) and r.null_mask is b.null_mask
+        assert np.array_equal(r.data.bits, np.packbits(~d, bitorder="little"))

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--gib", type=float, default=1.0)
     ap.add_argument("--out", default="")
     ap.add_argument("--only", default="", help="comma-separated substrings of kernel labels to run")
+    ap.add_argument("--iters", type=int, default=15, help="timed launches per entry (median); 1 for ncu captures")
     ap.add_argument("--dtypes", default="", help="comma-separated numpy dtype names (default: all ten)")
     args = ap.parse_args()
 
@@ -65,7 +66,7 @@ def main():
     def entry(kernel, dtype, nbytes, fn):
         if args.only and not any(k in kernel for k in args.only.split(",")):
             return
-        med, best = event_time_ms(torch, fn, 15)
+        med, best = event_time_ms(torch, fn, args.iters, warmup=min(3, args.iters))
         gbs = nbytes / med / 1e6
         rows_out.append({"kernel": kernel, "dtype": dtype, "GB/s": round(gbs, 1), "frac": round(gbs / peak, 3),
                          "ms": round(med, 4), "bytes": int(nbytes)})
