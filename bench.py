@@ -855,20 +855,46 @@ def run_b200(args):
                 avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable"))
         except Exception:  # noqa: BLE001
             avail = 64 << 30
-        if rows * 8.125 * world > avail / 4:
+        if rows * 8.125 * world * (2 if (world > 1 and strong) else 1) > avail / 4:
             raise SystemExit(f"bench.py: {rows} rows x {world} ranks of pinned host memory do not fit a quarter of "
                              f"MemAvailable ({avail >> 30} GiB); rerun with --no-e2e or fewer --rows")
-        host_data = torch.empty(rows, dtype=torch.int64, pin_memory=True)
-        host_bits = torch.empty(bits.numel(), dtype=torch.uint8, pin_memory=True)
-        host_data.copy_(data)
-        host_bits.copy_(bits)
+        # N > 1, strong scaling: the HOST column is cut in proportion to each rank's host->device copy rate with all links
+        # busy (GPUs behind a shared PCIe uplink copy slower: 23 vs 35 GB/s per GPU on the 8-GPU boxes; an even split makes
+        # everyone wait for the slowest link).  The rates come from a probe copy all ranks run at once.
+        e_rows, e_sum, e_cnt, link = rows, exp_sum, exp_cnt, None
+        if world > 1:
+            ph = torch.empty(1 << 28, dtype=torch.uint8, pin_memory=True)
+            pd = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+            pd.copy_(ph, non_blocking=True)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(4):
+                pd.copy_(ph, non_blocking=True)
+            c1.record()
+            c1.synchronize()
+            bw = torch.tensor([4 * ph.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+            allbw = torch.zeros(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allbw, bw)
+            link = [round(float(x), 1) for x in allbw]
+            del ph, pd
+            if strong:
+                e_rows = mnr.sharded.shard_rows_weighted(args.rows, link)[rank][1]
+        if e_rows == rows:
+            e_data, e_bits = data, bits
+        else:
+            e_data, e_bits, e_sum, e_cnt = gen_column(torch, e_rows, 3000 + rank, dev)
+        host_data = torch.empty(e_rows, dtype=torch.int64, pin_memory=True)
+        host_bits = torch.empty(e_bits.numel(), dtype=torch.uint8, pin_memory=True)
+        host_data.copy_(e_data)
+        host_bits.copy_(e_bits)
         torch.cuda.synchronize()
         agg = mnr._lib.Agg()
         hp, vp = C.c_void_p(host_data.data_ptr()), C.c_void_p(host_bits.data_ptr())
         hpart = torch.zeros(4, dtype=torch.int64, pin_memory=True)
 
         def e2e_step():
-            mnr.core.check(ctx.lib.mnr_stats_host(ctx.h, 2, hp, rows, vp, 0, C.byref(agg)))   # 2 = MNR_I64
+            mnr.core.check(ctx.lib.mnr_stats_host(ctx.h, 2, hp, e_rows, vp, 0, C.byref(agg)))   # 2 = MNR_I64
             if world > 1:
                 hpart[0], hpart[3] = agg.sum.i64, agg.count
                 partial.copy_(hpart, non_blocking=True)
@@ -881,11 +907,11 @@ def run_b200(args):
         barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        data.copy_(host_data, non_blocking=True)
-        bits.copy_(host_bits, non_blocking=True)
+        e_data.copy_(host_data, non_blocking=True)
+        e_bits.copy_(host_bits, non_blocking=True)
         c1.record()
         c1.synchronize()
-        h2d_gbs = (rows * 8 + bits.numel()) / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        h2d_gbs = (e_rows * 8 + e_bits.numel()) / (c0.elapsed_time(c1) * 1e-3) / 1e9
         barrier()
         l0 = ctx.launch_count
         w0 = time.perf_counter()
@@ -895,27 +921,40 @@ def run_b200(args):
         w1 = time.perf_counter()
         e2e_launches = ctx.launch_count - l0
         barrier()
+        e_exp = torch.tensor([e_sum, e_cnt], dtype=torch.int64, device=dev)
         if world > 1:
-            assert int(g[:, 3].sum()) == tot_cnt
+            dist.all_reduce(e_exp)
+            g_sum = int(np.sum(g.numpy()[:, 0].astype(np.uint64), dtype=np.uint64).astype(np.int64))
+            assert (g_sum, int(g[:, 3].sum())) == (int(e_exp[0]), int(e_exp[1])), "e2e sum mismatch"
         else:
             assert (agg.sum.i64, agg.count) == (tot_sum, tot_cnt), "e2e sum mismatch"
+        e_total = torch.tensor([e_rows], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(e_total)
+        e_total = int(e_total)
         tsec = torch.tensor([(w1 - w0) / args.e2e_steps, h2d_gbs], dtype=torch.float64, device=dev)
+        hsum = tsec[1:].clone()
         if world > 1:
             tmin = tsec.clone()
             dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
             dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hsum)
             h2d_gbs = float(tmin[1])
-        nchunks = (rows + (1 << 22) - 1) // (1 << 22)
-        e2e = {"value": round(total_rows * BYTES_PER_ROW / float(tsec[0]) / 1e9, 3), "unit": UNIT,
-               "h2d_bytes_per_step": int(total_rows * 8 + (total_rows + 7) // 8), "d2h_bytes_per_step": 32 * nchunks * world,
+        nchunks = (e_rows + (1 << 22) - 1) // (1 << 22)
+        e2e = {"value": round(e_total * BYTES_PER_ROW / float(tsec[0]) / 1e9, 3), "unit": UNIT,
+               "h2d_bytes_per_step": int(e_total * 8 + (e_total + 7) // 8), "d2h_bytes_per_step": 32 * nchunks * world,
                "ms_per_step": round(float(tsec[0]) * 1e3, 3), "steps": args.e2e_steps,
                "api": "mnr_stats_host (C ABI, pinned host column + validity -> 32-byte aggregate)",
                "timer": "host wall clock around synchronous calls, max over ranks",
                "gpu_launches": int(e2e_launches), "pcie_h2d_copy_GBps_per_gpu": round(h2d_gbs, 2),
-               "frac_of_pcie_copy": round(rows * BYTES_PER_ROW / float(tsec[0]) / 1e9 / h2d_gbs, 4), "numa": numa,
+               "frac_of_pcie_copy": round(e_total * BYTES_PER_ROW / float(tsec[0]) / 1e9 / float(hsum[0]), 4), "numa": numa,
+               "host_sharding": ("rows proportional to each rank's concurrent H2D rate (sharded.shard_rows_weighted)" if link and strong
+                                 else "even"), "link_GBps_all_ranks_copying": link, "rows_this_rank": e_rows,
                "note": "bound by the host->device link: the same bytes as one plain pinned cudaMemcpy take 1/frac of this; "
                        "a single pass over host-resident bytes cannot beat the host's own DRAM through PCIe Gen5 x16 "
                        "(~55 GB/s per GPU) - see resident_pipeline for what keeping columns in HBM buys"}
+        if e_data is not data:
+            del e_data, e_bits
         if world == 1:
             e2e.update(e2e_extras(torch, mnr, ctx, dev, data, bits, rows, host_data, host_bits))
 

@@ -53,6 +53,29 @@ def shard_rows(n_rows: int, world: int, align: int = 64) -> List[Tuple[int, int]
     return out
 
 
+def shard_rows_weighted(n_rows: int, weights: Sequence[float], align: int = 64) -> List[Tuple[int, int]]:
+    """Like `shard_rows`, but rank r gets a share of the rows proportional to `weights[r]` (cut on `align`-row boundaries,
+    contiguous, in rank order).  For HOST-resident columns the right weights are the ranks' measured host->device copy
+    rates: GPUs behind a shared PCIe uplink copy slower when all links are busy (23 vs 35 GB/s per GPU on the 8-GPU boxes
+    measured here), and an even split makes everyone wait for the slowest link."""
+    world = len(weights)
+    if world < 1 or align < 1 or any(not (w > 0) for w in weights):
+        raise KernelError("InvalidArguments", "weights must be positive, one per rank")
+    units = (n_rows + align - 1) // align
+    total = float(sum(weights))
+    cuts, acc = [0], 0.0
+    for r in range(world - 1):
+        acc += weights[r]
+        cuts.append(min(units, max(cuts[-1], int(round(units * acc / total)))))
+    cuts.append(units)
+    out = []
+    for r in range(world):
+        off = min(cuts[r] * align, n_rows)
+        end = min(cuts[r + 1] * align, n_rows)
+        out.append((off, end - off))
+    return out
+
+
 def rebalance_plan(rows: Sequence[int], align: int = 64) -> Tuple[List[List[Tuple[int, int, int]]], List[Tuple[int, int]]]:
     """Who sends which rows to whom when the shards of one column (rank order = row order, `rows[r]` rows on rank r) are
     re-cut into the even contiguous windows of `shard_rows` — the multi-GPU form of SuperArray::rechunk

@@ -33,6 +33,23 @@ def test_shard_rows_word_aligned():
                 pos += ln
 
 
+def test_shard_rows_weighted_is_contiguous_aligned_and_proportional():
+    for n in (0, 1, 63, 1000, 1_000_000_007):
+        for w in ([1.0], [1, 1], [23.2, 23.2, 23.2, 23.2, 35.2, 35.2, 35.2, 35.2], [1e-3, 5, 2]):
+            parts = sh.shard_rows_weighted(n, w)
+            assert sum(l for _, l in parts) == n and len(parts) == len(w)
+            pos = 0
+            for off, ln in parts:
+                assert off == pos and (off % 64 == 0 or ln == 0)
+                pos += ln
+            if n > 10_000:
+                for (off, ln), wi in zip(parts, w):
+                    assert abs(ln / n - wi / sum(w)) < 1e-3
+    assert sh.shard_rows_weighted(1 << 20, [1, 1, 1, 1]) == sh.shard_rows(1 << 20, 4)
+    with pytest.raises(sh.KernelError):
+        sh.shard_rows_weighted(10, [1, 0])
+
+
 def test_combine_partials_matches_whole_column():
     rng = np.random.default_rng(5)
     for dt in (np.int64, np.uint32, np.int32, np.float64, np.float32):
