@@ -23,14 +23,17 @@ echo "== ncu full: reduce (the bench's kernel: exchange form, world 1)"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:reduce_stats_kernel -s 30 -c 2 -f -o $OUT/prof_reduce \
     python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-secondary > $OUT/ncu_reduce.log 2>&1
 tail -2 $OUT/ncu_reduce.log
+ncu -i $OUT/prof_reduce.ncu-rep --page raw --csv > $OUT/prof_reduce_raw.csv 2>/dev/null; rm -f $OUT/prof_reduce.ncu-rep
 echo "== ncu full: ew f64 masked add / batched kernels (configs[2], configs[4])"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"ew_binary_kernel|batch_kernel" -s 6 -c 6 -f -o $OUT/prof_ew \
     python bench.py --steps 3 --warmup 3 --rows 67108864 --no-e2e --no-cpu > $OUT/ncu_ew.log 2>&1
 tail -2 $OUT/ncu_ew.log
+ncu -i $OUT/prof_ew.ncu-rep --page raw --csv > $OUT/prof_ew_raw.csv 2>/dev/null; rm -f $OUT/prof_ew.ncu-rep
 echo "== ncu full: packed u8 division + 8-bit power table + f64 power"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:ew_binary_kernel -c 12 -f -o $OUT/prof_narrow \
     python tools/dtype_matrix.py --only "div two,pow" --dtypes uint8,int8,float64 --gib 0.25 --iters 1 --out $OUT/ncu_narrow_matrix.md > $OUT/ncu_narrow.log 2>&1
 tail -2 $OUT/ncu_narrow.log
+ncu -i $OUT/prof_narrow.ncu-rep --page raw --csv > $OUT/prof_narrow_raw.csv 2>/dev/null; rm -f $OUT/prof_narrow.ncu-rep
 if [ -z "$NOSAN" ]; then
 python -c "import sys; sys.path.insert(0,'tests'); from test_cpp_host import build_cpp; build_cpp()"
 : > $OUT/sanitizer.txt
@@ -43,4 +46,4 @@ for exe in tests/cpp/test_reference_kats tests/cpp/test_container_routes "tests/
   done
 done
 fi
-ls -la $OUT | tail -30
+du -sh $OUT; ls -la $OUT | tail -40

@@ -47,9 +47,16 @@ def main():
                 f.write(f"| {len(v)} | {sum(v)/len(v):.1f} | {sum(v)/tot:.3f} | {g} | {b} | `{k[:140]}` |\n")
     traffic = {}
     md = [f"# {tag}: ncu --set full captures (per launch)\n"]
-    for rep in sorted(glob.glob(os.path.join(d, "*.ncu-rep"))):
-        name = os.path.splitext(os.path.basename(rep))[0]
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # .ncu-rep files brought back from the box, or — when they were too big to travel — their `--page raw --csv` export
+    # made on the box (tools/gpu_r02_final.sh writes <name>_raw.csv and deletes the report)
+    reps = sorted(glob.glob(os.path.join(d, "*.ncu-rep"))) + sorted(glob.glob(os.path.join(d, "prof_*_raw.csv")))
+    for rep in reps:
+        if rep.endswith(".csv"):
+            name = os.path.basename(rep)[:-len("_raw.csv")]
+            raw = open(rep).read()
+        else:
+            name = os.path.splitext(os.path.basename(rep))[0]
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         open(f"profiles/{tag}_{name}_raw.csv", "w").write(raw)
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
