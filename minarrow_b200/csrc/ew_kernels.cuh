@@ -229,38 +229,59 @@ template <int ESZ> __device__ __forceinline__ uint32_t lane_valid_to_bits(uint32
     else { const uint32_t x = m & 0x00010001u; return (x | (x >> 15)) & 3u; }
 }
 
+// A broadcast scalar divisor (the same value in every lane): its magnitude, sign mask and reciprocal are computed once
+// per thread, outside the loops, and a row costs one PRMT, FADD, FMUL and FADD.RZ.
+struct PackedDivisor {
+    uint32_t ra;    // |r| in every lane
+    uint32_t sr;    // 0xFF.. in every lane iff r < 0
+    float rc;       // MUFU.RCP(|r|): the same instruction on the same operand as the two-column path -> the same bits
+};
+template <int ESZ, bool SIGNED> __device__ __forceinline__ PackedDivisor packed_divisor(uint32_t sword) {
+    constexpr uint32_t ONE = ESZ == 1 ? 0x01010101u : 0x00010001u;
+    PackedDivisor d;
+    d.sr = SIGNED ? lane_neg_mask<ESZ>(sword) : 0u;
+    d.ra = SIGNED ? (sword ^ d.sr) + (d.sr & ONE) : sword;
+    const float fb = __fsub_rn(lane_biased<ESZ, 0>(d.ra), 8388608.0f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(d.rc) : "f"(fb));
+    return d;
+}
+
 // One 32-bit word of lanes.  `vm` (in/out): lanes that are valid on input -> lanes valid on output (zero divisors removed).
-template <int ESZ, bool SIGNED, int OP>
-__device__ __forceinline__ uint32_t packed_div_word(uint32_t lw, uint32_t rw, uint32_t& vm) {
+// SCALAR_R: the divisor is the broadcast scalar `ds` (rw is ignored).
+template <int ESZ, bool SIGNED, int OP, bool SCALAR_R = false>
+__device__ __forceinline__ uint32_t packed_div_word(uint32_t lw, uint32_t rw, uint32_t& vm, const PackedDivisor& ds = PackedDivisor{}) {
     constexpr int EPW = 4 / ESZ;
-    uint32_t sl = 0, sq = 0, la = lw, ra = rw;
+    uint32_t sl = 0, sq = 0, la = lw, ra = SCALAR_R ? ds.ra : rw;
     if constexpr (SIGNED) {
         sl = lane_neg_mask<ESZ>(lw);
-        const uint32_t sr = lane_neg_mask<ESZ>(rw);
+        const uint32_t sr = SCALAR_R ? ds.sr : lane_neg_mask<ESZ>(rw);
         sq = sl ^ sr;
         // |x| = (x ^ s) + 1 in negative lanes: ~x <= 2^(bits-1) - 1 there, so the increment never carries into the next lane
         constexpr uint32_t ONE = ESZ == 1 ? 0x01010101u : 0x00010001u;
         la = (lw ^ sl) + (sl & ONE);
-        ra = (rw ^ sr) + (sr & ONE);
+        if constexpr (!SCALAR_R) ra = (rw ^ sr) + (sr & ONE);
     }
     uint32_t t[EPW];
 #pragma unroll
     for (int k = 0; k < EPW; ++k) {
-        float fa, fb;
-        if (k == 0) { fa = lane_biased<ESZ, 0>(la); fb = lane_biased<ESZ, 0>(ra); }
-        else if (k == 1) { fa = lane_biased<ESZ, 1>(la); fb = lane_biased<ESZ, 1>(ra); }
-        else if (k == 2) { fa = lane_biased<ESZ, (EPW > 2 ? 2 : 0)>(la); fb = lane_biased<ESZ, (EPW > 2 ? 2 : 0)>(ra); }
-        else { fa = lane_biased<ESZ, (EPW > 2 ? 3 : 0)>(la); fb = lane_biased<ESZ, (EPW > 2 ? 3 : 0)>(ra); }
+        float fa, fb = 0.0f;
+        if (k == 0) { fa = lane_biased<ESZ, 0>(la); if constexpr (!SCALAR_R) fb = lane_biased<ESZ, 0>(ra); }
+        else if (k == 1) { fa = lane_biased<ESZ, 1>(la); if constexpr (!SCALAR_R) fb = lane_biased<ESZ, 1>(ra); }
+        else if (k == 2) { fa = lane_biased<ESZ, (EPW > 2 ? 2 : 0)>(la); if constexpr (!SCALAR_R) fb = lane_biased<ESZ, (EPW > 2 ? 2 : 0)>(ra); }
+        else { fa = lane_biased<ESZ, (EPW > 2 ? 3 : 0)>(la); if constexpr (!SCALAR_R) fb = lane_biased<ESZ, (EPW > 2 ? 3 : 0)>(ra); }
         fa = __fsub_rn(fa, 8388607.5f);   // |l| + 0.5, exact
-        fb = __fsub_rn(fb, 8388608.0f);   // |r|, exact
         float rc;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fb));
+        if constexpr (SCALAR_R) rc = ds.rc;
+        else {
+            fb = __fsub_rn(fb, 8388608.0f);   // |r|, exact
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fb));
+        }
         t[k] = __float_as_uint(__fadd_rz(__fmul_rn(fa, rc), 8388608.0f));
     }
     uint32_t uq;
     if constexpr (ESZ == 1) uq = __byte_perm(__byte_perm(t[0], t[1], 0x0040), __byte_perm(t[2], t[3], 0x0040), 0x5410);
     else uq = __byte_perm(t[0], t[1], 0x5410);
-    vm &= lane_nonzero_mask<ESZ>(rw);
+    if constexpr (!SCALAR_R) vm &= lane_nonzero_mask<ESZ>(rw);   // a scalar divisor on this path is non-zero by construction (api.cu)
     if constexpr (OP == MNR_DIV && !SIGNED) return uq;
     if constexpr (OP == MNR_FLOORDIV && !SIGNED) return uq;
     constexpr uint32_t ONE = ESZ == 1 ? 0x01010101u : 0x00010001u;
@@ -272,9 +293,9 @@ __device__ __forceinline__ uint32_t packed_div_word(uint32_t lw, uint32_t rw, ui
 }
 
 // One vector (NW words); returns the output validity bits of its lanes (MASKED) / whether a zero divisor was met (dense).
-template <int ESZ, bool SIGNED, int OP, bool MASKED, int NW>
+template <int ESZ, bool SIGNED, int OP, bool MASKED, int NW, bool SCALAR_NZ = false>
 __device__ __forceinline__ uint32_t packed_div_vec(const uint32_t (&a)[NW], bool has_a, const uint32_t (&b)[NW], bool has_b, uint32_t sword,
-                                                   uint32_t bits, uint32_t (&o)[NW]) {
+                                                   uint32_t bits, uint32_t (&o)[NW], const PackedDivisor& ds = PackedDivisor{}) {
     constexpr int EPW = 4 / ESZ;
     uint32_t even = 0, odd = 0, ob = 0;
     if constexpr (MASKED && ESZ == 1) { even = bits & 0x0F0F0F0Fu; odd = (bits >> 4) & 0x0F0F0F0Fu; }
@@ -285,7 +306,9 @@ __device__ __forceinline__ uint32_t packed_div_vec(const uint32_t (&a)[NW], bool
             if constexpr (ESZ == 1) vm = ((__byte_perm((j & 1) ? odd : even, 0u, 0x4440u | (uint32_t)(j >> 1)) * 0x00204081u) & 0x01010101u) * 0xFFu;
             else vm = expand_valid_word<ESZ>(bits >> (j * EPW));
         }
-        const uint32_t r = packed_div_word<ESZ, SIGNED, OP>(has_a ? a[j] : sword, has_b ? b[j] : sword, vm);
+        uint32_t r;
+        if (SCALAR_NZ) r = packed_div_word<ESZ, SIGNED, OP, true>(a[j], 0u, vm, ds);
+        else r = packed_div_word<ESZ, SIGNED, OP>(has_a ? a[j] : sword, has_b ? b[j] : sword, vm);
         if constexpr (MASKED) { o[j] = r & vm; ob |= lane_valid_to_bits<ESZ>(vm) << (j * EPW); }
         else { o[j] = r; ob |= ~vm; }   // dense: any zero divisor raises the flag (the reference panics)
     }
@@ -465,6 +488,13 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
     const uint32_t sword = sizeof(T) == 1 ? (uint32_t)(uint8_t)a.scalar_bits * 0x01010101u : (uint32_t)(uint16_t)a.scalar_bits * 0x00010001u;
     const DivMagic dm = a.magic;
     bool div0 = false;
+    // packed division by a non-zero broadcast scalar on the right: magnitude, sign and reciprocal of the divisor, once
+    bool scalar_nz = false;
+    PackedDivisor pds{};
+    if constexpr (PACKED_DIV) {
+        scalar_nz = rp == nullptr && lp != nullptr && (sizeof(T) == 1 ? (uint8_t)a.scalar_bits != 0 : (uint16_t)a.scalar_bits != 0);
+        if (scalar_nz) pds = packed_divisor<(sizeof(T) <= 2 ? (int)sizeof(T) : 1), Traits<T>::is_signed>(sword);
+    }
 
     for (uint64_t t = gwarp; t < ntiles; t += warps) {
         const uint64_t v0 = t * WTILE + lane;
@@ -507,7 +537,11 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
                 const bool ha = lp != nullptr, hb = rp != nullptr;
                 const uint32_t vb = MASKED ? mb[u] : 0u;
                 uint32_t r;
-                if (op == MNR_DIV) r = packed_div_vec<ESZ, SG, MNR_DIV, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
+                if (scalar_nz) {   // column (op) non-zero scalar: the divisor's reciprocal lives in registers (kernel-uniform branch)
+                    if (op == MNR_DIV) r = packed_div_vec<ESZ, SG, MNR_DIV, MASKED, NW, true>(PL.w, true, PR.w, false, sword, vb, PO.w, pds);
+                    else if (op == MNR_REM) r = packed_div_vec<ESZ, SG, MNR_REM, MASKED, NW, true>(PL.w, true, PR.w, false, sword, vb, PO.w, pds);
+                    else r = packed_div_vec<ESZ, SG, MNR_FLOORDIV, MASKED, NW, true>(PL.w, true, PR.w, false, sword, vb, PO.w, pds);
+                } else if (op == MNR_DIV) r = packed_div_vec<ESZ, SG, MNR_DIV, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
                 else if (op == MNR_REM) r = packed_div_vec<ESZ, SG, MNR_REM, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
                 else r = packed_div_vec<ESZ, SG, MNR_FLOORDIV, MASKED, NW>(PL.w, ha, PR.w, hb, sword, vb, PO.w);
                 O.v = PO.v;
