@@ -199,3 +199,74 @@ pub fn chunk_stats<'c, T: B200Dtype>(ctx: &'c Context, chunks: &[(&DeviceBuffer<
     check(unsafe { ffi::mnr_agg_combine(T::CODE, parts.as_ptr() as *const ffi::mnr_agg, chunks.len(), out.as_mut_ptr()) })?;
     Ok(unsafe { out.assume_init() })
 }
+
+// ---- SuperArray / SuperTable over all GPUs of the box, from one process (include/minarrow_b200.h "sharding") ----------------
+
+/// All GPUs of the box: one context + NVLink mailbox per device (`mnr_group`).  Chunk `i` of `n` lives on rank
+/// `floor(i * G / n)` (`mnr_shard_owner`) — contiguous blocks, so the SuperArray re-assembles with the same chunk
+/// boundaries (src/structs/chunked/super_array.rs:96-103).
+pub struct Group { h: *mut ffi::mnr_group, world: usize }
+unsafe impl Send for Group {}
+
+/// One chunk resident on its owning GPU (values + optional validity).  Freed with the group's per-rank context.
+pub struct ShardedChunk { buf: *mut ffi::mnr_buf, validity: *mut ffi::mnr_bits }
+impl Drop for ShardedChunk {
+    fn drop(&mut self) { unsafe { ffi::mnr_buf_free(self.buf); ffi::mnr_bits_free(self.validity) } }
+}
+
+impl Group {
+    /// `devices = None`: devices 0..world-1.
+    pub fn new(world: usize, devices: Option<&[i32]>) -> Result<Self, KernelError> {
+        let mut h = core::ptr::null_mut();
+        let dv: Option<Vec<c_int>> = devices.map(|d| d.iter().map(|&x| x as c_int).collect());
+        check(unsafe { ffi::mnr_group_create(world as c_int, dv.as_ref().map_or(core::ptr::null(), |v| v.as_ptr()), &mut h) })?;
+        Ok(Self { h, world })
+    }
+    pub fn world(&self) -> usize { self.world }
+    pub fn owner(&self, chunk: usize, n_chunks: usize) -> usize { unsafe { ffi::mnr_shard_owner(chunk, n_chunks, self.world as c_int) as usize } }
+
+    /// `SuperArray -> shards`: chunk i is uploaded to its owner, all PCIe links copying at once.
+    pub fn upload<T: B200Dtype>(&self, chunks: &[(&[T], Option<&Bitmask>)]) -> Result<Vec<ShardedChunk>, KernelError> {
+        let n = chunks.len();
+        let ptrs: Vec<*const c_void> = chunks.iter().map(|(d, _)| d.as_ptr() as *const c_void).collect();
+        let lens: Vec<usize> = chunks.iter().map(|(d, _)| d.len()).collect();
+        let masks: Vec<*const u8> = chunks.iter().map(|(_, m)| m.map_or(core::ptr::null(), |m| m.bits.as_ptr())).collect();
+        let mut bufs = vec![core::ptr::null_mut(); n];
+        let mut vals = vec![core::ptr::null_mut(); n];
+        check(unsafe { ffi::mnr_group_upload(self.h, T::CODE, n, ptrs.as_ptr(), lens.as_ptr(), masks.as_ptr(), bufs.as_mut_ptr(), vals.as_mut_ptr()) })?;
+        Ok(bufs.into_iter().zip(vals).map(|(buf, validity)| ShardedChunk { buf, validity }).collect())
+    }
+
+    /// `lhs[i] op rhs[i]` on the GPU that owns chunk pair i (route_super_array_broadcast, src/kernels/broadcast/super_array.rs:180-249:
+    /// validity = union of the two chunks' masks, fused into the kernel); one batched launch per device, no communication.
+    pub fn ew_binary(&self, op: ArithmeticOperator, lhs: &[ShardedChunk], rhs: &[ShardedChunk]) -> Result<Vec<ShardedChunk>, KernelError> {
+        let n = lhs.len();
+        let l: Vec<*const ffi::mnr_buf> = lhs.iter().map(|c| c.buf as *const _).collect();
+        let r: Vec<*const ffi::mnr_buf> = rhs.iter().map(|c| c.buf as *const _).collect();
+        let lm: Vec<*const ffi::mnr_bits> = lhs.iter().map(|c| c.validity as *const _).collect();
+        let rm: Vec<*const ffi::mnr_bits> = rhs.iter().map(|c| c.validity as *const _).collect();
+        let mut ob = vec![core::ptr::null_mut(); n];
+        let mut om = vec![core::ptr::null_mut(); n];
+        check(unsafe { ffi::mnr_group_ew_binary(self.h, op as c_int, n, l.as_ptr(), r.as_ptr(), lm.as_ptr(), rm.as_ptr(), ffi::MNR_MASK_OR,
+                                                ob.as_mut_ptr(), om.as_mut_ptr()) })?;
+        Ok(ob.into_iter().zip(om).map(|(buf, validity)| ShardedChunk { buf, validity }).collect())
+    }
+
+    /// Per-column {sum, min, max, count} of a sharded SuperTable (`columns[c]` = column c's chunks across the batches): batched
+    /// kernels on every GPU, per-column fold + NVLink mailbox exchange in the kernel that finishes last, rank-order combine —
+    /// one call, no NCCL, identical bits on every rank (benches/benchmark_parallel_simd.rs:81-97 over super_table.rs:38-73).
+    pub fn column_stats(&self, columns: &[(c_int, &[ShardedChunk])]) -> Result<Vec<ffi::mnr_agg>, KernelError> {
+        let mut bufs = Vec::new();
+        let mut vals = Vec::new();
+        let mut col = Vec::new();
+        for (c, (_, chunks)) in columns.iter().enumerate() {
+            for ch in chunks.iter() { bufs.push(ch.buf as *const ffi::mnr_buf); vals.push(ch.validity as *const ffi::mnr_bits); col.push(c as u32); }
+        }
+        let dts: Vec<c_int> = columns.iter().map(|(dt, _)| *dt).collect();
+        let mut out = vec![core::mem::MaybeUninit::<ffi::mnr_agg>::uninit(); columns.len()];
+        check(unsafe { ffi::mnr_group_reduce_stats(self.h, bufs.len(), bufs.as_ptr(), vals.as_ptr(), 1, columns.len(), col.as_ptr(), dts.as_ptr(),
+                                                   out.as_mut_ptr() as *mut ffi::mnr_agg) })?;
+        Ok(out.into_iter().map(|a| unsafe { a.assume_init() }).collect())
+    }
+}
+impl Drop for Group { fn drop(&mut self) { unsafe { ffi::mnr_group_destroy(self.h) } } }

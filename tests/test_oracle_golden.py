@@ -243,3 +243,38 @@ def test_par_masked_sum_matches_stats():
     assert orc.par_masked_sum_i64(d, V, threads=4) == (st["sum"], st["count"])
     with np.errstate(over="ignore"):
         assert st["sum"] == int(np.where(valid, d, 0).sum(dtype=np.int64))
+
+
+def test_array_superarray_rechunk_route_of_the_oracle():
+    """oracle.create_aligned_chunks_from_array / broadcast_array_superarray restate src/utils.rs:367-481 and
+    src/kernels/broadcast/mod.rs:1351-1361.  The reference's tests for these arms carry no null masks, so the mask rules are
+    pinned here on hand-worked literals (the same ones tests/cpp/test_container_routes.cpp runs on the GPU): chunk i is valid
+    where array_mask[window i] | chunk_mask[i]; a chunk WITHOUT a mask next to one with a mask is all valid in the union;
+    with no chunk masks at all the array's own window is used; no masks anywhere -> dense."""
+    B = orc.Bits.from_bools
+    arr = np.array([1, 2, 3, 4, 5, 6, 7], dtype=np.int32)
+    am = B([True, False, True, True, False, False, True])
+    sa = [(np.array([10, 20, 30], np.int32), B([False, False, True])), (np.array([40, 50, 60, 70], np.int32), None)]
+    out = orc.broadcast_array_superarray(orc.ADD, arr, am, sa, True)
+    assert out[0][0].tolist() == [11, 0, 33] and out[0][1].to_bools().tolist() == [True, False, True]
+    assert out[1][0].tolist() == [44, 55, 66, 77] and out[1][1].to_bools().all()
+    out = orc.broadcast_array_superarray(orc.SUB, arr, am, sa, False)          # SuperArray - Array
+    assert out[0][0].tolist() == [9, 0, 27] and out[1][0].tolist() == [36, 45, 54, 63]
+    plain = [(np.array([10, 20, 30], np.int32), None), (np.array([40, 50, 60, 70], np.int32), None)]
+    out = orc.broadcast_array_superarray(orc.MUL, arr, am, plain, True)         # no chunk masks: the array's windows
+    assert out[0][0].tolist() == [10, 0, 90] and out[1][0].tolist() == [160, 0, 0, 490]
+    assert out[1][1].to_bools().tolist() == [True, False, False, True]
+    out = orc.broadcast_array_superarray(orc.ADD, arr, None, plain, True)       # no masks anywhere
+    assert out[1][0].tolist() == [44, 55, 66, 77] and out[1][1] is None
+    al = orc.create_aligned_chunks_from_array(arr, am, sa)
+    assert [len(d) for d, _ in al] == [3, 4] and al[1][0].tolist() == [4, 5, 6, 7]
+    assert al[0][1].to_bools().tolist() == [True, False, True] and al[1][1].to_bools().all()
+    with pytest.raises(orc.KernelError):
+        orc.create_aligned_chunks_from_array(arr[:3], None, sa)
+    with pytest.raises(orc.KernelError):                                        # mask lengths must match for the union
+        orc.union_array_superarray_masks(B([True] * 6), sa)
+    # the SuperArray route itself: union of the chunk masks, or the one present, or none (super_array.rs:214-230)
+    r = orc.route_super_array_broadcast(orc.ADD, [(np.array([1, 2], np.int32), B([True, False]))], [(np.array([5, 5], np.int32), B([False, False]))])
+    assert r[0][0].tolist() == [6, 0] and r[0][1].to_bools().tolist() == [True, False]
+    with pytest.raises(orc.KernelError):
+        orc.route_super_array_broadcast(orc.ADD, [(np.array([1, 2], np.int32), None)], [(np.array([5], np.int32), None)])
