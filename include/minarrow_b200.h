@@ -106,7 +106,7 @@ void* mnr_ctx_stream(const mnr_ctx* ctx);
 /* Number of kernels of this library launched through `ctx` so far. */
 uint64_t mnr_ctx_launch_count(const mnr_ctx* ctx);
 /* Per-context options; contexts are independent (a knob set on one never changes another's launches).
- *   "ew_grid_cap", "ew_max_tier", "ew_sdiv64_cfg", "ew_fdiv_cfg", "ew_heavy_cfg": launch geometry of the element-wise
+ *   "ew_grid_cap", "ew_max_tier", "ew_sdiv64_cfg", "ew_fdiv_cfg", "ew_heavy_cfg", "ew_cheap8_cfg": launch geometry of the element-wise
  *       kernels for tuning sweeps — results never depend on them;
  *   "host_chunk_rows": rows per staging chunk of the host-slice drop-ins (multiple of 1024; default 4 Mi).  A float sum
  *       through mnr_stats_host folds one partial per staging chunk in chunk order, so its bits depend on this value

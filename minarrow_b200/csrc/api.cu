@@ -173,6 +173,7 @@ int mnr_ctx_set_option(mnr_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "ew_sdiv64_cfg")) { c->knobs.sdiv64_cfg = (int)value; return MNR_OK; }
     if (!strcmp(key, "ew_fdiv_cfg")) { c->knobs.fdiv_cfg = (int)value; return MNR_OK; }
     if (!strcmp(key, "ew_heavy_cfg")) { c->knobs.heavy_cfg = (int)value; return MNR_OK; }
+    if (!strcmp(key, "ew_cheap8_cfg")) { c->knobs.cheap8_cfg = (int)value; return MNR_OK; }
     if (!strcmp(key, "reduce_overlap")) { c->reduce_overlap = value != 0; return MNR_OK; }
     if (!strcmp(key, "host_chunk_rows")) {
         REQUIRE(value >= 1024 && value % 1024 == 0, MNR_ERR_INVALID_ARGUMENTS, "host_chunk_rows must be a multiple of 1024");

@@ -43,6 +43,7 @@ struct CfgFdiv3 { static constexpr int BLOCK = 256, U = 2, MINB = 3; static cons
 struct CfgPow4 { static constexpr int BLOCK = 128, U = 1, MINB = 6; static constexpr bool RESIDENT = false; using Wide = V32; };
 struct CfgPow5 { static constexpr int BLOCK = 128, U = 2, MINB = 4; static constexpr bool RESIDENT = false; using Wide = V32; };
 
+
 static EwDev to_dev(const EwArgs& a) {
     EwDev d;
     d.lhs = a.lhs; d.rhs = a.rhs; d.scalar_bits = a.scalar_bits; d.lmask = a.lmask; d.rmask = a.rmask;
@@ -165,7 +166,20 @@ static cudaError_t go_t(const EwArgs& a, cudaStream_t s) {
         }
     }
     switch (op_class(Traits<T>::is_float, a.op)) {
-        case CLS_CHEAP: return go_align<T, T, T, CLS_CHEAP>(a, s);
+        case CLS_CHEAP:
+            if constexpr (sizeof(T) == 1) {
+                // Masked add / sub / mul on 1-byte columns.  At CfgCheap's 4 x 256-bit per thread the kernel holds 128
+                // registers (16 warps per SM) and each warp alternates between a long load phase and 150 instructions of
+                // lane work: ncu (profiles/r02k_u8_masked_add_ncu.md) shows 20 % issue utilisation, 23 % warps active,
+                // DRAM 63 %.  Two 256-bit loads per thread at <= 85 registers keep 24 warps resident and lift array (+)
+                // array with two masks from 5.2 to 6.9-7.0 TB/s; array (+) scalar is a little faster as it was.
+                // ew_cheap8_cfg: 0 = this choice, 1 = CfgCheap, 2 / 3 = CfgFdiv2 / CfgFdiv3.
+                int cfg = a.k.cheap8_cfg;
+                if (cfg == 0) cfg = (a.lhs && a.rhs) ? 2 : 1;
+                if (cfg == 2 && (a.lmask || a.rmask)) return go_align<T, T, T, CLS_CHEAP, CfgFdiv2>(a, s);
+                if (cfg == 3 && (a.lmask || a.rmask)) return go_align<T, T, T, CLS_CHEAP, CfgFdiv3>(a, s);
+            }
+            return go_align<T, T, T, CLS_CHEAP>(a, s);
         case CLS_DIV:
             if constexpr (Traits<T>::is_float) {
                 // ew_fdiv_cfg: 0 = the table above, 1 = CfgHeavy, 2 / 3 = force CfgFdiv2 / CfgFdiv3

@@ -396,6 +396,19 @@ __device__ __forceinline__ void store_valid_bits(uint8_t* __restrict__ out_mask,
         for (int s = 1; s < LPB; s <<= 1) x |= __shfl_down_sync(0xffffffffu, x, s) << (VEC * s);
         if (((threadIdx.x & 31) % LPB) == 0 && row0 < n) out_mask[row0 >> 3] = (uint8_t)x;
     } else {
+        // 16 / 32 rows per lane (2- and 1-byte columns): one 16- / 32-bit store when the lane's rows are all inside the column
+        // and the address allows it (row0 is a multiple of VEC, so only the base pointer matters) — four byte stores per
+        // lane were a visible share of the LSU work of the 1-byte kernels
+        uint8_t* p = out_mask + (row0 >> 3);
+        if (row0 + VEC <= n && (reinterpret_cast<uintptr_t>(p) & (VEC / 8 - 1)) == 0) {
+            if constexpr (VEC == 32) *reinterpret_cast<uint32_t*>(p) = bits;
+            else if constexpr (VEC == 16) *reinterpret_cast<uint16_t*>(p) = (uint16_t)bits;
+            else {
+#pragma unroll
+                for (int j = 0; j < VEC / 8; ++j) p[j] = (uint8_t)(bits >> (8 * j));
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < VEC / 8; ++j)
             if (row0 + 8ull * j < n) out_mask[(row0 >> 3) + j] = (uint8_t)(bits >> (8 * j));

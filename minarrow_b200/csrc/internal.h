@@ -45,6 +45,7 @@ struct EwKnobs {
     int sdiv64_cfg = 0;   // geometry of 64-bit column / scalar (elementwise.cu CfgSdiv64)
     int fdiv_cfg = 0;     // geometry of float Div / FloorDiv (CfgFdiv2 / CfgFdiv3)
     int heavy_cfg = 0;    // geometry of integer Div/Rem/FloorDiv, float Rem, Power
+    int cheap8_cfg = 0;   // geometry of masked add / sub / mul on 1-byte columns
 };
 struct EwArgs {
     mnr_dtype dtype;
