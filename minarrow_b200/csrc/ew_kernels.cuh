@@ -358,6 +358,78 @@ __device__ __forceinline__ void packed_pow8_vec(const uint8_t* __restrict__ lut,
     }
 }
 
+// ---- 16-bit integer Power: square-and-multiply with a thread-uniform trip count -------------------------------------------
+// The per-element loop of int_elem ran ~80 instructions per row on 16-bit columns (r02z: 2.8 TB/s, 0.435 of the copy peak):
+// every row has its own `while (e)`, so a warp replays the loop body for each distinct bit length, each product is narrowed
+// back to 16 bits, and the operands are extracted and sign-extended one by one.  Here the exponent bits are tested in place
+// in the packed operand word (bit t of the low lane, bit t + 16 of the high lane), the products run in 32-bit registers without
+// narrowing (the low 16 bits of a product depend on the low 16 bits of the factors only; the high lane is `word >> 16`), and
+// the loop runs max-bit-length-of-the-vector times for all 16 rows of a thread: 2 IMAD + 1 LOP3 per row and bit.
+// A negative exponent is `rhs.to_u32().unwrap_or(0)` = 0 (std.rs:67) -> 1.
+template <bool SIGNED, bool MASKED, int NW>
+__device__ __forceinline__ void packed_pow16_vec(const uint32_t (&a)[NW], bool has_a, const uint32_t (&b)[NW], bool has_b, uint32_t sword,
+                                                 uint32_t bits, uint32_t (&o)[NW]) {
+    constexpr int CW = NW < 4 ? NW : 4;   // four words (8 rows) per loop: 5 live registers per word, the tile's other operands stay in registers
+#pragma unroll
+    for (int c = 0; c < NW; c += CW) {
+        uint32_t ew[CW], blo[CW], bhi[CW], alo[CW], ahi[CW];
+        uint32_t any = 0;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            uint32_t e = has_b ? b[c + j] : sword;
+            if constexpr (SIGNED) e &= ~lane_neg_mask<2>(e);
+            ew[j] = e;
+            any |= e;
+            const uint32_t lw = has_a ? a[c + j] : sword;
+            blo[j] = lw;
+            bhi[j] = lw >> 16;
+            alo[j] = 1u;
+            ahi[j] = 1u;
+        }
+        any = (any | (any >> 16)) & 0xFFFFu;
+        uint32_t mlo = 1u, mhi = 0x10000u;
+        while (any) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                if (ew[j] & mlo) alo[j] *= blo[j];
+                blo[j] *= blo[j];
+                if (ew[j] & mhi) ahi[j] *= bhi[j];
+                bhi[j] *= bhi[j];
+            }
+            mlo <<= 1;
+            mhi <<= 1;
+            any >>= 1;
+        }
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            uint32_t w = __byte_perm(alo[j], ahi[j], 0x5410);
+            if constexpr (MASKED) w &= expand_valid_word<2>(bits >> ((c + j) * 2));
+            o[c + j] = w;
+        }
+    }
+}
+
+// 32 / 64-bit integer Power of one vector: the same thread-uniform loop (no per-row divergence), exponents shifted in place.
+template <typename T> __device__ __forceinline__ uint32_t pow_exponent(T r) {   // rhs.to_u32().unwrap_or(0), std.rs:67
+    if constexpr (std::is_signed<T>::value) return (r < 0 || (uint64_t)r > 0xFFFFFFFFull) ? 0u : (uint32_t)r;
+    else return ((uint64_t)r > 0xFFFFFFFFull) ? 0u : (uint32_t)r;
+}
+template <typename UT, int VEC>
+__device__ __forceinline__ void int_pow_vec(UT (&base)[VEC], uint32_t (&e)[VEC], UT (&acc)[VEC]) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { any |= e[k]; acc[k] = 1; }
+    while (any) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            if (e[k] & 1u) acc[k] = (UT)(acc[k] * base[k]);
+            base[k] = (UT)(base[k] * base[k]);
+            e[k] >>= 1;
+        }
+        any >>= 1;
+    }
+}
+
 template <typename T, int CLS>
 __device__ __forceinline__ T elem(int op, T l, T r, bool& ok, const DivMagic& dm) {
     if constexpr (Traits<T>::is_float) { ok = true; return float_elem<T, CLS>(op, l, r); }
@@ -496,6 +568,11 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
     // ... and Power of 1-byte columns (packed_pow8_vec above: one shared-memory table lookup per row).
     constexpr bool PACKED_POW = CLS == CLS_POW && !Traits<T>::is_float && sizeof(T) == 1 && std::is_same<TL, T>::value &&
                                 std::is_same<TR, T>::value && sizeof(VecT) >= 16;
+    // ... Power of 2-byte columns (packed_pow16_vec) and of 4 / 8-byte columns (int_pow_vec): thread-uniform square-and-multiply.
+    constexpr bool PACKED_POW16 = CLS == CLS_POW && !Traits<T>::is_float && sizeof(T) == 2 && std::is_same<TL, T>::value &&
+                                  std::is_same<TR, T>::value && sizeof(VecT) >= 16;
+    constexpr bool VEC_POW = CLS == CLS_POW && !Traits<T>::is_float && sizeof(T) >= 4 && std::is_same<TL, T>::value &&
+                             std::is_same<TR, T>::value;
     __shared__ uint8_t pow_lut[PACKED_POW ? 128 * kPowLutRow : 1];
     if constexpr (PACKED_POW) build_pow8_lut<BLOCK>(pow_lut);
     const uint32_t sword = sizeof(T) == 1 ? (uint32_t)(uint8_t)a.scalar_bits * 0x01010101u : (uint32_t)(uint16_t)a.scalar_bits * 0x00010001u;
@@ -568,6 +645,27 @@ __device__ __forceinline__ void ew_binary_body(const EwDev& a) {
                 packed_pow8_vec<Traits<T>::is_signed, MASKED, NW>(pow_lut, PL.w, lp != nullptr, PR.w, rp != nullptr, sword, MASKED ? mb[u] : 0u, PO.w);
                 O.v = PO.v;
                 if constexpr (MASKED) ob = mb[u];      // Power never nulls a row: output validity = merged input validity
+            } else if constexpr (PACKED_POW16) {
+                constexpr int NW = sizeof(VecT) / 4;
+                union { VecT v; uint32_t w[NW]; } PL, PR, PO;
+                memcpy(&PL.v, &L[u].v, sizeof(VecT));
+                memcpy(&PR.v, &R[u].v, sizeof(VecT));
+                packed_pow16_vec<Traits<T>::is_signed, MASKED, NW>(PL.w, lp != nullptr, PR.w, rp != nullptr, sword, MASKED ? mb[u] : 0u, PO.w);
+                O.v = PO.v;
+                if constexpr (MASKED) ob = mb[u];
+            } else if constexpr (VEC_POW) {
+                using UT = typename std::make_unsigned<T>::type;
+                UT base[VEC], acc[VEC];
+                uint32_t e[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    base[k] = (UT)(lp ? (T)L[u].e[k] : sval);
+                    e[k] = pow_exponent<T>(rp ? (T)R[u].e[k] : sval);
+                }
+                int_pow_vec<UT, VEC>(base, e, acc);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) O.e[k] = (!MASKED || ((mb[u] >> k) & 1u)) ? (T)acc[k] : (T)0;
+                if constexpr (MASKED) ob = mb[u];
             } else
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {

@@ -115,7 +115,7 @@ def test_every_geometry_of_masked_1byte_add_mul_matches_the_oracle(gpu_ctx, dt):
                         if mode == "or":
                             m = orc.Bits.from_bools(va[lo:lo + cnt] | vb[lo:lo + cnt])
                         else:
-                            m = orc.and_masks(ma, mb) if (l is not None and r is not None) else (l if l is not None else r)
+                            m = orc.Bits.from_bools(va[lo:lo + cnt] & vb[lo:lo + cnt]) if (l is not None and r is not None) else (l if l is not None else r)
                         exp, em = orc.apply_int(sa, sb, op, m)
                         ob, om = dev.ew_binary(gpu_ctx, op, A.slice(lo, cnt), B.slice(lo, cnt),
                                                VA if l is not None else None, VB if r is not None else None,

@@ -161,3 +161,53 @@ def test_float_remainder_is_exact_fmod(gpu_ctx, dt):
         got = dev.ew_scalar(gpu_ctx, orc.REM, mnr.DeviceBuffer.upload(gpu_ctx, a), s, lhs, None)[0].download()
         nan_e = np.isnan(exp)
         assert np.array_equal(nan_e, np.isnan(got)) and np.array_equal(exp.view(ui)[~nan_e], got.view(ui)[~nan_e])
+
+
+@pytest.mark.parametrize("dt", [np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64])
+def test_integer_power_full_exponent_range(gpu_ctx, dt):
+    """16 / 32 / 64-bit Power runs square-and-multiply with a trip count shared by the rows of one thread (ew_kernels.cuh
+    packed_pow16_vec / int_pow_vec).  Exponents over the whole range of the type — bit lengths mixed inside a vector, a lone
+    large exponent among zeros, negative ones (-> 0, std.rs:67) and, for 64-bit columns, ones beyond u32::MAX (-> 0) —
+    masked, dense, unaligned and with a scalar on either side, against the oracle; a sample is also checked against
+    Python's pow(base, e, 2^bits)."""
+    import minarrow_b200 as mnr
+    dev = mnr.device_ops
+    rng = np.random.default_rng(77)
+    info = np.iinfo(dt)
+    bits = 8 * np.dtype(dt).itemsize
+    n = 262_144 + 37
+    a = rng.integers(info.min, info.max, n, dtype=dt, endpoint=True)
+    a[::11] = rng.integers(-3 if info.min < 0 else 0, 3, a[::11].size).astype(dt)
+    nb = rng.integers(0, bits + 1, n)                                    # bit length of each exponent: uniform, so vectors mix them
+    b = (rng.integers(0, 1 << 62, n, dtype=np.int64).astype(np.uint64) * np.uint64(4) + np.uint64(3))
+    b = np.where(nb == 0, np.uint64(0), b >> (np.uint64(64) - np.maximum(nb, 1).astype(np.uint64))).astype(np.uint64)
+    b = b.astype(dt) if info.min == 0 else b.astype(np.dtype(f"u{bits // 8}")).view(dt)   # signed: top bit set = negative exponent
+    b[1000:3000] = 0
+    b[2017] = dt(info.max)                                                # a lone long exponent in a run of zeros
+    b[5000:5100] = np.arange(100).astype(dt)
+    valid = rng.random(n) < 0.8
+    A, B = mnr.DeviceBuffer.upload(gpu_ctx, a), mnr.DeviceBuffer.upload(gpu_ctx, b)
+    V = mnr.DeviceBitmask.upload(gpu_ctx, mnr.Bitmask.from_bools(valid))
+    exp, em = orc.apply_int(a, b, orc.POW, orc.Bits.from_bools(valid))
+    ob, om = dev.ew_binary(gpu_ctx, orc.POW, A, B, V, None, mnr.MaskMode.And)
+    got = ob.download()
+    assert got.tobytes() == exp.tobytes(), (dt, [(int(a[i]), int(b[i]), int(got[i]), int(exp[i])) for i in np.flatnonzero(got != exp)[:5]])
+    assert np.array_equal(om.download().bits, em.bits), dt
+    exp, _ = orc.apply_int(a, b, orc.POW, None)
+    ob, om = dev.ew_binary(gpu_ctx, orc.POW, A, B, None, None, mnr.MaskMode.And)
+    got = ob.download()
+    assert om is None and got.tobytes() == exp.tobytes(), (dt, "dense")
+    for i in rng.integers(0, n, 300):                                     # independent of the oracle's loop
+        e = int(b[i])
+        e = 0 if (e < 0 or e > 0xFFFFFFFF) else e
+        assert int(got[i]) % (1 << bits) == pow(int(a[i]), e, 1 << bits), (dt, int(a[i]), int(b[i]))
+    ob, _ = dev.ew_binary(gpu_ctx, orc.POW, A.slice(3, n - 5), B.slice(3, n - 5), None, None, mnr.MaskMode.And)
+    assert ob.download().tobytes() == orc.apply_int(a[3:-2], b[3:-2], orc.POW, None)[0].tobytes(), (dt, "unaligned")
+    for s in (info.min, 0, 1, 2, 3, 13, 1000, info.max):
+        full = np.full(n, s, dtype=dt)
+        for s_lhs in (False, True):
+            l, r = (full, b) if s_lhs else (a, full)
+            D = B if s_lhs else A
+            exp, em = orc.apply_int(l, r, orc.POW, orc.Bits.from_bools(valid))
+            ob, om = dev.ew_scalar(gpu_ctx, orc.POW, D, dt(s), s_lhs, V)
+            assert ob.download().tobytes() == exp.tobytes() and np.array_equal(om.download().bits, em.bits), (dt, int(s), s_lhs, "scalar")
