@@ -168,9 +168,12 @@ __device__ __forceinline__ void accum_vec(const VecT& v, uint32_t bits, typename
 //   * the word's 4 (or 2) validity bits are expanded to a byte (halfword) mask with one multiply-and-mask;
 //   * sum: IDP.4A / IDP.2A dot product of the masked word with 0x01..01 into a 32-bit accumulator, folded into
 //     the 64-bit sum once per vector (a vector adds at most 32 * 255 or 16 * 65535, far from 2^31);
-//   * min / max: invalid lanes are replaced by the identity with one LOP3, bytes are widened to 16-bit lanes with
-//     PRMT (sign- or zero-extending) and folded with VIMNMX3.{S,U}16x2, 16-bit columns with VIMNMX.{S,U}16x2.
-// About 3 instructions per row for an 8-bit column with min/max, 1.3 without.  Same results as the per-element
+//   * min / max: invalid lanes are replaced by the identity with one LOP3; 16-bit columns fold with VIMNMX.{S,U}16x2.
+//     8-bit columns are compared as the HIGH byte of a 16-bit lane — whatever sits in the low byte can only break ties
+//     between equal high bytes — so bytes 1 and 3 are in place in the word as it is and bytes 0 and 2 after `<< 8`:
+//     VIMNMX3.{S,U}16x2(acc, w, w << 8) takes in four rows with one shift, no widening PRMTs (four per word before:
+//     r02z had the masked 8-bit sum+min+max at 0.80 of the copy peak, ALU-pipe bound).
+// About 2.7 instructions per row for an 8-bit column with min/max, 1.3 without.  Same results as the per-element
 // path: wrapping 64-bit sums and integer min/max do not depend on the order of combination.
 template <typename T> struct NarrowState {
     static constexpr bool kSigned = Traits<T>::is_signed;
@@ -179,7 +182,9 @@ template <typename T> struct NarrowState {
     uint32_t mn2, mx2;                          // running min / max, two 16-bit lanes
     __device__ __forceinline__ void init() {
         sum = 0;
-        const uint32_t idmin = (uint16_t)(int16_t)MinMax<T>::min_identity(), idmax = (uint16_t)(int16_t)MinMax<T>::max_identity();
+        // 8-bit columns keep the running value in the high byte of each lane (see above)
+        const uint32_t idmin = sizeof(T) == 1 ? (uint32_t)(uint8_t)MinMax<T>::min_identity() << 8 : (uint16_t)(int16_t)MinMax<T>::min_identity();
+        const uint32_t idmax = sizeof(T) == 1 ? (uint32_t)(uint8_t)MinMax<T>::max_identity() << 8 : (uint16_t)(int16_t)MinMax<T>::max_identity();
         mn2 = idmin | (idmin << 16);
         mx2 = idmax | (idmax << 16);
     }
@@ -191,15 +196,6 @@ template <typename T> struct NarrowState {
     static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) {
         return kSigned ? __vimax3_s16x2(a, b, c) : __vimax3_u16x2(a, b, c);
     }
-    // bytes 0,1 / 2,3 of w widened to two 16-bit lanes (PRMT: selector bit 3 replicates the selected byte's sign)
-    // (__byte_perm ignores that bit, so this is the PTX instruction itself.)
-    static __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
-        uint32_t d;
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
-        return d;
-    }
-    static __device__ __forceinline__ uint32_t widen_lo(uint32_t w) { return prmt(w, kSigned ? 0x9180u : 0x4140u); }
-    static __device__ __forceinline__ uint32_t widen_hi(uint32_t w) { return prmt(w, kSigned ? 0xB3A2u : 0x4342u); }
 
     // One 32-bit word = EPW elements; `bits` = their validity in the low EPW bits (ignored when !MASKED).
     template <bool MASKED, bool MINMAX> __device__ __forceinline__ void add_word(uint32_t w, uint32_t bits, uint32_t& acc32) {
@@ -213,8 +209,8 @@ template <typename T> struct NarrowState {
                 const uint32_t m = s01 * 0xFFu;
                 const uint32_t wmn = kSigned ? ((w & m) | (0x7f7f7f7fu & ~m)) : (w | ~m);
                 const uint32_t wmx = kSigned ? ((w & m) | (0x80808080u & ~m)) : (w & m);
-                mn2 = min3(mn2, widen_lo(wmn), widen_hi(wmn));
-                mx2 = max3(mx2, widen_lo(wmx), widen_hi(wmx));
+                mn2 = min3(mn2, wmn, wmn << 8);
+                mx2 = max3(mx2, wmx, wmx << 8);
             }
             return;
         }
@@ -234,8 +230,8 @@ template <typename T> struct NarrowState {
             const uint32_t wmn = MASKED ? (wz | (IDMIN & ~m)) : w;
             const uint32_t wmx = MASKED ? (wz | (IDMAX & ~m)) : w;
             if constexpr (sizeof(T) == 1) {
-                mn2 = min3(mn2, widen_lo(wmn), widen_hi(wmn));
-                mx2 = max3(mx2, widen_lo(wmx), widen_hi(wmx));
+                mn2 = min3(mn2, wmn, wmn << 8);
+                mx2 = max3(mx2, wmx, wmx << 8);
             } else {
                 mn2 = min2(mn2, wmn);
                 mx2 = max2(mx2, wmx);
@@ -248,12 +244,14 @@ template <typename T> struct NarrowState {
         else sum += (uint64_t)acc32;
     }
     __device__ __forceinline__ T min_value() const {
-        if constexpr (kSigned) { const int16_t a = (int16_t)(mn2 & 0xffffu), b = (int16_t)(mn2 >> 16); return (T)(a < b ? a : b); }
-        else { const uint16_t a = (uint16_t)(mn2 & 0xffffu), b = (uint16_t)(mn2 >> 16); return (T)(a < b ? a : b); }
+        constexpr int SH = sizeof(T) == 1 ? 8 : 0;
+        if constexpr (kSigned) { const int16_t a = (int16_t)(mn2 & 0xffffu), b = (int16_t)(mn2 >> 16); return (T)((a < b ? a : b) >> SH); }
+        else { const uint16_t a = (uint16_t)(mn2 & 0xffffu), b = (uint16_t)(mn2 >> 16); return (T)((a < b ? a : b) >> SH); }
     }
     __device__ __forceinline__ T max_value() const {
-        if constexpr (kSigned) { const int16_t a = (int16_t)(mx2 & 0xffffu), b = (int16_t)(mx2 >> 16); return (T)(a > b ? a : b); }
-        else { const uint16_t a = (uint16_t)(mx2 & 0xffffu), b = (uint16_t)(mx2 >> 16); return (T)(a > b ? a : b); }
+        constexpr int SH = sizeof(T) == 1 ? 8 : 0;
+        if constexpr (kSigned) { const int16_t a = (int16_t)(mx2 & 0xffffu), b = (int16_t)(mx2 >> 16); return (T)((a > b ? a : b) >> SH); }
+        else { const uint16_t a = (uint16_t)(mx2 & 0xffffu), b = (uint16_t)(mx2 >> 16); return (T)((a > b ? a : b) >> SH); }
     }
 };
 
