@@ -103,6 +103,14 @@ def main():
         E = mnr.DeviceBuffer.wrap(ctx, np.dtype(name), te.data_ptr(), n, te)
         entry("ew pow two masks (exponents 0..7)", name, n * (3 * sz + 0.375),
               lambda: ops.ew_binary_into(ctx, A.Power, X, E, MX, MY, mnr.MaskMode.And, O, OM))
+        if np.dtype(name).kind == "f":
+            # the same launch on |x|: float Power is exp(b ln a), NaN for every negative base — a column of positive bases
+            # is the case that computes something
+            tp = tx.abs() + 0.5
+            P = mnr.DeviceBuffer.wrap(ctx, np.dtype(name), tp.data_ptr(), n, tp)
+            entry("ew pow two masks, positive bases", name, n * (3 * sz + 0.375),
+                  lambda: ops.ew_binary_into(ctx, A.Power, P, E, MX, MY, mnr.MaskMode.And, O, OM))
+            del P, tp
         del E, te
         entry("ew add dense", name, n * 3 * sz, lambda: ops.ew_binary_into(ctx, A.Add, X, Y, None, None, mnr.MaskMode.And, O, None))
         entry("ew scalar add masked", name, n * (2 * sz + 0.25), lambda: ops.ew_scalar_into(ctx, A.Add, X, 3, False, MX, O, OM))
