@@ -112,6 +112,7 @@ static int ctx_alloc(mnr_ctx* c, cudaStream_t stream, bool own) {
     CU(cudaMalloc(&c->fold_local, sizeof(AggRaw) * MNR_XCHG_MAX_AGGS));
     CU(cudaMalloc(&c->fold_result, sizeof(AggRaw) * MNR_XCHG_MAX_AGGS));
     CU(cudaHostAlloc(&c->h_scratch, 256, cudaHostAllocMapped | cudaHostAllocPortable));   // kernels store results here directly
+    memset(c->h_scratch, 0, 256);
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, c->device));
     uint64_t thr = UINT64_MAX;   // keep freed blocks cached: fresh outputs per call without cudaMalloc cost
@@ -760,12 +761,21 @@ static int popcount_sync(mnr_ctx* c, const mnr_bits* a, uint64_t ap, const mnr_b
                          uint64_t* ones) {
     CU(cudaSetDevice(c->device));
     if (len == 0) { *ones = 0; return MNR_OK; }
-    // The kernel's last block stores the count straight into mapped pinned host memory: launch + one stream sync.
-    unsigned long long* h = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->h_scratch) + 64);
+    // The kernel's last block stores the count straight into mapped pinned host memory with one 8-byte store (a single PCIe
+    // write).  A count is at most `len`, so all-ones cannot be a result: the slot is armed with it and polled — the call
+    // returns when the count lands instead of when the stream has drained (bounded; then cudaStreamSynchronize as before).
+    volatile unsigned long long* h = reinterpret_cast<volatile unsigned long long*>(static_cast<char*>(c->h_scratch) + 64);
+    *h = ~0ull;
     CU(launch_bits_popcount(a->ptr, ap, a->len, b ? b->ptr : nullptr, bp, b ? b->len : 0, len,
-                            reinterpret_cast<unsigned long long*>(c->partials[3]), c->ticket[3] + 4, c->d_count, h, c->stream));
+                            reinterpret_cast<unsigned long long*>(c->partials[3]), c->ticket[3] + 4, c->d_count,
+                            const_cast<unsigned long long*>(h), c->stream));
     c->launches++;
+    for (int spin = 0; spin < 100000; ++spin) {
+        const unsigned long long r = *h;
+        if (r != ~0ull) { *ones = r; return MNR_OK; }
+    }
     CU(cudaStreamSynchronize(c->stream));
+    REQUIRE(*h != ~0ull, MNR_ERR_CUDA, "popcount finished without a result");
     *ones = *h;
     return MNR_OK;
 }
@@ -983,15 +993,37 @@ int mnr_reduce_stats_async(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, int 
 
 // Synchronous form: the kernel's finishing block also stores the aggregate into mapped pinned host memory, so the call
 // is one launch + one stream synchronise (no D2H memcpy).
+// Synchronous reduction: the kernel stores the aggregate into mapped pinned host memory, each 32-bit word framed with this
+// call's sequence number (reduce_kernels.cuh, host_seq), and the host polls the slot instead of waiting for the stream to
+// drain — on an 8 KB column (BASELINE configs[0]) the stream synchronisation was the larger half of the call.  The poll is
+// bounded: after ~50 us without the result the call falls back to cudaStreamSynchronize (long reductions; a faulted kernel
+// reports its error there).
+static bool host_result_ready(const volatile uint64_t* slot, uint32_t seq, mnr_agg* out) {
+    uint32_t w[8];
+    for (int i = 0; i < 8; ++i) {
+        const uint64_t x = slot[i];
+        if ((uint32_t)(x >> 32) != seq) return false;
+        w[i] = (uint32_t)x;
+    }
+    memcpy(out, w, sizeof(mnr_agg));
+    return true;
+}
 static int reduce_sync(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, bool minmax, mnr_agg* out) {
+    static_assert(sizeof(mnr_agg) == 32, "eight 32-bit words");
     int rc = check_reduce(c, b, v);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
+    c->host_seq = (c->host_seq + 1) & 0xFFFFFFu;
+    if (c->host_seq == 0) c->host_seq = 1;
+    const uint32_t seq = c->host_seq;
+    volatile uint64_t* slot = reinterpret_cast<volatile uint64_t*>(static_cast<char*>(c->h_scratch) + 192);
     CU(launch_reduce_stats(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, minmax, c->partials[3], c->ticket[3], c->d_agg,
-                           static_cast<AggRaw*>(c->h_scratch), c->stream));
+                           reinterpret_cast<AggRaw*>(const_cast<uint64_t*>(slot)), c->stream, seq));
     c->launches++;
+    for (int spin = 0; spin < 20000; ++spin)
+        if (host_result_ready(slot, seq, out)) return MNR_OK;
     CU(cudaStreamSynchronize(c->stream));
-    memcpy(out, c->h_scratch, sizeof(mnr_agg));
+    REQUIRE(host_result_ready(slot, seq, out), MNR_ERR_CUDA, "reduction finished without a result");
     return MNR_OK;
 }
 

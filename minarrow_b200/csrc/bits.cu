@@ -143,7 +143,7 @@ __device__ __forceinline__ void popcount_finish(unsigned long long acc, unsigned
 #pragma unroll
         for (int w = 0; w < kBBlock / 32; ++w) r += sm[w];
         *result = r;
-        if (result_host) { *result_host = r; __threadfence_system(); }
+        if (result_host) *result_host = r;   // one 8-byte store into mapped pinned host memory; the host polls the slot (api.cu popcount_sync)
         *ticket = 0;
     }
 }

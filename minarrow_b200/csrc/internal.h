@@ -13,8 +13,10 @@ struct AggRaw;
 // ---- kernel launchers (one per .cu) --------------------------------------------------------------------
 int reduce_max_grid();
 // out_host: optional mapped pinned host address that receives a second copy of the aggregate (NULL = none).
+// host_seq != 0 (24 bits): out_host is a 64-byte slot that receives eight {sequence, 32-bit word} pairs the host can poll.
 cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
-                                AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s);
+                                AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s,
+                                uint32_t host_seq = 0);
 // Fused reduction + cross-GPU exchange over peer memory (reduce_kernels.cuh "fused cross-GPU finish").
 struct XchgDev;
 // late_wait: take the programmatic-dependency wait after the streaming phase (column known to be at rest).
@@ -118,6 +120,7 @@ struct mnr_ctx {
     mnr::AggRaw* d_agg = nullptr;          // result slot for synchronous reductions
     unsigned long long* d_count = nullptr; // popcount result
     void* h_scratch = nullptr;             // 256 bytes, pinned
+    uint32_t host_seq = 0;                 // sequence number of the last polled host result (reduce_sync)
     // host drop-in pipeline: 3 staging slots, one stream each
     cudaStream_t slot_stream[3] = {};
     void* stage[3][6] = {};                // lhs, rhs, acc, out, mask, out_mask

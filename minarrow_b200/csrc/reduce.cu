@@ -43,7 +43,7 @@ static cudaError_t launch_one(const void* data, const uint8_t* mask, uint64_t n,
     cfg.attrs = at;
     cfg.numAttrs = (flags & kReduceNoPdl) ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, reduce_stats_kernel<T, VecT, MASKED, MINMAX, kRBlock, RMinB<T>::value, RU<VecT, MINMAX>::value>,
-                              static_cast<const T*>(data), mask, n, partials, ticket, out, out_host, x, flags & kReduceLateWait);
+                              static_cast<const T*>(data), mask, n, partials, ticket, out, out_host, x, flags & ~kReduceNoPdl);
 }
 
 template <typename T, typename VecT, bool MASKED, bool MINMAX>
@@ -195,9 +195,10 @@ int reduce_tier(const void* data, bool minmax) {
 }
 
 cudaError_t launch_reduce_stats(mnr_dtype dt, const void* data, const uint8_t* mask, uint64_t n, bool minmax,
-                                AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s) {
+                                AggRaw* partials, unsigned int* ticket, AggRaw* out, AggRaw* out_host, cudaStream_t s, uint32_t host_seq) {
     const XchgDev none{};
-    MNR_DTYPE_SWITCH(dt, reduce_single, data, mask, n, minmax, partials, ticket, out, out_host, none, 0, s);
+    const int flags = (int)(host_seq << kReduceHostSeqShift);
+    MNR_DTYPE_SWITCH(dt, reduce_single, data, mask, n, minmax, partials, ticket, out, out_host, none, flags, s);
     return cudaErrorInvalidValue;
 }
 

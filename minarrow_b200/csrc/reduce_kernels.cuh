@@ -419,7 +419,7 @@ __device__ __forceinline__ bool reduce_stats_body(const T* __restrict__ data, co
                                                   AggRaw* __restrict__ partials, unsigned int* __restrict__ ticket,
                                                   AggRaw* __restrict__ out, AggRaw* __restrict__ out_host,
                                                   const unsigned int bid, const unsigned int nblk, const XchgDev& x,
-                                                  const bool late_wait) {
+                                                  const bool late_wait, const uint32_t host_seq = 0) {
     constexpr int VEC = sizeof(VecT) / sizeof(T);
     using A = typename Traits<T>::Acc;
     using P = Partial<T, MINMAX>;
@@ -540,8 +540,20 @@ __device__ __forceinline__ bool reduce_stats_body(const T* __restrict__ data, co
         AggRaw r = q.raw();
         if (poisoned) r.count = kAggPoison;
         *out = r;
-        if (out_host) *out_host = r;   // second copy straight into mapped pinned host memory (synchronous APIs: no D2H memcpy); kernel
-                                       // completion makes it visible to the host — no system fence on the latency path
+        if (out_host) {
+            // second copy straight into mapped pinned host memory (synchronous APIs: no D2H memcpy, no system fence on the
+            // latency path).  host_seq == 0: plain image, visible to the host once the kernel has completed.  host_seq != 0:
+            // every 32-bit word of the image travels in its own 8-byte store next to the call's sequence number, so the host
+            // can poll the slot and take the result the moment all eight flags match — it does not wait for the stream to
+            // drain (api.cu reduce_sync; 8-byte stores are single PCIe writes, the framing NCCL's LL protocol relies on).
+            if (host_seq) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+                uint64_t* o = reinterpret_cast<uint64_t*>(out_host);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(o + i), "l"(((uint64_t)host_seq << 32) | w[i]) : "memory");
+            } else *out_host = r;
+        }
         if (nblk > 1) *ticket = 0;   // re-arm for the next launch on this stream
         if (x.world > 0) { __threadfence(); st_release_gpu(x.done, x.epoch); }   // last: the successor may post / write now
     }
@@ -550,6 +562,7 @@ __device__ __forceinline__ bool reduce_stats_body(const T* __restrict__ data, co
 
 constexpr int kReduceLateWait = 1;   // flags bit 0 of reduce_stats_kernel
 constexpr int kReduceNoPdl = 2;      // host-side only: launch without the programmatic-launch attribute
+constexpr int kReduceHostSeqShift = 8;   // flags bits 8..31: sequence number of a polled host result (0 = plain image, see out_host)
 
 template <typename T, typename VecT, bool MASKED, bool MINMAX, int BLOCK, int MINB, int U>
 __global__ void __launch_bounds__(BLOCK, MINB)
@@ -559,7 +572,8 @@ reduce_stats_kernel(const T* __restrict__ data, const uint8_t* __restrict__ mask
     pdl_launch_dependents();
     const bool late = (flags & kReduceLateWait) != 0;
     if (!late) pdl_wait();
-    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(data, mask, n, partials, ticket, out, out_host, blockIdx.x, gridDim.x, x, late);
+    reduce_stats_body<T, VecT, MASKED, MINMAX, BLOCK, U>(data, mask, n, partials, ticket, out, out_host, blockIdx.x, gridDim.x, x, late,
+                                                         (uint32_t)flags >> kReduceHostSeqShift);
 }
 
 // One launch, many columns/chunks (SuperArray / SuperTable fan-out, broadcast/super_table.rs:38-73 walks them one
