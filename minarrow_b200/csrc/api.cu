@@ -1008,23 +1008,33 @@ static bool host_result_ready(const volatile uint64_t* slot, uint32_t seq, mnr_a
     memcpy(out, w, sizeof(mnr_agg));
     return true;
 }
+static volatile uint64_t* host_result_slot(mnr_ctx* c) {
+    return reinterpret_cast<volatile uint64_t*>(static_cast<char*>(c->h_scratch) + 192);
+}
+static uint32_t next_host_seq(mnr_ctx* c) {
+    c->host_seq = (c->host_seq + 1) & 0xFFFFFFu;
+    if (c->host_seq == 0) c->host_seq = 1;
+    return c->host_seq;
+}
+static int await_host_result(mnr_ctx* c, cudaStream_t s, uint32_t seq, mnr_agg* out) {
+    const volatile uint64_t* slot = host_result_slot(c);
+    for (int spin = 0; spin < 20000; ++spin)
+        if (host_result_ready(slot, seq, out)) return MNR_OK;
+    CU(cudaStreamSynchronize(s));
+    REQUIRE(host_result_ready(slot, seq, out), MNR_ERR_CUDA, "reduction finished without a result");
+    return MNR_OK;
+}
 static int reduce_sync(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, bool minmax, mnr_agg* out) {
     static_assert(sizeof(mnr_agg) == 32, "eight 32-bit words");
     int rc = check_reduce(c, b, v);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    c->host_seq = (c->host_seq + 1) & 0xFFFFFFu;
-    if (c->host_seq == 0) c->host_seq = 1;
-    const uint32_t seq = c->host_seq;
-    volatile uint64_t* slot = reinterpret_cast<volatile uint64_t*>(static_cast<char*>(c->h_scratch) + 192);
+    const uint32_t seq = next_host_seq(c);
+    volatile uint64_t* slot = host_result_slot(c);
     CU(launch_reduce_stats(b->dtype, b->ptr, v ? v->ptr : nullptr, b->len, minmax, c->partials[3], c->ticket[3], c->d_agg,
                            reinterpret_cast<AggRaw*>(const_cast<uint64_t*>(slot)), c->stream, seq));
     c->launches++;
-    for (int spin = 0; spin < 20000; ++spin)
-        if (host_result_ready(slot, seq, out)) return MNR_OK;
-    CU(cudaStreamSynchronize(c->stream));
-    REQUIRE(host_result_ready(slot, seq, out), MNR_ERR_CUDA, "reduction finished without a result");
-    return MNR_OK;
+    return await_host_result(c, c->stream, seq, out);
 }
 
 int mnr_reduce_stats(mnr_ctx* c, const mnr_buf* b, const mnr_bits* v, mnr_agg* out_host) {
@@ -1637,6 +1647,22 @@ int mnr_stats_host(mnr_ctx* c, mnr_dtype dtype, const void* data, size_t len, co
         c->chunk_aggs = nullptr; c->chunk_aggs_cap = 0;   // never leave a dangling pointer behind a failed cudaMalloc
         CU(cudaMalloc(&c->chunk_aggs, sizeof(AggRaw) * nchunks));
         c->chunk_aggs_cap = nchunks;
+    }
+    if (nchunks == 1) {
+        // One chunk (every column up to host_chunk_rows rows): copy in, one launch, the aggregate polled out of mapped pinned
+        // host memory as in reduce_sync — no stream synchronisation and no device-to-host copy on the way back.
+        cudaStream_t s = c->slot_stream[0];
+        void** st = c->stage[0];
+        if (len) {
+            CU(cudaMemcpyAsync(st[0], data, len * es, cudaMemcpyHostToDevice, s));
+            if (validity) CU(cudaMemcpyAsync(st[4], validity, mask_bytes(len), cudaMemcpyHostToDevice, s));
+        }
+        const uint32_t seq = next_host_seq(c);
+        CU(launch_reduce_stats(dtype, st[0], validity ? static_cast<uint8_t*>(st[4]) : nullptr, len, with_minmax != 0,
+                               c->partials[0], c->ticket[0], c->chunk_aggs,
+                               reinterpret_cast<AggRaw*>(const_cast<uint64_t*>(host_result_slot(c))), s, seq));
+        c->launches++;
+        return await_host_result(c, s, seq, out);
     }
     for (size_t k = 0; k < nchunks; ++k) {
         const int sl = (int)(k % 3);
