@@ -2,6 +2,7 @@
 // for the hot path: same names, argument meaning and error behaviour, so tests read like the reference's own.
 //
 //   apply_int_i32/u32/i64/u64, apply_float_f32/f64   src/kernels/arithmetic/dispatch.rs:74-79,147-152,376-402
+//   apply_datetime_i32/u32/i64/u64                   src/kernels/arithmetic/dispatch.rs:300-372,420-427
 //   apply_fma_f32/f64                                dispatch.rs:221-226,404-418
 //   and_masks / or_masks / xor_masks / not_mask / popcount_mask / all_true_mask / all_false_mask / merge_bitmasks_to_new
 //                                                    src/kernels/bitmask/dispatch.rs:96-295, bitmask/mod.rs:171-197
@@ -12,6 +13,7 @@
 // Rust `Result<_, KernelError>` -> a thrown `KernelError` (kind = variant name); the reference's dense-integer
 // divide-by-zero *panic* (std.rs:54-55) is kind "DivideByZero".  Header-only; link with -lminarrow_b200.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <initializer_list>
@@ -109,6 +111,22 @@ template <class T> struct FloatArray {
     size_t len() const { return data.size(); }
     bool is_empty() const { return data.empty(); }
 };
+
+// DatetimeArray<T> {data, null_mask, time_unit} (structs/variants/datetime/mod.rs:90-140): integer offsets from the epoch.
+template <class T> struct DatetimeArray {
+    Vec64<T> data;
+    std::optional<Bitmask> null_mask;
+    std::optional<std::string> time_unit;
+    size_t len() const { return data.size(); }
+    bool is_empty() const { return data.empty(); }
+    static DatetimeArray from_slice(std::initializer_list<T> v, std::optional<std::string> unit = std::nullopt) {
+        DatetimeArray a;
+        a.data.assign(v.begin(), v.end());
+        a.time_unit = std::move(unit);
+        return a;
+    }
+};
+template <class T> using DatetimeAVT = std::tuple<const DatetimeArray<T>&, size_t, size_t>;   // (&DatetimeArray, offset, len), aliases.rs
 
 template <class T> struct DType;
 template <> struct DType<int32_t> { static constexpr mnr_dtype code = MNR_I32; };
@@ -242,6 +260,46 @@ private:
     Context* ctx_;
     mnr_buf* h_ = nullptr;
 };
+
+// ---- datetime delegation: apply_datetime_{i32,u32,i64,u64} (dispatch.rs:300-372, 420-427) -----------------------------------
+// The integer kernels over the two data windows; output validity = merge_bitmasks_to_new(lhs.null_mask, rhs.null_mask, llen),
+// i.e. bits [0, llen) of each ARRAY's mask (the reference does not offset them by the window start, :321-322), fused into the
+// launch as two mask operands.  Some(mask) iff either side has one.
+namespace detail {
+template <class T>
+DatetimeArray<T> apply_datetime(Context& ctx, DatetimeAVT<T> lhs, DatetimeAVT<T> rhs, ArithmeticOperator op) {
+    const auto& [la, lo, ll] = lhs;
+    const auto& [ra, ro, rl] = rhs;
+    if (ll != rl) throw KernelError(MNR_ERR_LENGTH_MISMATCH, "LengthMismatch", "apply_datetime: length mismatch");
+    if (lo + ll > la.data.size() || ro + rl > ra.data.size()) throw KernelError(MNR_ERR_OUT_OF_BOUNDS, "OutOfBounds", "apply_datetime: window leaves the array");
+    DatetimeArray<T> out;
+    out.time_unit = la.time_unit;
+    const bool any_mask = la.null_mask.has_value() || ra.null_mask.has_value();
+    if (ll == 0) { if (any_mask) out.null_mask = Bitmask::new_set_all(0, false); return out; }
+    auto up_mask = [&](const std::optional<Bitmask>& m) -> std::optional<DeviceBitmask> {
+        if (!m) return std::nullopt;
+        if (m->len < ll) throw KernelError(MNR_ERR_INVALID_ARGUMENTS, "InvalidArguments", "Bitmask too short in merge");
+        Bitmask w = Bitmask::new_set_all(ll, false);
+        std::copy(m->bits.begin(), m->bits.begin() + (ll + 7) / 8, w.bits.begin());
+        if (ll & 7) w.bits.back() &= uint8_t((1u << (ll & 7)) - 1u);
+        return DeviceBitmask(ctx, w);
+    };
+    std::optional<DeviceBitmask> lm = up_mask(la.null_mask), rm = up_mask(ra.null_mask);
+    mnr_buf *L = nullptr, *R = nullptr;
+    check(mnr_buf_upload(ctx.get(), DType<T>::code, la.data.data() + lo, ll, &L));
+    DeviceBuffer<T> dl(ctx, L);
+    check(mnr_buf_upload(ctx.get(), DType<T>::code, ra.data.data() + ro, rl, &R));
+    DeviceBuffer<T> dr(ctx, R);
+    auto [ob, om] = dl.binary(op, dr, lm ? &*lm : nullptr, rm ? &*rm : nullptr, MNR_MASK_AND);
+    out.data = ob.download();
+    if (om) out.null_mask = om->download();
+    return out;
+}
+}  // namespace detail
+inline DatetimeArray<int32_t> apply_datetime_i32(DatetimeAVT<int32_t> l, DatetimeAVT<int32_t> r, ArithmeticOperator op, Context& ctx = Context::thread_default()) { return detail::apply_datetime<int32_t>(ctx, l, r, op); }
+inline DatetimeArray<uint32_t> apply_datetime_u32(DatetimeAVT<uint32_t> l, DatetimeAVT<uint32_t> r, ArithmeticOperator op, Context& ctx = Context::thread_default()) { return detail::apply_datetime<uint32_t>(ctx, l, r, op); }
+inline DatetimeArray<int64_t> apply_datetime_i64(DatetimeAVT<int64_t> l, DatetimeAVT<int64_t> r, ArithmeticOperator op, Context& ctx = Context::thread_default()) { return detail::apply_datetime<int64_t>(ctx, l, r, op); }
+inline DatetimeArray<uint64_t> apply_datetime_u64(DatetimeAVT<uint64_t> l, DatetimeAVT<uint64_t> r, ArithmeticOperator op, Context& ctx = Context::thread_default()) { return detail::apply_datetime<uint64_t>(ctx, l, r, op); }
 
 // ---- bitmask kernels over host masks (BitmaskVT windows) ------------------------------------------------------------------
 namespace detail {

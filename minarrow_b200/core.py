@@ -311,6 +311,25 @@ class FloatArray:
 
 
 @dataclass
+class DatetimeArray:
+    """`DatetimeArray<T> {data, null_mask, time_unit}` (src/structs/variants/datetime/mod.rs:90-140): integer offsets from the
+    epoch in `time_unit`; arithmetic on it is the integer kernels' (dispatch.rs:300-372)."""
+    data: np.ndarray
+    null_mask: Optional[Bitmask] = None
+    time_unit: Optional[str] = None
+
+    @classmethod
+    def from_slice(cls, data, time_unit: Optional[str] = None) -> "DatetimeArray":
+        return cls(np.ascontiguousarray(data), None, time_unit)
+
+    def __len__(self) -> int:
+        return int(self.data.size)
+
+    def is_empty(self) -> bool:
+        return self.data.size == 0
+
+
+@dataclass
 class BooleanArray:
     """`BooleanArray {data: Bitmask, null_mask, len}` (src/structs/variants/boolean.rs:108-119)."""
     data: Bitmask

@@ -109,3 +109,58 @@ def apply_fma_f32(lhs, rhs, acc, mask: Optional[Bitmask] = None, ctx=None) -> Fl
 def apply_fma_f64(lhs, rhs, acc, mask: Optional[Bitmask] = None, ctx=None) -> FloatArray:
     """apply_fma_f64 (dispatch.rs:412-418)."""
     return _fma(np.float64, lhs, rhs, acc, mask, ctx)
+
+
+# ---- datetime delegation (dispatch.rs:300-372, 420-427) ----------------------------------------------------------------
+def _apply_datetime(dtype, lhs, rhs, op, ctx):
+    """`apply_datetime_*(lhs: DatetimeAVT<T>, rhs: DatetimeAVT<T>, op)`: the integer kernels over the two data windows.
+    Output validity = merge_bitmasks_to_new(lhs.null_mask, rhs.null_mask, llen) — bits [0, llen) of each array's mask, which
+    the reference does not offset by the window start (dispatch.rs:321-322) — fused into the launch as two mask operands
+    (per-row AND); `Some(mask)` iff either side has one.  LengthMismatch like the reference's `confirm_equal_len`; dense
+    integer division by zero is DivideByZero where the reference panics."""
+    from .. import device_ops as dev
+    from ..core import DatetimeArray, DeviceBitmask, DeviceBuffer, MaskMode
+    ctx = ctx or default_context()
+    (larr, loff, llen), (rarr, roff, rlen) = lhs, rhs
+    if llen != rlen:
+        raise KernelError("LengthMismatch", f"apply_datetime: length mismatch (lhs: {llen}, rhs: {rlen})")
+    ld = np.ascontiguousarray(larr.data, dtype=dtype)
+    rd = np.ascontiguousarray(rarr.data, dtype=dtype)
+    if loff + llen > ld.size or roff + rlen > rd.size:
+        raise KernelError("OutOfBounds", f"apply_datetime: window ({loff}, {llen}) / ({roff}, {rlen}) outside the arrays ({ld.size}, {rd.size})")
+    unit = larr.time_unit
+    if llen == 0:
+        both = larr.null_mask is not None or rarr.null_mask is not None
+        return DatetimeArray(np.empty(0, dtype=dtype), Bitmask(np.zeros(0, dtype=np.uint8), 0) if both else None, unit)
+    masks = []
+    for arr in (larr, rarr):
+        if arr.null_mask is None:
+            masks.append(None)
+            continue
+        if arr.null_mask.len < llen:
+            raise KernelError("InvalidArguments", f"Bitmask too short in merge ({arr.null_mask.len} < {llen})")
+        masks.append(DeviceBitmask.upload(ctx, Bitmask(arr.null_mask.bits[:(llen + 7) // 8], llen)))
+    L = DeviceBuffer.upload(ctx, ld[loff:loff + llen])
+    R = DeviceBuffer.upload(ctx, rd[roff:roff + rlen])
+    ob, om = dev.ew_binary(ctx, int(op), L, R, masks[0], masks[1], MaskMode.And)
+    return DatetimeArray(ob.download(), om.download() if om is not None else None, unit)
+
+
+def apply_datetime_i32(lhs, rhs, op: ArithmeticOperator, ctx=None):
+    """apply_datetime_i32 (dispatch.rs:420-421)."""
+    return _apply_datetime(np.int32, lhs, rhs, op, ctx)
+
+
+def apply_datetime_u32(lhs, rhs, op: ArithmeticOperator, ctx=None):
+    """apply_datetime_u32 (dispatch.rs:422-423)."""
+    return _apply_datetime(np.uint32, lhs, rhs, op, ctx)
+
+
+def apply_datetime_i64(lhs, rhs, op: ArithmeticOperator, ctx=None):
+    """apply_datetime_i64 (dispatch.rs:424-425)."""
+    return _apply_datetime(np.int64, lhs, rhs, op, ctx)
+
+
+def apply_datetime_u64(lhs, rhs, op: ArithmeticOperator, ctx=None):
+    """apply_datetime_u64 (dispatch.rs:426-427)."""
+    return _apply_datetime(np.uint64, lhs, rhs, op, ctx)

@@ -121,6 +121,17 @@ def apply_int(lhs, rhs, op: int, mask=None):
     return out, (Bits(om, n) if om is not None else None)
 
 
+def apply_datetime(l_data, l_mask, l_off: int, l_len: int, r_data, r_mask, r_off: int, r_len: int, op: int):
+    """apply_datetime_{i32,u32,i64,u64}(lhs: DatetimeAVT, rhs: DatetimeAVT, op) — src/kernels/arithmetic/dispatch.rs:309-372:
+    the integer kernels over the two data windows; the output validity is merge_bitmasks_to_new(lhs.null_mask, rhs.null_mask,
+    llen), i.e. bits [0, llen) of each ARRAY's mask (the reference does not offset the masks by the window start, :321-322)."""
+    if l_len != r_len:
+        raise KernelError("LengthMismatch", f"apply_datetime: length mismatch (lhs: {l_len}, rhs: {r_len})")
+    l = np.ascontiguousarray(l_data)[l_off:l_off + l_len]
+    r = np.ascontiguousarray(r_data, dtype=l.dtype)[r_off:r_off + r_len]
+    return apply_int(l, r, op, merge_bitmasks_to_new(l_mask, r_mask, l_len))
+
+
 def apply_float(lhs, rhs, op: int, mask=None):
     """apply_float_{f32,f64} — src/kernels/arithmetic/dispatch.rs:138-206."""
     lhs = np.ascontiguousarray(lhs)

@@ -357,6 +357,39 @@ int main(int argc, char** argv) {
             Bitmask t = Bitmask::new_set_all(10, true);          // clear_trailing_bits: 10 bits -> last byte 0x03 (bitmask/mod.rs:240-287)
             CHECK(not_mask({Bitmask::new_set_all(10, false), 0, 10}).bits[1] == 0x03 && t.bits[1] == 0x03);
         }
+        {   // datetime delegation (arithmetic/mod.rs:418-506: datetime_add, datetime_all_ops, datetime_masked_and_empty,
+            // datetime_len_mismatch_panics) — the integer kernels with the two arrays' masks merged
+            using DA = DatetimeArray<int64_t>;
+            DA l = DA::from_slice({1000, 2000, 3000}), r = DA::from_slice({10, 20, 30});
+            auto out = apply_datetime_i64({l, 0, l.len()}, {r, 0, r.len()}, Op::Add);
+            CHECK(same<int64_t>(out.data, {1010, 2020, 3030}) && !out.null_mask);
+            DA a = DA::from_slice({10, 20, 30, 40}), b = DA::from_slice({1, 2, 3, 4});
+            auto run = [&](Op op) { return apply_datetime_i64({a, 0, 4}, {b, 0, 4}, op); };
+            CHECK(same<int64_t>(run(Op::Add).data, {11, 22, 33, 44}));
+            CHECK(same<int64_t>(run(Op::Subtract).data, {9, 18, 27, 36}));
+            CHECK(same<int64_t>(run(Op::Multiply).data, {10, 40, 90, 160}));
+            CHECK(same<int64_t>(run(Op::Divide).data, {10, 10, 10, 10}));
+            CHECK(same<int64_t>(run(Op::Remainder).data, {0, 0, 0, 0}));
+            CHECK(same<int64_t>(run(Op::Power).data, {10, 400, 27000, 2560000}));
+            DA am = a;
+            am.null_mask = Bitmask::from_bools({true, false, true, true});
+            auto mo = apply_datetime_i64({am, 0, 4}, {b, 0, 4}, Op::Add);
+            CHECK(same<int64_t>(mo.data, {11, 0, 33, 44}) && mask_is(mo.null_mask, {true, false, true, true}));
+            DA bm = b;
+            bm.null_mask = Bitmask::from_bools({true, true, false, true});
+            auto both = apply_datetime_i64({am, 0, 4}, {bm, 0, 4}, Op::Add);               // both masks: per-row AND
+            CHECK(same<int64_t>(both.data, {11, 0, 0, 44}) && mask_is(both.null_mask, {true, false, false, true}));
+            auto win = apply_datetime_i64({am, 1, 2}, {b, 2, 2}, Op::Add);                 // windows: data offset, masks from bit 0 (dispatch.rs:321-322)
+            CHECK(same<int64_t>(win.data, {23, 0}) && mask_is(win.null_mask, {true, false}));
+            DA e = DA::from_slice({});
+            CHECK(apply_datetime_i64({e, 0, 0}, {e, 0, 0}, Op::Add).is_empty());
+            DA s2 = DA::from_slice({1000, 2000}), s1 = DA::from_slice({10});
+            bool lm = false;
+            try { apply_datetime_i64({s2, 0, 2}, {s1, 0, 1}, Op::Add); } catch (const KernelError& ex) { lm = ex.kind == "LengthMismatch"; }
+            CHECK(lm);
+            DA z = DA::from_slice({1, 0, 3, 4});
+            CHECK(panics([&] { apply_datetime_i64({a, 0, 4}, {z, 0, 4}, Op::Divide); }));   // dense integer kernel: division by zero
+        }
         {   // bench self-checks: sum(0..1000) = 499500 (hotloop_benchmark_simd.rs); device-resident + null-aware aggregates
             Vec64<int64_t> v(1000);
             std::iota(v.begin(), v.end(), 0);

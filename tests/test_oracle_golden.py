@@ -278,3 +278,28 @@ def test_array_superarray_rechunk_route_of_the_oracle():
     assert r[0][0].tolist() == [6, 0] and r[0][1].to_bools().tolist() == [True, False]
     with pytest.raises(orc.KernelError):
         orc.route_super_array_broadcast(orc.ADD, [(np.array([1, 2], np.int32), None)], [(np.array([5], np.int32), None)])
+
+
+def test_datetime_delegation_reference_vectors():
+    """apply_datetime_i64 — the reference's own tests (src/kernels/arithmetic/mod.rs:418-506: datetime_add, datetime_all_ops,
+    datetime_masked_and_empty, datetime_len_mismatch_panics): integer kernels + merge of the two arrays' masks."""
+    i64 = np.int64
+    out, m = orc.apply_datetime(np.array([1000, 2000, 3000], i64), None, 0, 3, np.array([10, 20, 30], i64), None, 0, 3, orc.ADD)
+    assert out.tolist() == [1010, 2020, 3030] and m is None
+    a, b = np.array([10, 20, 30, 40], i64), np.array([1, 2, 3, 4], i64)
+    exp = {orc.ADD: [11, 22, 33, 44], orc.SUB: [9, 18, 27, 36], orc.MUL: [10, 40, 90, 160], orc.DIV: [10, 10, 10, 10],
+           orc.REM: [0, 0, 0, 0], orc.POW: [10, 20 ** 2, 30 ** 3, 40 ** 4]}
+    for op, e in exp.items():
+        out, m = orc.apply_datetime(a, None, 0, 4, b, None, 0, 4, op)
+        assert out.tolist() == e and m is None, op
+    mask = orc.Bits.from_bools([True, False, True, True])
+    out, m = orc.apply_datetime(a, mask, 0, 4, b, None, 0, 4, orc.ADD)
+    assert out.tolist() == [11, 0, 33, 44] and m.to_bools().tolist() == [True, False, True, True]
+    out, m = orc.apply_datetime(np.zeros(0, i64), None, 0, 0, np.zeros(0, i64), None, 0, 0, orc.ADD)
+    assert out.size == 0
+    with pytest.raises(orc.KernelError) as ei:
+        orc.apply_datetime(np.array([1000, 2000], i64), None, 0, 2, np.array([10], i64), None, 0, 1, orc.ADD)
+    assert ei.value.kind == "LengthMismatch"
+    # windows: the data is offset, the masks are merged from bit 0 (dispatch.rs:321-322)
+    out, m = orc.apply_datetime(a, mask, 1, 2, b, None, 2, 2, orc.ADD)
+    assert out.tolist() == [23, 0] and m.to_bools().tolist() == [True, False]
