@@ -8,19 +8,20 @@ from bench import event_time_ms
 dev = torch.device("cuda:0"); ctx = mnr.Context(0, torch.cuda.current_stream().cuda_stream); ops = mnr.device_ops
 A = mnr.ArithmeticOperator
 g = torch.Generator(device=dev); g.manual_seed(1)
-for name in ("int8", "uint8"):
-    nd = np.dtype(name); n = 1 << 30
-    x = torch.randint(-100, 100, (n,), dtype=torch.int8, device=dev, generator=g); y = torch.randint(-100, 100, (n,), dtype=torch.int8, device=dev, generator=g)
+for name in (sys.argv[1:] or ["int8", "uint8"]):
+    nd = np.dtype(name); n = (1 << 30) // nd.itemsize
+    carrier = {1: torch.int8, 2: torch.int16}[nd.itemsize]
+    x = torch.randint(-100, 100, (n,), dtype=carrier, device=dev, generator=g); y = torch.randint(-100, 100, (n,), dtype=carrier, device=dev, generator=g)
     o = torch.empty_like(x)
     m1 = torch.randint(0, 256, (n // 8,), dtype=torch.uint8, device=dev, generator=g); m2 = torch.randint(0, 256, (n // 8,), dtype=torch.uint8, device=dev, generator=g)
     om = torch.empty_like(m1)
     W = lambda t: mnr.DeviceBuffer.wrap(ctx, nd, t.data_ptr(), n, t)
     B = lambda t: mnr.DeviceBitmask.wrap(ctx, t.data_ptr(), n, t)
     X, Y, O, M1, M2, OM = W(x), W(y), W(o), B(m1), B(m2), B(om)
-    cases = [("add two masks", lambda: ops.ew_binary_into(ctx, A.Add, X, Y, M1, M2, mnr.MaskMode.And, O, OM), n * 3.375),
-             ("mul two masks", lambda: ops.ew_binary_into(ctx, A.Multiply, X, Y, M1, M2, mnr.MaskMode.And, O, OM), n * 3.375),
-             ("add one mask", lambda: ops.ew_binary_into(ctx, A.Add, X, Y, M1, None, mnr.MaskMode.And, O, OM), n * 3.25),
-             ("scalar add masked", lambda: ops.ew_scalar_into(ctx, A.Add, X, 3, False, M1, O, OM), n * 2.25)]
+    cases = [("add two masks", lambda: ops.ew_binary_into(ctx, A.Add, X, Y, M1, M2, mnr.MaskMode.And, O, OM), n * (3 * nd.itemsize + 0.375)),
+             ("mul two masks", lambda: ops.ew_binary_into(ctx, A.Multiply, X, Y, M1, M2, mnr.MaskMode.And, O, OM), n * (3 * nd.itemsize + 0.375)),
+             ("add one mask", lambda: ops.ew_binary_into(ctx, A.Add, X, Y, M1, None, mnr.MaskMode.And, O, OM), n * (3 * nd.itemsize + 0.25)),
+             ("scalar add masked", lambda: ops.ew_scalar_into(ctx, A.Add, X, 3, False, M1, O, OM), n * (2 * nd.itemsize + 0.25))]
     ref = {}
     for cfg in (1, 2, 3):
         ctx.set_option("ew_cheap8_cfg", cfg)
