@@ -120,7 +120,6 @@ def _apply_datetime(dtype, lhs, rhs, op, ctx):
     integer division by zero is DivideByZero where the reference panics."""
     from .. import device_ops as dev
     from ..core import DatetimeArray, DeviceBitmask, DeviceBuffer, MaskMode
-    ctx = ctx or default_context()
     (larr, loff, llen), (rarr, roff, rlen) = lhs, rhs
     if llen != rlen:
         raise KernelError("LengthMismatch", f"apply_datetime: length mismatch (lhs: {llen}, rhs: {rlen})")
@@ -139,7 +138,9 @@ def _apply_datetime(dtype, lhs, rhs, op, ctx):
             continue
         if arr.null_mask.len < llen:
             raise KernelError("InvalidArguments", f"Bitmask too short in merge ({arr.null_mask.len} < {llen})")
-        masks.append(DeviceBitmask.upload(ctx, Bitmask(arr.null_mask.bits[:(llen + 7) // 8], llen)))
+        masks.append(Bitmask(arr.null_mask.bits[:(llen + 7) // 8], llen))
+    ctx = ctx or default_context()      # every argument error above is raised before a device is touched
+    masks = [None if m is None else DeviceBitmask.upload(ctx, m) for m in masks]
     L = DeviceBuffer.upload(ctx, ld[loff:loff + llen])
     R = DeviceBuffer.upload(ctx, rd[roff:roff + rlen])
     ob, om = dev.ew_binary(ctx, int(op), L, R, masks[0], masks[1], MaskMode.And)

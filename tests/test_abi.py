@@ -114,3 +114,27 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 code = "\n".join(l for l in txt.splitlines() if not l.strip().startswith(("//", "#", "*", "/*")))
                 assert "oracle" not in code.lower(), f"{f} references the oracle: the product must not route through it"
+
+
+def test_datetime_delegation_argument_errors_without_gpu():
+    """apply_datetime_* (dispatch.rs:300-372) rejects bad arguments before any device is touched: the reference's
+    `confirm_equal_len` (LengthMismatch), a window outside the array, a mask shorter than the window."""
+    import numpy as np
+    import pytest
+    import minarrow_b200 as mnr
+    from minarrow_b200.kernels import arithmetic as ar
+    A = mnr.ArithmeticOperator
+    a = mnr.DatetimeArray.from_slice(np.array([1000, 2000], np.int64))
+    b = mnr.DatetimeArray.from_slice(np.array([10], np.int64))
+    with pytest.raises(mnr.KernelError) as ei:
+        ar.apply_datetime_i64((a, 0, 2), (b, 0, 1), A.Add)
+    assert ei.value.kind == "LengthMismatch" and "apply_datetime: length mismatch" in str(ei.value)
+    with pytest.raises(mnr.KernelError) as ei:
+        ar.apply_datetime_i64((a, 1, 2), (a, 0, 2), A.Add)
+    assert ei.value.kind == "OutOfBounds"
+    short = mnr.DatetimeArray(a.data, mnr.Bitmask.from_bools([True]))
+    with pytest.raises(mnr.KernelError) as ei:
+        ar.apply_datetime_i64((short, 0, 2), (a, 0, 2), A.Add)
+    assert ei.value.kind == "InvalidArguments"
+    e = mnr.DatetimeArray.from_slice(np.zeros(0, np.int64))
+    assert ar.apply_datetime_i64((e, 0, 0), (e, 0, 0), A.Add).is_empty()      # empty in, empty out: no launch
