@@ -436,6 +436,46 @@ def broadcast_tableview_to_superarrayview(op: ArithmeticOperator, table_view: De
 
 
 # ---- Value-level dispatch -----------------------------------------------------------------------------------------------------------
+def broadcast_array_to_supertable(op: ArithmeticOperator, arr: DeviceArray, st: DeviceSuperTable, array_is_lhs: bool = True,
+                                 ctx: Optional[Context] = None) -> DeviceSuperTable:
+    """`array op supertable` / `supertable op array` (array.rs:236-252, super_table.rs `broadcast_supertable_to_array`): the
+    array against every column of every batch (`broadcast_array_to_table` per batch, so its length must be each batch's
+    row count or 1); all batches x columns in one batched call."""
+    leaves, shape = [], []
+    for b in st.batches:
+        for c in b.cols:
+            leaves.append(_Leaf(arr, c) if array_is_lhs else _Leaf(c, arr))
+        shape.append((b.name, b.n_cols()))
+    res = route_leaves(op, leaves, MaskMode.And, ctx)
+    out, k = [], 0
+    for name, n in shape:
+        out.append(DeviceTable(name, res[k:k + n]))
+        k += n
+    return DeviceSuperTable(out, st.name)
+
+
+def scalar_arithmetic(lhs, rhs, op: ArithmeticOperator):
+    """`scalar_arithmetic(Scalar, Scalar, op)` (routing/arithmetic.rs:34-209): two host scalars — no array, no launch.  Same
+    type -> same type for Add / Subtract / Multiply / Divide (integer division truncates, integers wrap like the release
+    build); int (op) float promotes the integer; anything else is NotImplemented."""
+    a, b = np.asarray(lhs), np.asarray(rhs)
+    if a.dtype.kind in "iu" and b.dtype.kind == "f":
+        a = a.astype(b.dtype)
+    elif a.dtype.kind == "f" and b.dtype.kind in "iu":
+        b = b.astype(a.dtype)
+    if a.dtype != b.dtype or a.dtype.kind not in "iuf" or int(op) > int(ArithmeticOperator.Divide):
+        raise KernelError("NotImplemented", f"Scalar arithmetic operation {ArithmeticOperator(op).name} between {a.dtype} and {b.dtype}")
+    if int(op) == int(ArithmeticOperator.Divide) and a.dtype.kind in "iu":
+        if b == 0:
+            raise KernelError("DivideByZero", "attempt to divide by zero")
+        q = abs(int(a)) // abs(int(b))
+        return a.dtype.type(np.array(-q if (int(a) < 0) != (int(b) < 0) else q).astype(a.dtype))
+    with np.errstate(all="ignore"):
+        r = {int(ArithmeticOperator.Add): np.add, int(ArithmeticOperator.Subtract): np.subtract,
+             int(ArithmeticOperator.Multiply): np.multiply, int(ArithmeticOperator.Divide): np.divide}[int(op)](a, b)
+    return a.dtype.type(r)
+
+
 def _is_scalar(x) -> bool:
     return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
 
@@ -443,8 +483,31 @@ def _is_scalar(x) -> bool:
 def broadcast_value(op: ArithmeticOperator, lhs, rhs, ctx: Optional[Context] = None):
     """`broadcast_value(op, Value, Value)` (broadcast/mod.rs:152-...) on device-resident Values: Scalar (python / numpy
     number), DeviceArray (also ArrayView), DeviceSuperArray (also SuperArrayView), DeviceTable (also TableView),
-    DeviceSuperTable.  The result is device-resident as well, so `a * b + c` chains in HBM."""
+    DeviceSuperTable, python tuples of 2-6 Values (Tuple2..Tuple6) and lists (VecValue).  The result is device-resident as
+    well, so `a * b + c` chains in HBM."""
     L, R = lhs, rhs
+    if _is_scalar(L) and _is_scalar(R):
+        # mod.rs:161-163 passes ArithmeticOperator::Add to scalar_arithmetic whatever `op` is; a drop-in returns what the
+        # reference returns
+        return scalar_arithmetic(L, R, ArithmeticOperator.Add)
+    # Tuple2..Tuple6 (mod.rs:305-353) and VecValue (:356-372): element-wise; an array-like operand against a tuple meets every
+    # element (array.rs:269-447, mod.rs:766-907)
+    if isinstance(L, tuple) and isinstance(R, tuple):
+        if len(L) != len(R) or not 2 <= len(L) <= 6:
+            raise KernelError("UnsupportedType", f"no route for Tuple{len(L)} (op) Tuple{len(R)}")
+        return tuple(broadcast_value(op, a, b, ctx) for a, b in zip(L, R))
+    if isinstance(L, list) and isinstance(R, list):
+        if len(L) != len(R):
+            raise KernelError("LengthMismatch", f"ColumnLengthMismatch: col 0, expected {len(L)}, found {len(R)}")
+        return [broadcast_value(op, a, b, ctx) for a, b in zip(L, R)]
+    if isinstance(R, tuple) and isinstance(L, (DeviceArray, DeviceSuperArray)) and 2 <= len(R) <= 6:
+        return tuple(broadcast_value(op, L, b, ctx) for b in R)
+    if isinstance(L, tuple) and isinstance(R, (DeviceArray, DeviceSuperArray)) and 2 <= len(L) <= 6:
+        return tuple(broadcast_value(op, a, R, ctx) for a in L)
+    if isinstance(L, DeviceArray) and isinstance(R, DeviceSuperTable):
+        return broadcast_array_to_supertable(op, L, R, True, ctx)
+    if isinstance(L, DeviceSuperTable) and isinstance(R, DeviceArray):
+        return broadcast_array_to_supertable(op, R, L, False, ctx)
     if isinstance(L, DeviceSuperTable) and isinstance(R, DeviceSuperTable):
         return broadcast_super_table_with_operator(op, L, R, ctx)
     if isinstance(L, DeviceSuperTable) and _is_scalar(R):

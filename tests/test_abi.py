@@ -138,3 +138,24 @@ def test_datetime_delegation_argument_errors_without_gpu():
     assert ei.value.kind == "InvalidArguments"
     e = mnr.DatetimeArray.from_slice(np.zeros(0, np.int64))
     assert ar.apply_datetime_i64((e, 0, 0), (e, 0, 0), A.Add).is_empty()      # empty in, empty out: no launch
+
+
+def test_scalar_arithmetic_and_the_scalar_scalar_arm():
+    """`scalar_arithmetic` (routing/arithmetic.rs:34-209) is host arithmetic on two scalars; `broadcast_value` on two Scalars
+    calls it with ArithmeticOperator::Add whatever the operator (broadcast/mod.rs:161-163) — reproduced as is."""
+    import numpy as np
+    import pytest
+    import minarrow_b200 as mnr
+    from minarrow_b200.containers import broadcast_value, scalar_arithmetic
+    A = mnr.ArithmeticOperator
+    assert scalar_arithmetic(np.int32(7), np.int32(-2), A.Divide) == -3 and scalar_arithmetic(np.int32(7), np.int32(-2), A.Divide).dtype == np.int32
+    assert scalar_arithmetic(np.int64(2 ** 62), np.int64(2 ** 62), A.Add) == np.int64(-2 ** 63)           # wraps like the release build
+    assert scalar_arithmetic(np.int64(3), np.float64(0.5), A.Multiply) == 1.5                             # Int + Float = Float
+    assert scalar_arithmetic(np.float32(1), np.float32(3), A.Divide).dtype == np.float32
+    assert scalar_arithmetic(np.uint32(5), np.uint32(7), A.Subtract) == np.uint32(2 ** 32 - 2)
+    for bad in ((np.int32(1), np.int64(2), A.Add), (np.int64(1), np.int64(2), A.Power)):
+        with pytest.raises(mnr.KernelError) as ei:
+            scalar_arithmetic(*bad)
+        assert ei.value.kind == "NotImplemented"
+    assert broadcast_value(A.Multiply, np.int64(6), np.int64(7)) == 13
+    assert broadcast_value(A.Subtract, 1.5, 2) == 3.5

@@ -223,3 +223,46 @@ def test_boolean_array_not(gpu_ctx):
         r = ~b
         assert np.array_equal(r.data.to_bools(), ~d) and r.null_mask is b.null_mask
         assert np.array_equal(r.data.bits, np.packbits(~d, bitorder="little"))
+
+
+def test_array_supertable_tuple_and_vecvalue_arms(gpu_ctx, oracle):
+    """The compositional arms of `broadcast_value` (broadcast/mod.rs): Array (op) SuperTable and the mirror (:557-562, one
+    batched call), Tuple2..6 and VecValue element-wise (:305-372), an array against every element of a tuple (:766-907), and
+    Scalar (op) Scalar, which the reference always evaluates as Add (:161-163)."""
+    import minarrow_b200 as mnr
+    from minarrow_b200 import containers as dc
+    from minarrow_b200.kernels import broadcast as B
+    A = mnr.ArithmeticOperator
+    rng = np.random.default_rng(5)
+    n = 1000
+    dt = np.int64
+
+    def col(mask):
+        return mnr.core.make_array(rng.integers(-1000, 1000, n).astype(dt), mnr.Bitmask.from_bools(rng.random(n) < 0.8) if mask else None)
+    st = B.SuperTable([B.Table(f"b{i}", [col(False), col(True)]) for i in range(3)], "T")
+    arr = col(True)
+    dst, darr = dc.DeviceSuperTable.from_host(gpu_ctx, st), dc.DeviceArray.from_host(gpu_ctx, arr)
+    for array_is_lhs in (True, False):
+        l0 = gpu_ctx.launch_count
+        got = (dc.broadcast_value(A.Subtract, darr, dst, gpu_ctx) if array_is_lhs else dc.broadcast_value(A.Subtract, dst, darr, gpu_ctx))
+        assert gpu_ctx.launch_count - l0 == 1        # six leaves of one (dtype, class) in one launch
+        got = got.to_host()
+        assert got.name == "T" and got.n_batches() == 3
+        for b in range(3):
+            for c in range(2):
+                # broadcast_array_to_table -> resolve_binary_arithmetic(op, array, col, None): the kernels get no mask, the
+                # operands' own validity is not consulted and the result carries none (routing/arithmetic.rs:214-222)
+                h = st.batches[b].cols[c]
+                ed, em = oracle.apply_int(arr.data, h.data, oracle.SUB, None) if array_is_lhs else oracle.apply_int(h.data, arr.data, oracle.SUB, None)
+                _same(got.batches[b].cols[c], ed, em, (array_is_lhs, b, c))
+    # tuples / lists
+    x, y = dc.DeviceArray.from_host(gpu_ctx, col(False)), dc.DeviceArray.from_host(gpu_ctx, col(False))
+    t = dc.broadcast_value(A.Add, (x, y, 2), (y, x, 3), gpu_ctx)
+    assert isinstance(t, tuple) and len(t) == 3 and t[2] == 5
+    assert np.array_equal(t[0].to_host().data, x.to_host().data + y.to_host().data)
+    v = dc.broadcast_value(A.Multiply, [x, y], [y, y], gpu_ctx)
+    assert isinstance(v, list) and np.array_equal(v[1].to_host().data, y.to_host().data * y.to_host().data)
+    with pytest.raises(mnr.KernelError):
+        dc.broadcast_value(A.Multiply, [x, y], [y], gpu_ctx)
+    at = dc.broadcast_value(A.Add, x, (y, x), gpu_ctx)
+    assert isinstance(at, tuple) and np.array_equal(at[1].to_host().data, 2 * x.to_host().data)
