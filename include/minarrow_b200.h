@@ -211,7 +211,8 @@ int mnr_bits_not(mnr_ctx* ctx, const mnr_bits* src, size_t offset, size_t len, m
 int mnr_bits_not_into(mnr_ctx* ctx, const mnr_bits* src, size_t offset, size_t len, mnr_bits* out);
 /* popcount_mask (dispatch.rs:258-267 -> simd.rs:596-645): set bits of words [offset/64 ..) over `len` bits.
  * Bitmask::count_ones / null_count (bitmask.rs:393-417): offset 0, len = mask len; null_count = len - ones.
- * Synchronises. */
+ * Blocks until the count has arrived in host memory (polled out of mapped pinned memory; work queued on the stream before
+ * the call has completed by then, the stream itself may still be retiring the kernel). */
 int mnr_bits_popcount(mnr_ctx* ctx, const mnr_bits* mask, size_t offset, size_t len, uint64_t* ones);
 /* Asynchronous form for device-resident pipelines: the count is written to DEVICE memory `out_device` (one uint64,
  * 8-byte aligned) on the context stream; no synchronisation (null_count feeding a later kernel never visits the host). */
@@ -255,7 +256,8 @@ int mnr_eq_mask(mnr_ctx* ctx, const mnr_buf* data, const void* field_mask, const
  * use the fixed order documented in DESIGN.md (<= 1e-12 relative to the reference order).  count / min /
  * max / mean and null-skipping are not in the reference tree (downstream `simd-kernels` crate); their
  * definition is DESIGN.md "A.6".  `validity` may be NULL (dense).  I32/U32 widen to 64-bit sums, F32 sums in f64. */
-int mnr_reduce_stats(mnr_ctx* ctx, const mnr_buf* buf, const mnr_bits* validity, mnr_agg* out_host);  /* syncs */
+int mnr_reduce_stats(mnr_ctx* ctx, const mnr_buf* buf, const mnr_bits* validity, mnr_agg* out_host);  /* blocks until the aggregate
+    has arrived in host memory (polled, sequence-framed stores into mapped pinned memory; no stream synchronisation) */
 int mnr_reduce_sum(mnr_ctx* ctx, const mnr_buf* buf, const mnr_bits* validity, mnr_scalar64* out_sum,
                    uint64_t* out_count);                                                             /* syncs */
 /* Asynchronous forms: the 32-byte mnr_agg is written to DEVICE memory `out_device` (16-byte aligned) on the

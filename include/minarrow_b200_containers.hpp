@@ -394,6 +394,19 @@ template <class S> SuperTable broadcast_super_table_to_scalar(ArithmeticOperator
     return SuperTable::from_batches(std::move(out), t.name);
 }
 
+// broadcast_array_to_supertable (array.rs:236-252) / broadcast_supertable_to_array (super_table.rs): the array against every
+// column of every batch, operand order kept.
+inline SuperTable broadcast_array_to_supertable(ArithmeticOperator op, const Array& a, const SuperTable& st, Context& ctx = Context::thread_default()) {
+    std::vector<Table> out;
+    for (const auto& b : st.batches) out.push_back(broadcast_array_to_table(op, a, *b, ctx));
+    return SuperTable::from_batches(std::move(out), st.name);
+}
+inline SuperTable broadcast_supertable_to_array(ArithmeticOperator op, const SuperTable& st, const Array& a, Context& ctx = Context::thread_default()) {
+    std::vector<Table> out;
+    for (const auto& b : st.batches) out.push_back(broadcast_table_to_array(op, *b, a, ctx));
+    return SuperTable::from_batches(std::move(out), st.name);
+}
+
 
 // ---- device-resident containers: operands stay in HBM between calls --------------------------------------------------------
 // The same containers holding mnr_buf / mnr_bits handles.  A route gathers every (chunk, column) leaf call and issues them

@@ -188,6 +188,11 @@ int main(int argc, char** argv) {
             CHECK(is<int32_t>(o.batches[0]->cols[0], {2, 3, 4}) && is<int32_t>(o.batches[1]->cols[0], {6, 7, 8}) && is<int32_t>(o.batches[2]->cols[0], {10, 11, 12}));
             o = broadcast_super_table_to_scalar<int32_t>(Op::Add, l3, 100);
             CHECK(is<int32_t>(o.batches[2]->cols[1], {170, 180, 190}));
+            // Array (op) SuperTable and the mirror (broadcast/mod.rs:557-562, array.rs:236-252): every column of every batch
+            o = broadcast_array_to_supertable(Op::Subtract, i32({100, 200, 300}), l3);
+            CHECK(o.n_batches() == 3 && is<int32_t>(o.batches[0]->cols[0], {99, 198, 297}) && is<int32_t>(o.batches[2]->cols[1], {30, 120, 210}));
+            o = broadcast_supertable_to_array(Op::Subtract, l3, i32({100, 200, 300}));
+            CHECK(is<int32_t>(o.batches[1]->cols[0], {-96, -195, -294}) && is<int32_t>(o.batches[1]->cols[1], {-60, -150, -240}));
         }
         {   // Array (op) SuperArray with re-chunking and the union mask (broadcast/mod.rs:1351-1361, utils.rs:367-481).  The
             // reference has no test with null masks for these arms; expectations are the route's definition worked by hand:
