@@ -435,6 +435,64 @@ def broadcast_tableview_to_superarrayview(op: ArithmeticOperator, table_view: De
     return DeviceSuperTable([DeviceTable(table_view.name, res[k * nc:(k + 1) * nc]) for k in range(len(sav.chunks))], table_view.name)
 
 
+def broadcast_superarrayview_to_tableview(op: ArithmeticOperator, sav: DeviceSuperArray, table_view: DeviceTable,
+                                          ctx: Optional[Context] = None) -> DeviceSuperTable:
+    """super_array_view.rs:22-80 and super_table_view.rs:108-154 (`broadcast_superarrayview_to_table`): the mirror of
+    `broadcast_tableview_to_superarrayview` — SuperArrayView slice i on the LEFT of the aligned TableView slice i."""
+    if len(sav) != table_view.n_rows():
+        raise ShapeError(f"SuperArrayView length ({len(sav)}) does not match TableView length ({table_view.n_rows()})")
+    leaves, start = [], 0
+    for s in sav.chunks:
+        leaves += [_Leaf(s, c.view(start, len(s))) for c in table_view.cols]
+        start += len(s)
+    res = route_leaves(op, leaves, MaskMode.And, ctx)
+    nc = table_view.n_cols()
+    return DeviceSuperTable([DeviceTable(table_view.name, res[k * nc:(k + 1) * nc]) for k in range(len(sav.chunks))], table_view.name)
+
+
+def _split_like(res: List[DeviceArray], stv: DeviceSuperTable) -> DeviceSuperTable:
+    out, k = [], 0
+    for b in stv.batches:
+        out.append(DeviceTable(b.name, res[k:k + b.n_cols()]))
+        k += b.n_cols()
+    return DeviceSuperTable(out, stv.name)
+
+
+def broadcast_supertableview_to_arrayview(op: ArithmeticOperator, stv: DeviceSuperTable, av: DeviceArray, stv_is_lhs: bool = True,
+                                          check_len: bool = True, ctx: Optional[Context] = None) -> DeviceSuperTable:
+    """`supertableview op arrayview` and the mirror (super_table_view.rs:66-105, array_view.rs `broadcast_arrayview_to_
+    supertableview`): table slice i meets the window [sum of earlier slice lengths, + its own length) of the ArrayView,
+    column by column; all slices x columns in one batched call.  `check_len=False` is the Array form
+    (`broadcast_supertableview_to_array`, :157-180; `broadcast_array_to_supertableview`, array.rs:451-476), which only needs
+    the array to be long enough."""
+    if check_len and len(av) != stv.n_rows():
+        raise ShapeError(f"ArrayView length ({len(av)}) does not match SuperTableView length ({stv.n_rows()})")
+    leaves, start = [], 0
+    for b in stv.batches:
+        w = av.view(start, b.n_rows())
+        leaves += [_Leaf(c, w) if stv_is_lhs else _Leaf(w, c) for c in b.cols]
+        start += b.n_rows()
+    return _split_like(route_leaves(op, leaves, MaskMode.And, ctx), stv)
+
+
+def broadcast_supertableview_to_table(op: ArithmeticOperator, stv: DeviceSuperTable, table: DeviceTable, stv_is_lhs: bool = True,
+                                      ctx: Optional[Context] = None) -> DeviceSuperTable:
+    """`supertableview op table` / `table op supertableview` (super_table_view.rs:183-250): the Table is promoted to slices
+    aligned with the SuperTableView's and slice i meets slice i through the TableView route (equal column counts)."""
+    if stv.n_rows() != table.n_rows():
+        raise ShapeError(f"SuperTableView length ({stv.n_rows()}) does not match Table rows ({table.n_rows()})" if stv_is_lhs else
+                         f"Table rows ({table.n_rows()}) does not match SuperTableView length ({stv.n_rows()})")
+    leaves, start = [], 0
+    for b in stv.batches:
+        if b.n_cols() != table.n_cols():
+            raise ShapeError(f"TableView column count mismatch: {b.n_cols() if stv_is_lhs else table.n_cols()} vs {table.n_cols() if stv_is_lhs else b.n_cols()}")
+        for c, t in zip(b.cols, table.cols):
+            w = t.view(start, b.n_rows())
+            leaves.append(_Leaf(c, w) if stv_is_lhs else _Leaf(w, c))
+        start += b.n_rows()
+    return _split_like(route_leaves(op, leaves, MaskMode.And, ctx), stv)
+
+
 # ---- Value-level dispatch -----------------------------------------------------------------------------------------------------------
 def broadcast_array_to_supertable(op: ArithmeticOperator, arr: DeviceArray, st: DeviceSuperTable, array_is_lhs: bool = True,
                                  ctx: Optional[Context] = None) -> DeviceSuperTable:
@@ -500,9 +558,9 @@ def broadcast_value(op: ArithmeticOperator, lhs, rhs, ctx: Optional[Context] = N
         if len(L) != len(R):
             raise KernelError("LengthMismatch", f"ColumnLengthMismatch: col 0, expected {len(L)}, found {len(R)}")
         return [broadcast_value(op, a, b, ctx) for a, b in zip(L, R)]
-    if isinstance(R, tuple) and isinstance(L, (DeviceArray, DeviceSuperArray)) and 2 <= len(R) <= 6:
-        return tuple(broadcast_value(op, L, b, ctx) for b in R)
-    if isinstance(L, tuple) and isinstance(R, (DeviceArray, DeviceSuperArray)) and 2 <= len(L) <= 6:
+    if isinstance(R, tuple) and (isinstance(L, (DeviceArray, DeviceSuperArray)) or _is_scalar(L)) and 2 <= len(R) <= 6:
+        return tuple(broadcast_value(op, L, b, ctx) for b in R)       # array / scalar against every element (scalar.rs:300-420)
+    if isinstance(L, tuple) and (isinstance(R, (DeviceArray, DeviceSuperArray)) or _is_scalar(R)) and 2 <= len(L) <= 6:
         return tuple(broadcast_value(op, a, R, ctx) for a in L)
     if isinstance(L, DeviceArray) and isinstance(R, DeviceSuperTable):
         return broadcast_array_to_supertable(op, L, R, True, ctx)

@@ -110,6 +110,19 @@ class SuperTable:
         return self.batches[0].n_cols() if self.batches else 0
 
 
+@dataclass
+class SuperTableV:
+    """`SuperTableV {slices: Vec<TableV>, len}` (src/structs/views/chunked/super_table_view.rs): row windows of tables."""
+    slices: List[TableV] = field(default_factory=list)
+
+    @property
+    def len(self) -> int:
+        return sum(s.len for s in self.slices)
+
+    def n_slices(self) -> int:
+        return len(self.slices)
+
+
 def _is_scalar(x) -> bool:
     return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
 
@@ -135,6 +148,12 @@ def to_device(ctx: Context, v):
         return dc.DeviceTable.from_host(ctx, v)
     if isinstance(v, TableV):
         return dc.DeviceTable(v.table.name, [dc.DeviceArray.from_host(ctx, _window(c, v.offset, v.len)) for c in v.table.cols])
+    if isinstance(v, SuperTableV):
+        return dc.DeviceSuperTable([to_device(ctx, s) for s in v.slices])
+    if isinstance(v, tuple):
+        return tuple(to_device(ctx, x) for x in v)
+    if isinstance(v, list):
+        return [to_device(ctx, x) for x in v]
     if isinstance(v, SuperArray):
         return dc.DeviceSuperArray.from_host(ctx, v)
     if isinstance(v, SuperArrayV):
@@ -144,9 +163,17 @@ def to_device(ctx: Context, v):
     return dc.DeviceArray.from_host(ctx, v)
 
 
-def _run(op, lhs, rhs, ctx, fn=dc.broadcast_value):
+def _to_host(v):
+    if isinstance(v, tuple):
+        return tuple(_to_host(x) for x in v)
+    if isinstance(v, list):
+        return [_to_host(x) for x in v]
+    return v.to_host() if hasattr(v, "to_host") else v      # scalars stay as they are
+
+
+def _run(op, lhs, rhs, ctx, fn=dc.broadcast_value, **kw):
     ctx = ctx or default_context()
-    return fn(op, to_device(ctx, lhs), to_device(ctx, rhs), ctx).to_host()
+    return _to_host(fn(op, to_device(ctx, lhs), to_device(ctx, rhs), ctx=ctx, **kw))
 
 
 def route_super_array_broadcast(op: ArithmeticOperator, lhs: SuperArray, rhs: SuperArray,
@@ -230,6 +257,29 @@ def broadcast_tableview_to_tableview(op: ArithmeticOperator, lhs: TableV, rhs: T
     return out
 
 
+def broadcast_supertableview_to_arrayview(op: ArithmeticOperator, stv: SuperTableV, view: ArrayV, ctx=None) -> SuperTable:
+    """super_table_view.rs:66-105: table slice i against the aligned window of the ArrayView; the ArrayView must be as long
+    as the SuperTableView (ShapeError "... does not match ...").  Slices come back materialised (`TableV::from_table(result,
+    0, n)` in the reference), i.e. as the batches of a SuperTable."""
+    return _run(op, stv, view, ctx, dc.broadcast_supertableview_to_arrayview, stv_is_lhs=True)
+
+
+def broadcast_arrayview_to_supertableview(op: ArithmeticOperator, view: ArrayV, stv: SuperTableV, ctx=None) -> SuperTable:
+    """array_view.rs `broadcast_arrayview_to_supertableview`: the mirror, ArrayView windows on the left."""
+    return _run(op, stv, view, ctx, dc.broadcast_supertableview_to_arrayview, stv_is_lhs=False)
+
+
+def broadcast_supertableview_to_scalar(op: ArithmeticOperator, stv: SuperTableV, scalar, ctx=None) -> SuperTable:
+    """super_table_view.rs:28-62: every slice, every column against the typed scalar — one batched call."""
+    return _run(op, stv, scalar, ctx)
+
+
+def broadcast_superarrayview_to_tableview(op: ArithmeticOperator, sav, table, ctx=None) -> SuperTable:
+    """super_array_view.rs:22-80 / super_table_view.rs:108-154 (`broadcast_superarrayview_to_table`): the Table / TableView
+    is cut into slices aligned with the SuperArrayView's and slice i meets slice i, SuperArrayView on the left."""
+    return _run(op, sav, table, ctx, dc.broadcast_superarrayview_to_tableview)
+
+
 def broadcast_value(op: ArithmeticOperator, lhs, rhs, ctx=None):
     """`broadcast_value(op, Value, Value)` (src/kernels/broadcast/mod.rs:152-...) for the Value variants on this path:
     Scalar (python / numpy number), Array (numpy, IntegerArray, FloatArray), ArrayV, SuperArray, SuperArrayV, Table, TableV,
@@ -238,17 +288,32 @@ def broadcast_value(op: ArithmeticOperator, lhs, rhs, ctx=None):
     ArrayV (op) SuperArray goes chunk by chunk with no mask (super_array.rs:255-365); Array (op) TableV takes the table
     view's window of the array (mod.rs:1386-1393)."""
     if _is_scalar(lhs) and _is_scalar(rhs):
-        raise KernelError("UnsupportedType", "Scalar op Scalar is host arithmetic, not a kernel route")
+        return dc.broadcast_value(op, lhs, rhs)      # scalar_arithmetic on the host: nothing to launch (mod.rs:161-163)
     ctx = ctx or default_context()
     L, R = lhs, rhs
     chunked = (SuperArray, SuperArrayV)
+    plain = lambda x: not isinstance(x, (Table, TableV, SuperTable, SuperTableV, ArrayV, tuple, list)) and not _is_scalar(x) and not isinstance(x, chunked)
+    # SuperTableView arms (mod.rs:521-528, 612-618, 644-660, 1394-...): aligned windows, slice by slice
+    if isinstance(L, SuperTableV) or isinstance(R, SuperTableV):
+        stv, other, stv_is_lhs = (L, R, True) if isinstance(L, SuperTableV) else (R, L, False)
+        if _is_scalar(other):
+            return _run(op, L, R, ctx)                                                  # broadcast_supertableview_to_scalar
+        if isinstance(other, ArrayV):
+            return broadcast_supertableview_to_arrayview(op, stv, other, ctx) if stv_is_lhs else broadcast_arrayview_to_supertableview(op, other, stv, ctx)
+        if isinstance(other, Table):
+            return _run(op, stv, other, ctx, dc.broadcast_supertableview_to_table, stv_is_lhs=stv_is_lhs)
+        if plain(other):
+            return _run(op, stv, other, ctx, dc.broadcast_supertableview_to_arrayview, stv_is_lhs=stv_is_lhs, check_len=False)
+        raise KernelError("UnsupportedType", f"no route for {type(L).__name__} (op) {type(R).__name__}")
+    if isinstance(L, SuperArrayV) and isinstance(R, (Table, TableV)):
+        return broadcast_superarrayview_to_tableview(op, L, R, ctx)
     if isinstance(L, ArrayV) and isinstance(R, chunked):
         return broadcast_arrayview_to_superarray(op, L, R, ctx)
     if isinstance(L, chunked) and isinstance(R, ArrayV):
         return broadcast_superarray_to_arrayview(op, L, R, ctx)
-    if isinstance(R, TableV) and not isinstance(L, (Table, TableV, SuperTable, ArrayV)) and not _is_scalar(L) and not isinstance(L, chunked):
+    if isinstance(R, TableV) and plain(L):
         L = ArrayV(L, R.offset, R.len)          # Array (op) TableView: ArrayV::new(array, tv.offset, tv.len)
-    if isinstance(L, TableV) and not isinstance(R, (Table, TableV, SuperTable, ArrayV)) and not _is_scalar(R) and not isinstance(R, chunked):
+    if isinstance(L, TableV) and plain(R):
         R = ArrayV(R, L.offset, L.len)
     if isinstance(L, TableV) and isinstance(R, TableV):
         return broadcast_tableview_to_tableview(op, L, R, ctx)
