@@ -383,6 +383,54 @@ def broadcast_super_table_with_operator(op: ArithmeticOperator, lhs: DeviceSuper
     return DeviceSuperTable(out, lhs.name)
 
 
+def broadcast_table_add(lhs: DeviceTable, rhs: DeviceTable, null_mask: Optional[DeviceBitmask] = None,
+                        ctx: Optional[Context] = None) -> DeviceTable:
+    """`broadcast_table_add(lhs, rhs, null_mask)` (table.rs:69-128): column i + column i through `broadcast_array_add`, i.e.
+    `resolve_binary_arithmetic(Add, l, r, null_mask)` — the SAME optional mask for every column (one row count), the columns'
+    own validity not consulted; ONE batched call.  Shape errors are the reference's BroadcastingError texts."""
+    if lhs.n_cols() != rhs.n_cols():
+        raise KernelError("BroadcastingError", f"Table column count mismatch: LHS {lhs.n_cols()} cols, RHS {rhs.n_cols()} cols")
+    if lhs.n_rows() != rhs.n_rows():
+        raise KernelError("BroadcastingError", f"Table row count mismatch: LHS {lhs.n_rows()} rows, RHS {rhs.n_rows()} rows")
+    leaves = [_Leaf(l, r, null_mask, None) for l, r in zip(lhs.cols, rhs.cols)]
+    return DeviceTable(lhs.name, route_leaves(ArithmeticOperator.Add, leaves, MaskMode.And, ctx))
+
+
+def broadcast_super_table_add(lhs: DeviceSuperTable, rhs: DeviceSuperTable, null_mask: Optional[DeviceBitmask] = None,
+                              ctx: Optional[Context] = None) -> DeviceSuperTable:
+    """`broadcast_super_table_add` (table.rs:135-176): chunk i + chunk i through `broadcast_table_add` with the same optional
+    mask; all chunks x columns in ONE batched call.  The result takes the first slice's name, or "SuperTable"."""
+    if lhs.n_batches() != rhs.n_batches():
+        raise KernelError("BroadcastingError", f"SuperTable chunk count mismatch: LHS {lhs.n_batches()} chunks, RHS {rhs.n_batches()} chunks")
+    leaves, shape = [], []
+    for i, (lb, rb) in enumerate(zip(lhs.batches, rhs.batches)):
+        if lb.n_cols() != rb.n_cols():
+            raise KernelError("BroadcastingError", f"Chunk {i} addition failed: Table column count mismatch: LHS {lb.n_cols()} cols, RHS {rb.n_cols()} cols")
+        if lb.n_rows() != rb.n_rows():
+            raise KernelError("BroadcastingError", f"Chunk {i} addition failed: Table row count mismatch: LHS {lb.n_rows()} rows, RHS {rb.n_rows()} rows")
+        leaves += [_Leaf(l, r, null_mask, None) for l, r in zip(lb.cols, rb.cols)]
+        shape.append((lb.name, lb.n_cols()))
+    res = route_leaves(ArithmeticOperator.Add, leaves, MaskMode.And, ctx)
+    out, k = [], 0
+    for name, n in shape:
+        out.append(DeviceTable(name, res[k:k + n]))
+        k += n
+    name = lhs.batches[0].name if lhs.batches and lhs.batches[0].name else "SuperTable"
+    return DeviceSuperTable(out, name)
+
+
+def broadcast_table_to_superarray(op: ArithmeticOperator, table: DeviceTable, sa: DeviceSuperArray, table_is_lhs: bool = True,
+                                  ctx: Optional[Context] = None) -> DeviceSuperArray:
+    """`table op superarray` (table.rs:382-406) / `superarray op table` (super_array.rs:153-176): every CHUNK against the whole
+    table through the Table-Array route, which must leave a single column — so the table has one column as long as each
+    chunk; one batched call over the chunks."""
+    if table.n_cols() != 1:
+        raise ShapeError(("Table-SuperArray" if table_is_lhs else "SuperArray-Table") + " broadcasting should result in single column")
+    c = table.cols[0]
+    leaves = [_Leaf(c, ch) if table_is_lhs else _Leaf(ch, c) for ch in sa.chunks]
+    return DeviceSuperArray(route_leaves(op, leaves, MaskMode.And, ctx))
+
+
 def broadcast_table_to_array(op: ArithmeticOperator, table: DeviceTable, arr: DeviceArray, table_is_lhs: bool = True,
                              ctx: Optional[Context] = None) -> DeviceTable:
     """`table op array` / `array op table` (table.rs:179-228, array.rs:187-236; view forms table_view.rs:108-146): every

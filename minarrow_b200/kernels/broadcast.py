@@ -236,6 +236,35 @@ def broadcast_super_table_with_operator(op: ArithmeticOperator, lhs, rhs, ctx=No
     return [b.cols for b in out.batches] if as_list else out
 
 
+def _device_mask(ctx, null_mask):
+    from ..core import DeviceBitmask
+    return None if null_mask is None else DeviceBitmask.upload(ctx, null_mask)
+
+
+def broadcast_table_add(lhs, rhs, null_mask: Optional[Bitmask] = None, ctx=None) -> Table:
+    """`broadcast_table_add(lhs: impl Into<TableV>, rhs, null_mask)` (table.rs:69-128): Table or TableV operands; the optional
+    mask is handed to every column's kernel (`broadcast_array_add`)."""
+    ctx = ctx or default_context()
+    return _to_host(dc.broadcast_table_add(to_device(ctx, lhs), to_device(ctx, rhs), _device_mask(ctx, null_mask), ctx))
+
+
+def broadcast_super_table_add(lhs, rhs, null_mask: Optional[Bitmask] = None, ctx=None) -> SuperTable:
+    """`broadcast_super_table_add(lhs: impl Into<SuperTableV>, rhs, null_mask)` (table.rs:135-176): SuperTable or SuperTableV
+    operands, chunk by chunk; all chunks x columns in one batched call."""
+    ctx = ctx or default_context()
+    return _to_host(dc.broadcast_super_table_add(to_device(ctx, lhs), to_device(ctx, rhs), _device_mask(ctx, null_mask), ctx))
+
+
+def broadcast_table_to_superarray(op: ArithmeticOperator, table, sa: SuperArray, ctx=None) -> SuperArray:
+    """table.rs:382-406: every chunk of the SuperArray against the whole (single-column) table."""
+    return _run(op, table, sa, ctx, dc.broadcast_table_to_superarray, table_is_lhs=True)
+
+
+def broadcast_superarray_to_table(op: ArithmeticOperator, sa: SuperArray, table, ctx=None) -> SuperArray:
+    """super_array.rs:153-176: the mirror, chunks on the left."""
+    return _run(op, table, sa, ctx, dc.broadcast_table_to_superarray, table_is_lhs=False)
+
+
 def broadcast_arrayview_to_superarray(op: ArithmeticOperator, view: ArrayV, sa, ctx=None) -> SuperArray:
     """ArrayView (op) SuperArray / SuperArrayView (super_array.rs:255-309, 367-419): NO mask, chunk by chunk."""
     ctx = ctx or default_context()
@@ -307,6 +336,11 @@ def broadcast_value(op: ArithmeticOperator, lhs, rhs, ctx=None):
         raise KernelError("UnsupportedType", f"no route for {type(L).__name__} (op) {type(R).__name__}")
     if isinstance(L, SuperArrayV) and isinstance(R, (Table, TableV)):
         return broadcast_superarrayview_to_tableview(op, L, R, ctx)
+    # an OWNING SuperArray against a Table / TableView (mod.rs:622-641): every chunk meets the whole table
+    if isinstance(L, SuperArray) and isinstance(R, (Table, TableV)):
+        return broadcast_superarray_to_table(op, L, R, ctx)
+    if isinstance(L, (Table, TableV)) and isinstance(R, SuperArray):
+        return broadcast_table_to_superarray(op, L, R, ctx)
     if isinstance(L, ArrayV) and isinstance(R, chunked):
         return broadcast_arrayview_to_superarray(op, L, R, ctx)
     if isinstance(L, chunked) and isinstance(R, ArrayV):

@@ -161,3 +161,41 @@ def test_scalar_rs_and_array_rs(B, gpu_ctx):
     assert t[0].data.tolist() == [10, 20, 30] and t[4].data.tolist() == [50, 60, 70] and len(t) == 5
     t = B.broadcast_value(A.Subtract, i32(5, 5, 5), (i32(10, 10, 10), i32(20, 20, 20), i32(15, 15, 15), i32(8, 8, 8), i32(12, 12, 12), i32(6, 6, 6)), gpu_ctx)
     assert t[0].data.tolist() == [-5, -5, -5] and t[5].data.tolist() == [-1, -1, -1] and len(t) == 6
+
+
+def test_table_rs_and_super_array_rs_remaining(B, gpu_ctx):
+    """table.rs:568-760 (table - arrayview, SuperTableV + SuperTableV, table + SuperArray, table * SuperArrayView) and
+    super_array.rs:674-719 (SuperArray + table)."""
+    import minarrow_b200 as mnr
+    A = mnr.ArithmeticOperator
+    t = table(B, (10, 20, 30), (100, 200, 300), name="table1")
+    r = B.broadcast_value(A.Subtract, t, B.ArrayV(i32(2, 3, 4)), gpu_ctx)
+    assert col(r, 0) == [8, 17, 26] and col(r, 1) == [98, 197, 296]
+    t1, t2 = table(B, (1, 2, 3), (10, 20, 30), name="table1"), table(B, (4, 5, 6), (40, 50, 60), name="table2")
+    t3, t4 = table(B, (7, 8, 9), (70, 80, 90), name="table3"), table(B, (1, 1, 1), (2, 2, 2), name="table4")
+    r = B.broadcast_super_table_add(stv(B, t1, t2), stv(B, t3, t4), None, gpu_ctx)
+    assert r.n_batches() == 2 and r.name == "table1"
+    assert col(r.batches[0], 0) == [8, 10, 12] and col(r.batches[0], 1) == [80, 100, 120]
+    assert col(r.batches[1], 0) == [5, 6, 7] and col(r.batches[1], 1) == [42, 52, 62]
+    with pytest.raises(mnr.KernelError) as ei:
+        B.broadcast_super_table_add(stv(B, t1, t2), stv(B, t3), None, gpu_ctx)
+    assert ei.value.kind == "BroadcastingError" and "chunk count mismatch: LHS 2 chunks, RHS 1 chunks" in str(ei.value)
+    # the optional mask goes to every column's kernel (table.rs:98-101): masked rows are 0 and null in every result column
+    m = mnr.Bitmask.from_bools([True, False, True])
+    r = B.broadcast_table_add(t1, t3, m, gpu_ctx)
+    assert r.name == "table1" and [c.data.tolist() for c in r.cols] == [[8, 0, 12], [80, 0, 120]]
+    assert all(c.null_mask.to_bools().tolist() == [True, False, True] for c in r.cols)
+    with pytest.raises(mnr.KernelError) as ei:
+        B.broadcast_table_add(t1, table(B, (1, 2, 3)), None, gpu_ctx)
+    assert "Table column count mismatch: LHS 2 cols, RHS 1 cols" in str(ei.value)
+    r = B.broadcast_value(A.Add, table(B, (2, 3, 4)), B.SuperArray([i32(10, 20, 30), i32(40, 50, 60)]), gpu_ctx)
+    assert r.n_chunks() == 2 and r.chunks[0].data.tolist() == [12, 23, 34] and r.chunks[1].data.tolist() == [42, 53, 64]
+    arr = i32(10, 20, 30, 40, 50, 60)
+    sav = B.SuperArrayV([B.ArrayV(arr).slice(0, 3), B.ArrayV(arr).slice(3, 3)])
+    r = B.broadcast_value(A.Multiply, table(B, (1, 2, 3, 4, 5, 6)), sav, gpu_ctx)
+    assert r.n_batches() == 2 and r.n_rows() == 6 and col(r.batches[0]) == [10, 40, 90] and col(r.batches[1]) == [160, 250, 360]
+    r = B.broadcast_value(A.Add, B.SuperArray([i32(1, 2, 3), i32(4, 5, 6)]), table(B, (10, 20, 30)), gpu_ctx)
+    assert r.n_chunks() == 2 and r.chunks[0].data.tolist() == [11, 22, 33] and r.chunks[1].data.tolist() == [14, 25, 36]
+    with pytest.raises(mnr.ShapeError) as ei:
+        B.broadcast_value(A.Add, B.SuperArray([i32(1, 2, 3)]), table(B, (10, 20, 30), (1, 2, 3)), gpu_ctx)
+    assert "should result in single column" in str(ei.value)
