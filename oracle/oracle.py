@@ -261,6 +261,63 @@ def broadcast_array_superarray(op: int, arr, arr_mask, sa_chunks, array_is_lhs: 
     return route_super_array_broadcast(op, aligned, sa_chunks) if array_is_lhs else route_super_array_broadcast(op, sa_chunks, aligned)
 
 
+# ---- Table / view arms: columns are plain np.ndarrays (these arms hand NO mask to the kernels) ----------------------------
+# A table is a list of columns; a table view is (columns, offset, len); a super table view is a list of table views.
+def _tv(tv):
+    cols, off, n = tv
+    return [np.asarray(c)[off:off + n] for c in cols]
+
+
+def broadcast_tableview_to_tableview(op: int, lhs_tv, rhs_tv):
+    """table_view.rs:25-60 (Table form table.rs:31-62): column i against column i, no mask."""
+    l, r = _tv(lhs_tv), _tv(rhs_tv)
+    if len(l) != len(r):
+        raise KernelError("ShapeError", f"TableView column count mismatch: {len(l)} vs {len(r)}")
+    return [resolve_binary_arithmetic(op, a, b, None)[0] for a, b in zip(l, r)]
+
+
+def broadcast_tableview_to_arrayview(op: int, tv, arr, table_is_lhs: bool = True):
+    """table_view.rs:108-146 / array_view.rs: every column against the same array window, operand order kept."""
+    arr = np.asarray(arr)
+    return [resolve_binary_arithmetic(op, c, arr, None)[0] if table_is_lhs else resolve_binary_arithmetic(op, arr, c, None)[0] for c in _tv(tv)]
+
+
+def broadcast_supertableview_to_arrayview(op: int, stv, arr, stv_is_lhs: bool = True, check_len: bool = True):
+    """super_table_view.rs:66-105 (and the mirror in array_view.rs; Array forms :157-180, array.rs:451-476 with
+    check_len=False): slice i meets arr[sum of earlier slice lengths ..][.. its own length]."""
+    arr = np.asarray(arr)
+    total = sum(n for _, _, n in stv)
+    if check_len and arr.size != total:
+        raise KernelError("ShapeError", f"ArrayView length ({arr.size}) does not match SuperTableView length ({total})")
+    out, start = [], 0
+    for tv in stv:
+        out.append(broadcast_tableview_to_arrayview(op, tv, arr[start:start + tv[2]], stv_is_lhs))
+        start += tv[2]
+    return out
+
+
+def broadcast_tableview_to_superarrayview(op: int, tv, slices, table_is_lhs: bool = True):
+    """table_view.rs:148-200 / super_array_view.rs:22-80: the table view cut into windows aligned with the array slices."""
+    cols, off, n = tv
+    total = sum(np.asarray(s).size for s in slices)
+    if n != total:
+        raise KernelError("ShapeError", (f"TableView length ({n}) does not match SuperArrayView length ({total})" if table_is_lhs else
+                                         f"SuperArrayView length ({total}) does not match TableView length ({n})"))
+    out, start = [], 0
+    for s in slices:
+        s = np.asarray(s)
+        out.append(broadcast_tableview_to_arrayview(op, (cols, off + start, s.size), s, table_is_lhs))
+        start += s.size
+    return out
+
+
+def broadcast_table_to_superarray(op: int, table_cols, chunks, table_is_lhs: bool = True):
+    """table.rs:382-406 / super_array.rs:153-176: every chunk against the whole table; the result must be one column."""
+    if len(table_cols) != 1:
+        raise KernelError("ShapeError", ("Table-SuperArray" if table_is_lhs else "SuperArray-Table") + " broadcasting should result in single column")
+    return [broadcast_tableview_to_arrayview(op, (table_cols, 0, np.asarray(table_cols[0]).size), ch, table_is_lhs)[0] for ch in chunks]
+
+
 # ---- bitmask kernels ----------------------------------------------------------------------------
 
 def _win(m):

@@ -303,3 +303,40 @@ def test_datetime_delegation_reference_vectors():
     # windows: the data is offset, the masks are merged from bit 0 (dispatch.rs:321-322)
     out, m = orc.apply_datetime(a, mask, 1, 2, b, None, 2, 2, orc.ADD)
     assert out.tolist() == [23, 0] and m.to_bools().tolist() == [True, False]
+
+
+def test_view_arm_restatements_on_reference_vectors():
+    """The oracle's table / view arms against the reference's own vectors (array_view.rs:170-411, table_view.rs:200-480,
+    super_array_view.rs:89-160, super_table_view.rs:256-570, table.rs:568-760, super_array.rs:674-719)."""
+    i = lambda *v: np.array(v, dtype=np.int32)
+    T = lambda *cols: ([i(*c) for c in cols], 0, len(cols[0]))
+    L = lambda res: [c.tolist() for c in res]
+    assert L(orc.broadcast_tableview_to_arrayview(orc.ADD, T((10, 20, 30), (100, 200, 300)), i(1, 2, 3), False)) == [[11, 22, 33], [101, 202, 303]]
+    assert L(orc.broadcast_tableview_to_arrayview(orc.MUL, T((10, 10, 10)), i(2, 3, 4), False)) == [[20, 30, 40]]
+    assert L(orc.broadcast_tableview_to_arrayview(orc.SUB, T((10, 20, 30), (100, 200, 300)), i(5, 5, 5), False)) == [[-5, -15, -25], [-95, -195, -295]]
+    stv = [T((10, 20, 30)), T((40, 50, 60))]
+    assert [L(t) for t in orc.broadcast_supertableview_to_arrayview(orc.ADD, stv, i(1, 2, 3, 4, 5, 6), False)] == [[[11, 22, 33]], [[44, 55, 66]]]
+    with pytest.raises(orc.KernelError, match="does not match"):
+        orc.broadcast_supertableview_to_arrayview(orc.ADD, stv, i(1, 2, 3, 4, 5), False)
+    assert L(orc.broadcast_tableview_to_tableview(orc.ADD, T((1, 2, 3), (10, 20, 30)), T((5, 5, 5), (100, 100, 100)))) == [[6, 7, 8], [110, 120, 130]]
+    with pytest.raises(orc.KernelError, match="column count mismatch"):
+        orc.broadcast_tableview_to_tableview(orc.ADD, T((1, 2, 3)), T((5, 5, 5), (10, 10, 10)))
+    assert L(orc.broadcast_tableview_to_arrayview(orc.SUB, T((100, 200, 300)), i(10, 20, 30))) == [[90, 180, 270]]
+    r = orc.broadcast_tableview_to_superarrayview(orc.MUL, T((1, 2, 3, 4, 5, 6)), [i(10, 20, 30), i(40, 50, 60)])
+    assert [L(t) for t in r] == [[[10, 40, 90]], [[160, 250, 360]]]
+    with pytest.raises(orc.KernelError, match="does not match"):
+        orc.broadcast_tableview_to_superarrayview(orc.ADD, T((1, 2, 3, 4, 5)), [i(10, 20, 30), i(40, 50, 60)])
+    assert [L(t) for t in orc.broadcast_tableview_to_superarrayview(orc.ADD, T((10, 20, 30)), [i(1, 2, 3)], False)] == [[[11, 22, 33]]]
+    with pytest.raises(orc.KernelError, match="does not match"):
+        orc.broadcast_tableview_to_superarrayview(orc.ADD, T((10, 20, 30, 40, 50)), [i(1, 2, 3)], False)
+    r = orc.broadcast_supertableview_to_arrayview(orc.MUL, [T((2, 3, 4)), T((5, 6, 7))], i(10, 10, 10, 10, 10, 10))
+    assert [L(t) for t in r] == [[[20, 30, 40]], [[50, 60, 70]]]
+    r = orc.broadcast_tableview_to_superarrayview(orc.SUB, T((10, 20, 30, 40, 50, 60)), [i(100, 200, 300), i(400, 500, 600)], False)
+    assert [L(t) for t in r] == [[[90, 180, 270]], [[360, 450, 540]]]
+    r = orc.broadcast_supertableview_to_arrayview(orc.DIV, [T((100, 200, 300)), T((400, 500, 600))], i(10, 20, 30, 40, 50, 60), True, False)
+    assert [L(t) for t in r] == [[[10, 10, 10]], [[10, 10, 10]]]
+    assert L(orc.broadcast_tableview_to_arrayview(orc.SUB, T((10, 20, 30), (100, 200, 300)), i(2, 3, 4))) == [[8, 17, 26], [98, 197, 296]]
+    assert L(orc.broadcast_table_to_superarray(orc.ADD, [i(2, 3, 4)], [i(10, 20, 30), i(40, 50, 60)])) == [[12, 23, 34], [42, 53, 64]]
+    assert L(orc.broadcast_table_to_superarray(orc.ADD, [i(10, 20, 30)], [i(1, 2, 3), i(4, 5, 6)], False)) == [[11, 22, 33], [14, 25, 36]]
+    with pytest.raises(orc.KernelError, match="single column"):
+        orc.broadcast_table_to_superarray(orc.ADD, [i(1, 2, 3), i(1, 2, 3)], [i(1, 2, 3)])
