@@ -347,6 +347,19 @@ inline Table broadcast_table_with_operator(ArithmeticOperator op, const Table& l
 inline Table broadcast_table_add(const Table& l, const Table& r, Context& ctx = Context::thread_default()) {
     return broadcast_table_with_operator(ArithmeticOperator::Add, l, r, ctx);
 }
+// broadcast_table_add(lhs, rhs, null_mask) (table.rs:69-128): column i + column i through broadcast_array_add =
+// resolve_binary_arithmetic(Add, l, r, null_mask) — the SAME optional mask for every column; the reference's BroadcastingError texts.
+inline Table broadcast_table_add(const Table& l, const Table& r, const Bitmask* null_mask, Context& ctx = Context::thread_default()) {
+    if (l.n_cols() != r.n_cols())
+        throw KernelError(MNR_ERR_SHAPE, "BroadcastingError", "Table column count mismatch: LHS " + std::to_string(l.n_cols()) + " cols, RHS " + std::to_string(r.n_cols()) + " cols");
+    if (l.n_rows() != r.n_rows())
+        throw KernelError(MNR_ERR_SHAPE, "BroadcastingError", "Table row count mismatch: LHS " + std::to_string(l.n_rows()) + " rows, RHS " + std::to_string(r.n_rows()) + " rows");
+    Table out;
+    out.name = l.name;
+    for (size_t i = 0; i < l.n_cols(); ++i)
+        out.cols.push_back(resolve_binary_arithmetic(ArithmeticOperator::Add, ArrayV(l.cols[i]), ArrayV(r.cols[i]), null_mask, ctx));
+    return out;
+}
 // table op array / array op table / table op scalar / scalar op table: operand order is significant.
 inline Table broadcast_table_to_array(ArithmeticOperator op, const Table& t, const Array& a, Context& ctx = Context::thread_default()) {
     Table out; out.name = t.name;
@@ -387,6 +400,21 @@ inline SuperTable broadcast_super_table_with_operator(ArithmeticOperator op, con
     std::vector<Table> out;
     for (size_t i = 0; i < l.n_batches(); ++i) out.push_back(broadcast_table_with_operator(op, *l.batches[i], *r.batches[i], ctx));
     return SuperTable::from_batches(std::move(out));
+}
+// broadcast_super_table_add (table.rs:135-176): chunk i + chunk i through broadcast_table_add with the same optional mask; the
+// result takes the first chunk's name, or "SuperTable".
+inline SuperTable broadcast_super_table_add(const SuperTable& l, const SuperTable& r, const Bitmask* null_mask = nullptr, Context& ctx = Context::thread_default()) {
+    if (l.n_batches() != r.n_batches())
+        throw KernelError(MNR_ERR_SHAPE, "BroadcastingError", "SuperTable chunk count mismatch: LHS " + std::to_string(l.n_batches()) + " chunks, RHS " + std::to_string(r.n_batches()) + " chunks");
+    std::vector<Table> out;
+    for (size_t i = 0; i < l.n_batches(); ++i) {
+        try {
+            out.push_back(broadcast_table_add(*l.batches[i], *r.batches[i], null_mask, ctx));
+        } catch (const KernelError& e) {
+            throw KernelError(MNR_ERR_SHAPE, "BroadcastingError", "Chunk " + std::to_string(i) + " addition failed: " + e.what());
+        }
+    }
+    return SuperTable::from_batches(std::move(out), (!l.batches.empty() && !l.batches[0]->name.empty()) ? l.batches[0]->name : std::string("SuperTable"));
 }
 template <class S> SuperTable broadcast_super_table_to_scalar(ArithmeticOperator op, const SuperTable& t, S scalar, Context& ctx = Context::thread_default()) {
     std::vector<Table> out;

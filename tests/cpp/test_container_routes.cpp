@@ -188,6 +188,20 @@ int main(int argc, char** argv) {
             CHECK(is<int32_t>(o.batches[0]->cols[0], {2, 3, 4}) && is<int32_t>(o.batches[1]->cols[0], {6, 7, 8}) && is<int32_t>(o.batches[2]->cols[0], {10, 11, 12}));
             o = broadcast_super_table_to_scalar<int32_t>(Op::Add, l3, 100);
             CHECK(is<int32_t>(o.batches[2]->cols[1], {170, 180, 190}));
+            {   // broadcast_super_table_add (table.rs:594-660) and the shared optional mask of broadcast_table_add (:98-101)
+                SuperTable a = SuperTable::from_batches({create_test_table("table1", {1, 2, 3}, {10, 20, 30}), create_test_table("table2", {4, 5, 6}, {40, 50, 60})});
+                SuperTable b = SuperTable::from_batches({create_test_table("table3", {7, 8, 9}, {70, 80, 90}), create_test_table("table4", {1, 1, 1}, {2, 2, 2})});
+                SuperTable s = broadcast_super_table_add(a, b);
+                CHECK(s.n_batches() == 2 && s.name == "table1");
+                CHECK(is<int32_t>(s.batches[0]->cols[0], {8, 10, 12}) && is<int32_t>(s.batches[0]->cols[1], {80, 100, 120}));
+                CHECK(is<int32_t>(s.batches[1]->cols[0], {5, 6, 7}) && is<int32_t>(s.batches[1]->cols[1], {42, 52, 62}));
+                std::string m2;
+                CHECK(error_kind([&] { broadcast_super_table_add(a, SuperTable::from_batches({create_test_table("t", {1, 2, 3}, {1, 2, 3})})); }, &m2) == "BroadcastingError" &&
+                      m2.find("chunk count mismatch: LHS 2 chunks, RHS 1 chunks") != std::string::npos);
+                Bitmask nm = Bitmask::from_bools({true, false, true});
+                Table t = broadcast_table_add(*a.batches[0], *b.batches[0], &nm);
+                CHECK(t.name == "table1" && is<int32_t>(t.cols[0], {8, 0, 12}) && is<int32_t>(t.cols[1], {80, 0, 120}));
+            }
             // Array (op) SuperTable and the mirror (broadcast/mod.rs:557-562, array.rs:236-252): every column of every batch
             o = broadcast_array_to_supertable(Op::Subtract, i32({100, 200, 300}), l3);
             CHECK(o.n_batches() == 3 && is<int32_t>(o.batches[0]->cols[0], {99, 198, 297}) && is<int32_t>(o.batches[2]->cols[1], {30, 120, 210}));
